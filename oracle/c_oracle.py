@@ -1,0 +1,95 @@
+"""ctypes binding of oracle/ctc_oracle.c (test infrastructure only).
+
+Builds ``liboracle_ctc.so`` with ``make`` on first use if it is missing.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle_ctc.so")
+    src = os.path.join(_HERE, "ctc_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle_ctc.so"],
+                              stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+    return _LIB
+
+
+def _p(a, t):
+    return a.ctypes.data_as(ctypes.POINTER(t)) if a is not None else None
+
+
+def num_threads():
+    return int(lib().oracle_num_threads())
+
+
+def ctc_loss_grad(logits, label_values, label_offsets, seq_len, blank=None, grad_loss=None,
+                  precision="f64", want_grad=True, num_threads=0):
+    """Returns (loss[B], grad[T,B,C] f32 or None, status[B])."""
+    logits = np.ascontiguousarray(logits, dtype=np.float32)
+    T, B, C = logits.shape
+    blank = C - 1 if blank is None else int(blank)
+    lv = np.ascontiguousarray(label_values, dtype=np.int32)
+    lo = np.ascontiguousarray(label_offsets, dtype=np.int32)
+    sl = np.ascontiguousarray(seq_len, dtype=np.int32)
+    real = np.float64 if precision == "f64" else np.float32
+    creal = ctypes.c_double if precision == "f64" else ctypes.c_float
+    loss = np.zeros(B, dtype=real)
+    grad = np.empty((T, B, C), dtype=np.float32) if want_grad else None
+    gl = None if grad_loss is None else np.ascontiguousarray(grad_loss, dtype=np.float32)
+    status = np.zeros(B, dtype=np.int32)
+    fn = getattr(lib(), "oracle_ctc_loss_grad_" + precision)
+    fn.restype = ctypes.c_int
+    fn(_p(logits, ctypes.c_float), T, B, C, _p(lv, ctypes.c_int32), _p(lo, ctypes.c_int32),
+       _p(sl, ctypes.c_int32), blank, _p(loss, creal), _p(grad, ctypes.c_float),
+       _p(gl, ctypes.c_float), _p(status, ctypes.c_int32), int(num_threads))
+    return loss, grad, status
+
+
+def greedy_decode(logits, seq_len, blank=None, merge_repeated=True, num_threads=0):
+    """Returns (hyp_values i64[M], hyp_offsets i32[B+1], neg_sum_logits f32[B])."""
+    logits = np.ascontiguousarray(logits, dtype=np.float32)
+    T, B, C = logits.shape
+    blank = C - 1 if blank is None else int(blank)
+    sl = np.ascontiguousarray(seq_len, dtype=np.int32)
+    hyp = np.zeros((B, max(T, 1)), dtype=np.int64)
+    hl = np.zeros(B, dtype=np.int32)
+    nsl = np.zeros(B, dtype=np.float32)
+    lib().oracle_greedy_decode(_p(logits, ctypes.c_float), T, B, C, _p(sl, ctypes.c_int32), blank,
+                               int(bool(merge_repeated)), _p(hyp, ctypes.c_int64),
+                               _p(hl, ctypes.c_int32), _p(nsl, ctypes.c_float), int(num_threads))
+    offs = np.zeros(B + 1, dtype=np.int32)
+    offs[1:] = np.cumsum(hl)
+    vals = (np.concatenate([hyp[b, :hl[b]] for b in range(B)]) if B else np.zeros(0, np.int64))
+    return vals.astype(np.int64), offs, nsl
+
+
+def edit_distance(hyp_values, hyp_offsets, truth_values, truth_offsets, normalize=True,
+                  num_threads=0):
+    hv = np.ascontiguousarray(hyp_values, dtype=np.int32)
+    ho = np.ascontiguousarray(hyp_offsets, dtype=np.int32)
+    tv = np.ascontiguousarray(truth_values, dtype=np.int32)
+    to = np.ascontiguousarray(truth_offsets, dtype=np.int32)
+    B = ho.size - 1
+    dist = np.zeros(B, dtype=np.int32)
+    ler = np.zeros(B, dtype=np.float32)
+    lib().oracle_edit_distance(_p(hv, ctypes.c_int32), _p(ho, ctypes.c_int32),
+                               _p(tv, ctypes.c_int32), _p(to, ctypes.c_int32), B,
+                               int(bool(normalize)), _p(dist, ctypes.c_int32),
+                               _p(ler, ctypes.c_float), int(num_threads))
+    return dist, ler
