@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — CTC loss+grad frames/sec on B200 (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3] [--impl ours|reference]
+
+ours       one rank per GPU (torchrun for N>1).  A step = one pass of the hot path (fused CTC
+           loss+grad launch, + the 4-scalar NCCL all-reduce when N>1) over one synthetic batch of
+           the workload shape that is already resident in HBM.  `value` = frames all ranks
+           processed / max-over-ranks device time.  `e2e` = the same metric through the HOST-buffer
+           C-ABI call (nasr_host_ctc_step): pinned H2D of logits/labels, kernel, D2H of grad/loss
+           inside the timed region.  `roofline` = algorithmic bytes / CUDA-event kernel time vs the
+           measured HBM peak.  `cpu_baseline` = the oracle's C port (TF's algorithm, float, all host
+           threads) timed on a bounded sample on rank 0.
+reference  the CPU arm: the reference's path is TensorFlow's CPU CTC kernel, not installable here, so
+           this times the oracle's C restatement of that algorithm on the host cores (kind "port").
+Weak scaling: every rank holds its own B-utterance batch (utterances are independent; the only
+exchange is the scalar all-reduce).
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {  # BASELINE.json configs; cfg3 is the one the metric is quoted on
+    "cfg1": dict(T=500, B=16, C=38, Lmax=100),
+    "cfg2": dict(T=800, B=64, C=38, Lmax=150),
+    "cfg3": dict(T=1000, B=256, C=38, Lmax=200),
+    "cfg4": dict(T=3000, B=32, C=38, Lmax=600),
+    "cfg5": dict(T=800, B=128, C=1024, Lmax=150),
+}
+METRIC = "ctc_loss_grad_frames_per_sec"
+UNIT = "frames/s"
+L2_BYTES = 126e6
+
+
+def synth(w, seed):
+    """SURVEY.md §8(d) throughput set: logits N(0,1)*3, labels uniform with 10% repeats,
+    L ~ U[Lmax/2, Lmax], seq_len = T for every utterance."""
+    rng = np.random.default_rng(seed)
+    T, B, C, Lmax = w["T"], w["B"], w["C"], w["Lmax"]
+    x = rng.standard_normal((T, B, C), dtype=np.float32) * np.float32(3.0)
+    L = rng.integers(Lmax // 2, Lmax + 1, size=B)
+    L[0] = Lmax
+    vals = rng.integers(0, C - 1, size=int(L.sum())).astype(np.int32)
+    rep = rng.random(vals.size) < 0.1
+    offs = np.zeros(B + 1, dtype=np.int32)
+    offs[1:] = np.cumsum(L)
+    starts = set(offs[:-1].tolist())
+    for i in np.nonzero(rep)[0]:
+        if i not in starts and i > 0:
+            vals[i] = vals[i - 1]
+    seq = np.full(B, T, dtype=np.int32)
+    return x, vals, offs, seq
+
+
+def algorithmic_bytes(w, seq, nlabels):
+    """4*C*(2*sum(seq_len) + T*B) + labels/seq_len/loss: logits read twice,
+    gradient written once."""
+    return 4 * w["C"] * (2 * int(seq.sum()) + w["T"] * w["B"]) + 4 * nlabels + 8 * w["B"]
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+
+    def sample(self):
+        if self._h is None:
+            return
+        nv = self._nv
+        try:
+            self.samples.append(int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+            r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+            names = {
+                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            }
+            for bit, name in names.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            self.sample()
+            self._stop_evt.wait(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.samples:
+            self.sample()
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_port_rate(w, x, vals, offs, seq, n_utt, reps, budget_s=20.0):
+    """frames/s of the oracle's C port (float, TF's algorithm, all host threads) on the first n_utt
+    utterances of the batch.  Returns (frames_per_s, threads, seconds_per_rep)."""
+    from oracle import c_oracle
+    n_utt = min(n_utt, w["B"])
+    xs = np.ascontiguousarray(x[:, :n_utt, :])
+    so = offs[: n_utt + 1].copy()
+    sv = vals[: so[-1]]
+    ss = seq[:n_utt]
+    best = None
+    t_start = time.perf_counter()
+    for _ in range(max(1, reps)):
+        t0 = time.perf_counter()
+        c_oracle.ctc_loss_grad(xs, sv, so, ss, precision="f32", want_grad=True)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    return float(ss.sum()) / best, c_oracle.num_threads(), best
+
+
+def run_reference(args, w, rank, world):
+    if rank != 0:
+        return
+    x, vals, offs, seq = synth(w, 1234)
+    n_utt = min(w["B"], 32)
+    from oracle import c_oracle
+    xs = np.ascontiguousarray(x[:, :n_utt, :])
+    so = offs[: n_utt + 1].copy()
+    sv = vals[: so[-1]]
+    ss = seq[:n_utt]
+    for _ in range(args.warmup):
+        c_oracle.ctc_loss_grad(xs, sv, so, ss, precision="f32")
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        c_oracle.ctc_loss_grad(xs, sv, so, ss, precision="f32")
+    dt = time.perf_counter() - t0
+    fps = float(ss.sum()) * args.steps / dt
+    cores = c_oracle.num_threads()
+    sample = "first %d of %d utterances per step (T=%d,C=%d), %d threads" % (n_utt, w["B"], w["T"], w["C"], cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "%s: B=%d,T=%d,C=%d,L<=%d" % (args.workload, w["B"], w["T"], w["C"], w["Lmax"]),
+                   "reference_kind": "C port of TensorFlow's CPU CTCLossCalculator (TF itself is not installable offline)"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_ours(args, w, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from neuralasr_b200 import _lib, host
+    from neuralasr_b200.networks import common
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    T, B, C = w["T"], w["B"], w["C"]
+    x, vals, offs, seq = synth(w, 1234 + rank)
+    lens = np.diff(offs)
+    rows = np.repeat(np.arange(B), lens)
+    cols = np.arange(offs[-1]) - np.repeat(offs[:-1], lens)
+    triple = (np.stack([rows, cols], 1).astype(np.int64), vals, np.asarray([B, int(lens.max())], np.int64))
+    lab = common.prepare_labels(triple, dev)
+    seq_d = torch.from_numpy(seq).to(dev)
+    # rotating input/gradient sets so that a step never finds its logits in L2 (126 MB)
+    set_bytes = 2 * x.nbytes
+    nsets = max(2, int(np.ceil(3 * L2_BYTES / set_bytes)))
+    x0 = torch.from_numpy(x).to(dev)
+    logits = [x0] + [x0.clone() for _ in range(nsets - 1)]
+    grads = [torch.empty_like(x0) for _ in range(nsets)]
+    gl = torch.full((B,), 1.0 / B, dtype=torch.float32, device=dev)
+    alg_bytes = algorithmic_bytes(w, seq, vals.size)
+
+    def step(i, ev=None):
+        k = i % nsets
+        if ev is not None:
+            ev[0].record()
+        loss_b, _, status = common.ctc_loss_and_grad(logits[k], lab, seq_d, grad_loss=gl, out_grad=grads[k])
+        if ev is not None:
+            ev[1].record()
+        sums = common.batch_sums(loss_b=loss_b)
+        if world > 1:
+            dist.all_reduce(sums)   # the path's one collective: 4 scalars
+        return sums
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = _lib.launch_count()
+    t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        sums = step(args.warmup + i, evs[i])
+    t_stop.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop()
+    ms_total = t_start.elapsed_time(t_stop)
+    kern_ms = [a.elapsed_time(b) for a, b in evs]
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    mean_loss = float(sums[0].item() / sums[3].item())
+    frames = float(seq.sum())
+    value = frames * world * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e through the HOST-buffer C-ABI call (pinned H2D + kernel + D2H per step) ----
+    ctx = host.HostContext(local_rank, T, B, C, w["Lmax"])
+    pin = ctx.pinned_logits[: x.size].reshape(T, B, C)
+    pin[...] = x
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        out = ctx.step(pin, vals, offs, seq, grad_loss=np.full(B, 1.0 / B, np.float32), want_decode=False)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out = ctx.step(pin, vals, offs, seq, grad_loss=np.full(B, 1.0 / B, np.float32), want_decode=False)
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    e2e_value = frames * world * e2e_steps / e2e_s
+    h2d = x.nbytes + vals.nbytes + offs.nbytes + seq.nbytes + 4 * B
+    d2h = x.nbytes + 4 * B + 4 * B
+    ctx.close()
+
+    # ---- decode + LER, reported beside the headline (not folded into it) ----
+    dec_ms = None
+    if rank == 0:
+        for _ in range(3):
+            d, _ = common.decoding(logits[0], seq_d)
+            common.edit_distance(d, lab)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(10):
+            d, _ = common.decoding(logits[i % nsets], seq_d)
+            common.edit_distance(d, lab)
+        b.record()
+        torch.cuda.synchronize()
+        dec_ms = a.elapsed_time(b) / 10
+
+    if rank == 0:
+        peak, peak_kind = hbm_peak()
+        k_ms = statistics.mean(kern_ms)
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload]["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        cpu = None
+        if world == 1 or True:
+            fps, cores, dt = cpu_port_rate(w, x, vals, offs, seq, n_utt=B, reps=5)
+            cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "whole %s batch (B=%d,T=%d), best of <=5 passes, %.3f s per pass" % (args.workload, B, T, dt)}
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: B=%d per GPU,T=%d,C=%d,L in [%d,%d],seq_len=T" % (args.workload, B, T, C, w["Lmax"] // 2, w["Lmax"]),
+                       "global_batch": B * world, "parallelism": "utterance-sharded dp%d" % world,
+                       "l2": "%d rotating logits/grad sets (%.0f MB) > 126 MB L2" % (nsets, nsets * set_bytes / 1e6),
+                       "mean_loss": mean_loss},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
+                         "kernel": "ctc_loss_grad_kernel", "kernel_ms": k_ms,
+                         "algorithmic_bytes_per_launch": alg_bytes},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "decode_ler_ms": dec_ms,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w, rank, world)
+    else:
+        run_ours(args, w, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

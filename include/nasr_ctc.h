@@ -1,0 +1,195 @@
+/*
+ * nasr_ctc.h — C-ABI of libnasr_ctc.so: the B200-native CTC training-loss / greedy-decode /
+ * label-error-rate path behind NeuralASR's loss(), decoding and label_error_rate.
+ *
+ * The reference has no FFI of its own on this path: its three helpers are Python methods that
+ * forward to TensorFlow 1.x CPU ops,
+ *     create_loss   networks/tfnetwork.py:58-59  tf.reduce_mean(tf.nn.ctc_loss(labels, logits, seq_len))
+ *     create_model  networks/tfnetwork.py:61-64  tf.nn.ctc_greedy_decoder(logits, seq_len) (line 63)
+ *     create_metric networks/tfnetwork.py:66-70  tf.reduce_mean(tf.edit_distance(cast(model), labels))
+ * so the entry points below are what a ctypes binding placed behind those three methods binds to
+ * (INTEGRATION.md shows the stub).  Each entry cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - every function returns an int status: NASR_OK or a NASR_ERR_* code; nasr_last_error() gives the
+ *     thread-local message of the last failure on the calling thread;
+ *   - all tensor pointers are DEVICE pointers unless the name says host; the caller owns every buffer
+ *     (outputs and workspace included); the library never allocates, frees or retains them, except
+ *     inside an explicit nasr_host_ctx (the HOST-buffer convenience path);
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = the legacy default stream)
+ *     and the call returns without synchronising, so it can be stream-captured into a CUDA graph;
+ *   - logits are float32, time-major [T, B, C], contiguous (what every model tail produces after its
+ *     transpose: networks/bilstm_ctc_net.py:48, lstm_ctc_net.py:43, deepspeech.py:126-127,
+ *     wavenet.py:171); blank is C-1 in the reference (preprocess_mfcc.py:81-92) and is passed
+ *     explicitly here;
+ *   - labels are CSR: label_values int32[N] (the `values` of the sparse triple utils.py:44-58 builds)
+ *     and label_offsets int32[B+1] (prefix sum of the rows of its `indices`);
+ *   - TF's InvalidArgument exceptions become per-utterance bit flags in status[B] (NASR_ST_*),
+ *     so a bad utterance does not abort the batch and no host sync is forced.
+ */
+#ifndef NASR_CTC_H_
+#define NASR_CTC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NASR_ABI_VERSION 1
+
+/* return codes */
+#define NASR_OK 0
+#define NASR_ERR_INVALID_ARGUMENT 1
+#define NASR_ERR_WORKSPACE_TOO_SMALL 2
+#define NASR_ERR_CUDA 3
+#define NASR_ERR_UNSUPPORTED 4
+
+/* per-utterance status bits (status[b]); 0 = OK.  TF raises InvalidArgumentError for the first three. */
+#define NASR_ST_LABEL_OUT_OF_RANGE 1   /* "Saw a non-null label (index >= num_classes - 1)..." */
+#define NASR_ST_SEQ_LEN_OUT_OF_RANGE 2 /* sequence_length(b) > max_time (or negative)          */
+#define NASR_ST_NOT_ENOUGH_TIME 4      /* "Not enough time for target transition sequence"     */
+#define NASR_ST_NO_VALID_PATH 8        /* log p = -inf: loss = +inf, gradient = softmax        */
+
+/* Minimal DLPack (v0.8 ABI) declarations so DLPack-capsule callers need no extra header.  Layout is
+ * identical to dlpack.h; include that header first if you have it. */
+#ifndef DLPACK_DLPACK_H_
+typedef enum { kDLCPU = 1, kDLCUDA = 2, kDLCUDAHost = 3 } DLDeviceType;
+typedef struct { int32_t device_type; int32_t device_id; } DLDevice;
+typedef struct { uint8_t code; uint8_t bits; uint16_t lanes; } DLDataType; /* code: 0 int, 1 uint, 2 float */
+typedef struct {
+  void* data;
+  DLDevice device;
+  int32_t ndim;
+  DLDataType dtype;
+  int64_t* shape;
+  int64_t* strides; /* NULL = compact row-major */
+  uint64_t byte_offset;
+} DLTensor;
+typedef struct DLManagedTensor {
+  DLTensor dl_tensor;
+  void* manager_ctx;
+  void (*deleter)(struct DLManagedTensor* self);
+} DLManagedTensor;
+#endif
+
+int nasr_abi_version(void);
+
+/* Message for the last non-OK return on this thread ("" if none). */
+const char* nasr_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * CTC loss + gradient.  Replaces tf.nn.ctc_loss + _CTCLossGrad behind create_loss
+ * (networks/tfnetwork.py:58-59) with the defaults that call uses: time-major, ctc_merge_repeated=True,
+ * preprocess_collapse_repeated=False, ignore_longer_outputs_than_inputs=False.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Bytes of device workspace nasr_ctc_loss_grad_f32 needs for these shapes
+ * (max_label_len = longest transcript in the batch; the extended state count is 2*max_label_len+1). */
+int nasr_ctc_workspace_bytes(int T, int B, int C, int max_label_len, size_t* out_bytes);
+
+/*
+ * loss[b]      = -log p(labels_b | softmax(logits[:seq_len[b], b, :]))          float32[B]
+ * grad[t,b,c]  = grad_loss[b] * (softmax(logits)[t,b,c] - occupancy[t,b,c])     float32[T,B,C]
+ *                exactly 0 for t >= seq_len[b]; grad may be NULL (loss only);
+ *                grad_loss may be NULL (= 1 for every b).  Under the reference's reduce_mean
+ *                (tfnetwork.py:59) the upstream gradient is 1/B.
+ * status[b]    = NASR_ST_* flags                                                int32[B]
+ * max_label_len must be >= every row length of the CSR labels (it sizes shared memory and workspace).
+ */
+int nasr_ctc_loss_grad_f32(const float* logits, int T, int B, int C,
+                           const int32_t* label_values, const int32_t* label_offsets,
+                           int max_label_len, const int32_t* seq_len, int blank,
+                           float* loss, float* grad, const float* grad_loss, int32_t* status,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same call with the tensors passed as DLPack tensors (the north-star "ctypes + DLPack buffers" form):
+ * device, dtype, rank and contiguity of every argument are validated here instead of in the caller.
+ * grad and grad_loss may be NULL. */
+int nasr_ctc_loss_grad_dl(const DLTensor* logits, const DLTensor* label_values,
+                          const DLTensor* label_offsets, int max_label_len, const DLTensor* seq_len,
+                          int blank, const DLTensor* loss, const DLTensor* grad,
+                          const DLTensor* grad_loss, const DLTensor* status,
+                          const DLTensor* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Greedy decode.  Replaces tf.nn.ctc_greedy_decoder(logits, seq_len, merge_repeated) — the `decoding`
+ * of the north star, networks/tfnetwork.py:63.
+ *   hyp            int64[B, T]  row b holds hyp_len[b] label ids (first-index argmax of the RAW logits
+ *                               per frame, blank dropped, repeats merged); the rest of the row is untouched
+ *   hyp_len        int32[B]
+ *   neg_sum_logits float32[B]   -(sum over frames of the max logit)   (TF's second output, [B,1])
+ * Frames t >= seq_len[b] are ignored; seq_len is clamped to [0, T].
+ * ---------------------------------------------------------------------------------------------- */
+int nasr_ctc_greedy_decode_i64(const float* logits, int T, int B, int C, const int32_t* seq_len,
+                               int blank, int merge_repeated, int64_t* hyp, int32_t* hyp_len,
+                               float* neg_sum_logits, void* stream);
+
+/* Dense hypotheses -> the SparseTensor triple TF returns as decoded[0] (tfnetwork.py:64):
+ * hyp_offsets int32[B+1] must hold the exclusive prefix sum of hyp_len (M = hyp_offsets[B]);
+ * indices int64[M,2] row-major (b, position), values int64[M], dense_shape int64[2] = [B, max len]. */
+int nasr_hyp_to_sparse_i64(const int64_t* hyp, int hyp_stride, const int32_t* hyp_offsets, int B,
+                           int64_t* indices, int64_t* values, int64_t* dense_shape, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Label error rate.  Replaces tf.edit_distance(tf.cast(model, tf.int32), labels, normalize) behind
+ * create_metric (networks/tfnetwork.py:66-70).  Hypotheses are the dense rows greedy decode wrote
+ * (row stride hyp_stride elements); truth is CSR.
+ *   dist[b] = Levenshtein(truth_b, hyp_b)                       int32[B]   (bit-exact integers)
+ *   ler[b]  = dist / |truth_b| if normalize else dist           float32[B]
+ *             (|truth_b| = 0: +inf if dist != 0 else 0)
+ * max_truth_len >= every truth row length (sizes shared memory).
+ * ---------------------------------------------------------------------------------------------- */
+int nasr_edit_distance_i64(const int64_t* hyp, int hyp_stride, const int32_t* hyp_len,
+                           const int32_t* truth_values, const int32_t* truth_offsets,
+                           int max_truth_len, int B, int normalize, int32_t* dist, float* ler,
+                           void* stream);
+
+/* Same, hypotheses given as CSR int64 values + int32 offsets (a decoded SparseTensor's values and the
+ * prefix sum of its row counts); max_hyp_len >= every hypothesis row length. */
+int nasr_edit_distance_csr_i64(const int64_t* hyp_values, const int32_t* hyp_offsets,
+                               int max_hyp_len, const int32_t* truth_values, const int32_t* truth_offsets,
+                               int max_truth_len, int B, int normalize, int32_t* dist, float* ler,
+                               void* stream);
+
+/* Batch reductions the reference wraps around the ops (tf.reduce_mean, tfnetwork.py:59,69) and the
+ * tower means of tfnetwork.py:135-136: sums[0] = sum loss, sums[1] = sum ler, sums[2] = sum dist,
+ * sums[3] = B, as float64[4] on the device (the 4-element vector each rank all-reduces). loss/ler/dist
+ * may be NULL (that slot is 0). Deterministic (single-block tree in fixed order). */
+int nasr_batch_sums_f64(const float* loss, const float* ler, const int32_t* dist, int B,
+                        double* sums, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * HOST-buffer path: what a caller that holds numpy arrays (the reference's feed_dict world,
+ * tfnetwork.py:183-190) uses.  The context owns device buffers, pinned staging and one stream, sized
+ * for the maxima given at creation.  One call = H2D of logits/labels/seq_len, loss+grad, greedy decode,
+ * edit distance, D2H of the results, and a stream synchronise.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct nasr_host_ctx nasr_host_ctx;
+
+int nasr_host_ctx_create(int device, int max_T, int max_B, int max_C, int max_label_len,
+                         nasr_host_ctx** out);
+void nasr_host_ctx_destroy(nasr_host_ctx* ctx);
+/* Pinned host staging the caller may fill directly to skip one host copy: logits float[max_T*max_B*max_C],
+ * grad float[same]. */
+float* nasr_host_ctx_pinned_logits(nasr_host_ctx* ctx);
+float* nasr_host_ctx_pinned_grad(nasr_host_ctx* ctx);
+
+/* All pointers are HOST pointers. logits/grad may be the ctx's pinned buffers (then no extra host copy is
+ * made). grad, hyp, hyp_len, neg_sum_logits, dist, ler may each be NULL to skip that output
+ * (decode runs only if hyp_len/dist/ler is wanted). */
+int nasr_host_ctc_step(nasr_host_ctx* ctx, const float* logits, int T, int B, int C,
+                       const int32_t* label_values, const int32_t* label_offsets,
+                       const int32_t* seq_len, int blank, const float* grad_loss,
+                       float* loss, float* grad, int32_t* status,
+                       int64_t* hyp /*[B,T]*/, int32_t* hyp_len, float* neg_sum_logits,
+                       int32_t* dist, float* ler);
+
+/* Number of kernel launches this library has enqueued since load (for bench.py's gpu_launches). */
+uint64_t nasr_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NASR_CTC_H_ */

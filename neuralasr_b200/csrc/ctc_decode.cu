@@ -1,0 +1,304 @@
+// Greedy CTC decode, Levenshtein label error rate and the small batch reductions, for sm_100a.
+//
+// Replaces tf.nn.ctc_greedy_decoder (reference networks/tfnetwork.py:63) and
+// tf.edit_distance(tf.cast(model, tf.int32), labels) + reduce_mean (networks/tfnetwork.py:66-70);
+// semantics per SURVEY.md Appendix A.2 / A.3.  Integer results are bit-exact by construction
+// (first-index argmax on the raw logits, exact integer DP); neg_sum_logits is accumulated in frame
+// order in fp32 like TF's scalar loop, so it is bit-exact too.
+#include "nasr_common.cuh"
+
+namespace nasr {
+namespace {
+
+constexpr int kDecodeThreads = 256;
+constexpr int kDecodeChunk = 2048;  // frames staged per pass (argmax ids + max logits in shared memory)
+
+// One CTA per utterance.  Phase 1: one warp per frame finds the first-index argmax of the raw logits
+// (coalesced row read).  Phase 2: warp 0 collapses (drop blank, merge repeats) with ballot compaction
+// while lane 0 of warp 1 accumulates -max in frame order.
+__global__ void __launch_bounds__(kDecodeThreads)
+greedy_decode_kernel(const float* __restrict__ logits, int T, int B, int C,
+                     const int32_t* __restrict__ seq_len, int blank, int merge_repeated,
+                     int64_t* __restrict__ hyp, int32_t* __restrict__ hyp_len,
+                     float* __restrict__ neg_sum_logits) {
+  __shared__ int s_id[kDecodeChunk];
+  __shared__ float s_mx[kDecodeChunk];
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  int Tb = seq_len[b];
+  Tb = max(0, min(T, Tb));
+  int count = 0;       // warp 0: symbols emitted so far
+  int carry_prev = -1; // warp 0: id of the previous frame
+  float acc = 0.f;     // warp 1 lane 0
+  for (int base = 0; base < Tb; base += kDecodeChunk) {
+    const int n = min(kDecodeChunk, Tb - base);
+    for (int i = warp; i < n; i += nw) {
+      const float* x = logits + ((size_t)(base + i) * B + b) * C;
+      float m = -INFINITY;
+      int am = 0x7fffffff;
+      for (int c = lane; c < C; c += 32) {
+        const float v = __ldg(x + c);
+        if (am == 0x7fffffff || v > m) {  // strict '>' keeps the earliest index within a lane
+          m = v;
+          am = c;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+        if (om > m || (om == m && oa < am)) {
+          m = om;
+          am = oa;
+        }
+      }
+      if (lane == 0) {
+        s_id[i] = am;
+        s_mx[i] = m;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int g = 0; g < n; g += 32) {
+        const int i = g + lane;
+        const bool valid = i < n;
+        const int id = valid ? s_id[i] : -1;
+        int prev = __shfl_up_sync(0xffffffffu, id, 1);
+        if (lane == 0) prev = carry_prev;
+        const bool emit = valid && id != blank && !(merge_repeated && id == prev);
+        const unsigned mask = __ballot_sync(0xffffffffu, emit);
+        if (emit) hyp[(size_t)b * T + count + __popc(mask & ((1u << lane) - 1))] = (int64_t)id;
+        count += __popc(mask);
+        const int last = min(31, n - g - 1);
+        carry_prev = __shfl_sync(0xffffffffu, id, last);
+      }
+    } else if (warp == 1 && lane == 0) {
+      for (int i = 0; i < n; i++) acc -= s_mx[i];
+    }
+    __syncthreads();
+  }
+  if (warp == 0 && lane == 0) hyp_len[b] = count;
+  if (warp == 1 && lane == 0 && neg_sum_logits) neg_sum_logits[b] = acc;
+}
+
+// One warp per utterance, anti-diagonal wavefront over the (truth x hyp) lattice; three diagonals and
+// both symbol strings live in shared memory.  dist = D[n][m], exact integers.
+template <typename HypT>
+__global__ void __launch_bounds__(32)
+edit_distance_kernel(const HypT* __restrict__ hyp, long hyp_stride, const int32_t* __restrict__ hyp_len,
+                     const int32_t* __restrict__ hyp_offsets,
+                     const int32_t* __restrict__ truth_values, const int32_t* __restrict__ truth_offsets,
+                     int max_truth_len, int max_hyp_len, int normalize, int32_t* __restrict__ dist,
+                     float* __restrict__ ler) {
+  extern __shared__ int sm[];
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int t0 = truth_offsets[b];
+  const int m = truth_offsets[b + 1] - t0;  // truth length
+  int n;                                     // hyp length
+  const HypT* h;
+  if (hyp_offsets) {
+    h = hyp + hyp_offsets[b];
+    n = hyp_offsets[b + 1] - hyp_offsets[b];
+  } else {
+    h = hyp + (size_t)b * hyp_stride;
+    n = hyp_len[b];
+  }
+  int d = 0;
+  if (m > max_truth_len || n > max_hyp_len) {
+    d = -1;  // caller's maxima were wrong: refuse rather than overrun shared memory
+  } else if (n == 0 || m == 0) {
+    d = n + m;
+  } else {
+    int* tr = sm;                       // [max_truth_len]
+    int* hy = tr + max_truth_len;       // [max_hyp_len]
+    int* d0 = hy + max_hyp_len;         // three diagonals, indexed by truth position j in [0, m]
+    int* d1 = d0 + max_truth_len + 1;
+    int* d2 = d1 + max_truth_len + 1;
+    for (int j = lane; j < m; j += 32) tr[j] = truth_values[t0 + j];
+    for (int i = lane; i < n; i += 32) hy[i] = (int)h[i];  // the reference casts int64 -> int32 first
+    __syncwarp();
+    // diagonal k holds cells (i, j) with i + j = k, i over hyp [0,n], j over truth [0,m]
+    int* pp = d0;  // diagonal k-2
+    int* pv = d1;  // diagonal k-1
+    int* cu = d2;  // diagonal k
+    for (int k = 0; k <= n + m; k++) {
+      const int jlo = max(0, k - n), jhi = min(m, k);
+      for (int j = jlo + lane; j <= jhi; j += 32) {
+        const int i = k - j;
+        int v;
+        if (i == 0) {
+          v = j;
+        } else if (j == 0) {
+          v = i;
+        } else {
+          v = min(min(pv[j] + 1, pv[j - 1] + 1), pp[j - 1] + (hy[i - 1] != tr[j - 1]));
+        }
+        cu[j] = v;
+      }
+      __syncwarp();
+      int* tmp = pp;
+      pp = pv;
+      pv = cu;
+      cu = tmp;
+    }
+    d = pv[m];
+  }
+  if (lane == 0) {
+    dist[b] = d;
+    float r;
+    if (!normalize) {
+      r = (float)d;
+    } else if (m == 0) {
+      r = d ? INFINITY : 0.f;
+    } else {
+      r = (float)d / (float)m;
+    }
+    ler[b] = r;
+  }
+}
+
+__global__ void hyp_to_sparse_kernel(const int64_t* __restrict__ hyp, long hyp_stride,
+                                     const int32_t* __restrict__ offs, int B,
+                                     int64_t* __restrict__ indices, int64_t* __restrict__ values) {
+  const int b = blockIdx.x;
+  const int o = offs[b], n = offs[b + 1] - o;
+  for (int p = threadIdx.x; p < n; p += blockDim.x) {
+    indices[2 * (size_t)(o + p)] = b;
+    indices[2 * (size_t)(o + p) + 1] = p;
+    values[o + p] = hyp[(size_t)b * hyp_stride + p];
+  }
+}
+
+__global__ void dense_shape_kernel(const int32_t* __restrict__ offs, int B, int64_t* __restrict__ shape) {
+  __shared__ int red[32];
+  int mx = 0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) mx = max(mx, offs[b + 1] - offs[b]);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    mx = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0;
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (threadIdx.x == 0) {
+      shape[0] = B;
+      shape[1] = mx;
+    }
+  }
+}
+
+// Fixed-order reduction (thread-strided partials, then a shared-memory tree): deterministic.
+__global__ void __launch_bounds__(256)
+batch_sums_kernel(const float* __restrict__ loss, const float* __restrict__ ler,
+                  const int32_t* __restrict__ dist, int B, double* __restrict__ sums) {
+  __shared__ double s[3][256];
+  double a = 0, c = 0, d = 0;
+  for (int b = threadIdx.x; b < B; b += 256) {
+    if (loss) a += (double)loss[b];
+    if (ler) c += (double)ler[b];
+    if (dist) d += (double)dist[b];
+  }
+  s[0][threadIdx.x] = a;
+  s[1][threadIdx.x] = c;
+  s[2][threadIdx.x] = d;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s[0][threadIdx.x] += s[0][threadIdx.x + o];
+      s[1][threadIdx.x] += s[1][threadIdx.x + o];
+      s[2][threadIdx.x] += s[2][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    sums[0] = s[0][0];
+    sums[1] = s[1][0];
+    sums[2] = s[2][0];
+    sums[3] = (double)B;
+  }
+}
+
+template <typename HypT>
+int launch_edit_distance(const HypT* hyp, long hyp_stride, const int32_t* hyp_len,
+                         const int32_t* hyp_offsets, const int32_t* truth_values,
+                         const int32_t* truth_offsets, int max_truth_len, int max_hyp_len, int B,
+                         int normalize, int32_t* dist, float* ler, cudaStream_t stream) {
+  const size_t smem = sizeof(int) * ((size_t)max_truth_len + max_hyp_len + 3 * ((size_t)max_truth_len + 1));
+  if (smem > 200 * 1024) {
+    set_error("nasr_edit_distance: max_truth_len=%d max_hyp_len=%d exceed shared memory", max_truth_len,
+              max_hyp_len);
+    return NASR_ERR_UNSUPPORTED;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    NASR_CUDA(cudaFuncSetAttribute(edit_distance_kernel<HypT>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  edit_distance_kernel<HypT><<<B, 32, smem, stream>>>(hyp, hyp_stride, hyp_len, hyp_offsets,
+                                                     truth_values, truth_offsets, max_truth_len,
+                                                     max_hyp_len, normalize, dist, ler);
+  count_launch();
+  NASR_CUDA(cudaGetLastError());
+  return NASR_OK;
+}
+
+}  // namespace
+
+int greedy_decode(const float* logits, int T, int B, int C, const int32_t* seq_len, int blank,
+                  int merge_repeated, int64_t* hyp, int32_t* hyp_len, float* neg_sum_logits,
+                  cudaStream_t stream) {
+  NASR_CHECK_ARG(T >= 0 && B >= 0 && C >= 1, "nasr_ctc_greedy_decode: bad shape T=%d B=%d C=%d", T, B, C);
+  if (B == 0) return NASR_OK;
+  NASR_CHECK_ARG((logits || T == 0) && seq_len && hyp_len && (hyp || T == 0),
+                 "nasr_ctc_greedy_decode: NULL argument");
+  greedy_decode_kernel<<<B, kDecodeThreads, 0, stream>>>(logits, T, B, C, seq_len, blank,
+                                                        merge_repeated, hyp, hyp_len, neg_sum_logits);
+  count_launch();
+  NASR_CUDA(cudaGetLastError());
+  return NASR_OK;
+}
+
+int edit_distance_dense(const int64_t* hyp, int hyp_stride, const int32_t* hyp_len,
+                        const int32_t* truth_values, const int32_t* truth_offsets, int max_truth_len,
+                        int B, int normalize, int32_t* dist, float* ler, cudaStream_t stream) {
+  NASR_CHECK_ARG(B >= 0 && hyp_stride >= 0 && max_truth_len >= 0, "nasr_edit_distance: bad sizes");
+  if (B == 0) return NASR_OK;
+  NASR_CHECK_ARG(hyp_len && truth_offsets && dist && ler, "nasr_edit_distance: NULL argument");
+  return launch_edit_distance<int64_t>(hyp, hyp_stride, hyp_len, nullptr, truth_values, truth_offsets,
+                                       max_truth_len, hyp_stride, B, normalize, dist, ler, stream);
+}
+
+int edit_distance_csr(const int64_t* hyp_values, const int32_t* hyp_offsets, int max_hyp_len,
+                      const int32_t* truth_values, const int32_t* truth_offsets, int max_truth_len,
+                      int B, int normalize, int32_t* dist, float* ler, cudaStream_t stream) {
+  NASR_CHECK_ARG(B >= 0 && max_truth_len >= 0 && max_hyp_len >= 0, "nasr_edit_distance_csr: bad sizes");
+  if (B == 0) return NASR_OK;
+  NASR_CHECK_ARG(hyp_offsets && truth_offsets && dist && ler, "nasr_edit_distance_csr: NULL argument");
+  return launch_edit_distance<int64_t>(hyp_values, 0, nullptr, hyp_offsets, truth_values, truth_offsets,
+                                       max_truth_len, max_hyp_len, B, normalize, dist, ler, stream);
+}
+
+int hyp_to_sparse(const int64_t* hyp, int hyp_stride, const int32_t* hyp_offsets, int B,
+                  int64_t* indices, int64_t* values, int64_t* dense_shape, cudaStream_t stream) {
+  NASR_CHECK_ARG(B >= 0, "nasr_hyp_to_sparse: bad B");
+  NASR_CHECK_ARG(hyp_offsets && dense_shape, "nasr_hyp_to_sparse: NULL argument");
+  if (B > 0 && indices && values) {
+    hyp_to_sparse_kernel<<<B, 128, 0, stream>>>(hyp, hyp_stride, hyp_offsets, B, indices, values);
+    count_launch();
+  }
+  dense_shape_kernel<<<1, 256, 0, stream>>>(hyp_offsets, B, dense_shape);
+  count_launch();
+  NASR_CUDA(cudaGetLastError());
+  return NASR_OK;
+}
+
+int batch_sums(const float* loss, const float* ler, const int32_t* dist, int B, double* sums,
+               cudaStream_t stream) {
+  NASR_CHECK_ARG(B >= 0 && sums, "nasr_batch_sums: bad argument");
+  batch_sums_kernel<<<1, 256, 0, stream>>>(loss, ler, dist, B, sums);
+  count_launch();
+  NASR_CUDA(cudaGetLastError());
+  return NASR_OK;
+}
+
+}  // namespace nasr

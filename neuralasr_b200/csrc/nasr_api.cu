@@ -1,0 +1,382 @@
+// extern "C" surface of libnasr_ctc.so (declared in include/nasr_ctc.h): argument checking,
+// DLPack unwrapping, the HOST-buffer context, and dispatch into the kernels of ctc_loss.cu /
+// ctc_decode.cu.  No torch types cross this boundary.
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+
+#include "nasr_common.cuh"
+
+namespace nasr {
+
+static thread_local char t_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+}
+
+// implemented in ctc_loss.cu / ctc_decode.cu
+int ctc_workspace_bytes(int T, int B, int C, int Lmax, size_t* out);
+int ctc_loss_grad(const float* logits, int T, int B, int C, const int32_t* label_values,
+                  const int32_t* label_offsets, int Lmax, const int32_t* seq_len, int blank,
+                  float* loss, float* grad, const float* grad_loss, int32_t* status, void* workspace,
+                  size_t workspace_bytes, cudaStream_t stream);
+int greedy_decode(const float* logits, int T, int B, int C, const int32_t* seq_len, int blank,
+                  int merge_repeated, int64_t* hyp, int32_t* hyp_len, float* neg_sum_logits,
+                  cudaStream_t stream);
+int edit_distance_dense(const int64_t* hyp, int hyp_stride, const int32_t* hyp_len,
+                        const int32_t* truth_values, const int32_t* truth_offsets, int max_truth_len,
+                        int B, int normalize, int32_t* dist, float* ler, cudaStream_t stream);
+int edit_distance_csr(const int64_t* hyp_values, const int32_t* hyp_offsets, int max_hyp_len,
+                      const int32_t* truth_values, const int32_t* truth_offsets, int max_truth_len,
+                      int B, int normalize, int32_t* dist, float* ler, cudaStream_t stream);
+int hyp_to_sparse(const int64_t* hyp, int hyp_stride, const int32_t* hyp_offsets, int B,
+                  int64_t* indices, int64_t* values, int64_t* dense_shape, cudaStream_t stream);
+int batch_sums(const float* loss, const float* ler, const int32_t* dist, int B, double* sums,
+               cudaStream_t stream);
+
+namespace {
+
+// DLPack validation: CUDA device, expected dtype, expected rank, compact row-major.
+bool dl_ok(const DLTensor* t, const char* name, int code, int bits, int ndim, int device_id) {
+  if (!t) {
+    set_error("%s: NULL DLTensor", name);
+    return false;
+  }
+  if (t->device.device_type != kDLCUDA) {
+    set_error("%s: not a CUDA tensor (device_type=%d)", name, (int)t->device.device_type);
+    return false;
+  }
+  if (device_id >= 0 && t->device.device_id != device_id) {
+    set_error("%s: on cuda:%d, expected cuda:%d", name, t->device.device_id, device_id);
+    return false;
+  }
+  if (t->dtype.code != code || t->dtype.bits != bits || t->dtype.lanes != 1) {
+    set_error("%s: dtype (code=%d,bits=%d) but expected (code=%d,bits=%d)", name, t->dtype.code,
+              t->dtype.bits, code, bits);
+    return false;
+  }
+  if (ndim >= 0 && t->ndim != ndim) {
+    set_error("%s: rank %d, expected %d", name, t->ndim, ndim);
+    return false;
+  }
+  if (t->strides) {
+    int64_t expect = 1;
+    for (int i = t->ndim - 1; i >= 0; i--) {
+      if (t->shape[i] != 1 && t->strides[i] != expect) {
+        set_error("%s: not contiguous (stride[%d]=%lld, expected %lld)", name, i,
+                  (long long)t->strides[i], (long long)expect);
+        return false;
+      }
+      expect *= t->shape[i];
+    }
+  }
+  return true;
+}
+
+template <typename T>
+T* dl_ptr(const DLTensor* t) {
+  return reinterpret_cast<T*>(static_cast<char*>(t->data) + t->byte_offset);
+}
+
+int64_t dl_numel(const DLTensor* t) {
+  int64_t n = 1;
+  for (int i = 0; i < t->ndim; i++) n *= t->shape[i];
+  return n;
+}
+
+}  // namespace
+}  // namespace nasr
+
+using namespace nasr;
+
+struct nasr_host_ctx {
+  int device;
+  int max_T, max_B, max_C, max_L;
+  cudaStream_t stream;
+  // device
+  float *d_logits, *d_grad, *d_loss, *d_grad_loss, *d_nsl, *d_ler;
+  int32_t *d_lab_vals, *d_lab_offs, *d_seq, *d_status, *d_hyp_len, *d_dist;
+  int64_t* d_hyp;
+  void* d_ws;
+  size_t ws_bytes;
+  // pinned host
+  float *h_logits, *h_grad;
+  char* h_small;  // labels, offsets, seq_len, grad_loss in; loss, status, hyp_len, nsl, dist, ler out
+  int64_t* h_hyp;
+  size_t small_bytes;
+};
+
+extern "C" {
+
+int nasr_abi_version(void) { return NASR_ABI_VERSION; }
+
+const char* nasr_last_error(void) { return t_err; }
+
+uint64_t nasr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int nasr_ctc_workspace_bytes(int T, int B, int C, int max_label_len, size_t* out_bytes) {
+  NASR_CHECK_ARG(out_bytes, "nasr_ctc_workspace_bytes: out_bytes is NULL");
+  NASR_CHECK_ARG(T >= 0 && B >= 0 && C >= 1 && max_label_len >= 0,
+                 "nasr_ctc_workspace_bytes: bad shape T=%d B=%d C=%d L=%d", T, B, C, max_label_len);
+  return ctc_workspace_bytes(T, B, C, max_label_len, out_bytes);
+}
+
+int nasr_ctc_loss_grad_f32(const float* logits, int T, int B, int C, const int32_t* label_values,
+                           const int32_t* label_offsets, int max_label_len, const int32_t* seq_len,
+                           int blank, float* loss, float* grad, const float* grad_loss,
+                           int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+  return ctc_loss_grad(logits, T, B, C, label_values, label_offsets, max_label_len, seq_len, blank,
+                       loss, grad, grad_loss, status, workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int nasr_ctc_loss_grad_dl(const DLTensor* logits, const DLTensor* label_values,
+                          const DLTensor* label_offsets, int max_label_len, const DLTensor* seq_len,
+                          int blank, const DLTensor* loss, const DLTensor* grad,
+                          const DLTensor* grad_loss, const DLTensor* status,
+                          const DLTensor* workspace, void* stream) {
+  if (!dl_ok(logits, "logits", 2, 32, 3, -1)) return NASR_ERR_INVALID_ARGUMENT;
+  const int dev = logits->device.device_id;
+  const int64_t T = logits->shape[0], B = logits->shape[1], C = logits->shape[2];
+  NASR_CHECK_ARG(T < (1 << 30) && B < (1 << 30) && C < (1 << 30), "logits: dimension too large");
+  if (!dl_ok(label_values, "label_values", 0, 32, 1, dev)) return NASR_ERR_INVALID_ARGUMENT;
+  if (!dl_ok(label_offsets, "label_offsets", 0, 32, 1, dev)) return NASR_ERR_INVALID_ARGUMENT;
+  if (!dl_ok(seq_len, "seq_len", 0, 32, 1, dev)) return NASR_ERR_INVALID_ARGUMENT;
+  if (!dl_ok(loss, "loss", 2, 32, 1, dev)) return NASR_ERR_INVALID_ARGUMENT;
+  if (!dl_ok(status, "status", 0, 32, 1, dev)) return NASR_ERR_INVALID_ARGUMENT;
+  if (!dl_ok(workspace, "workspace", 1, 8, 1, dev)) return NASR_ERR_INVALID_ARGUMENT;
+  NASR_CHECK_ARG(label_offsets->shape[0] == B + 1, "label_offsets: length %lld, expected B+1=%lld",
+                 (long long)label_offsets->shape[0], (long long)(B + 1));
+  NASR_CHECK_ARG(seq_len->shape[0] == B, "seq_len: length %lld, expected B=%lld",
+                 (long long)seq_len->shape[0], (long long)B);
+  NASR_CHECK_ARG(loss->shape[0] == B && status->shape[0] == B, "loss/status: length must be B=%lld",
+                 (long long)B);
+  float* g = nullptr;
+  if (grad) {
+    if (!dl_ok(grad, "grad", 2, 32, 3, dev)) return NASR_ERR_INVALID_ARGUMENT;
+    NASR_CHECK_ARG(grad->shape[0] == T && grad->shape[1] == B && grad->shape[2] == C,
+                   "grad: shape differs from logits");
+    g = dl_ptr<float>(grad);
+  }
+  const float* gl = nullptr;
+  if (grad_loss) {
+    if (!dl_ok(grad_loss, "grad_loss", 2, 32, 1, dev)) return NASR_ERR_INVALID_ARGUMENT;
+    NASR_CHECK_ARG(grad_loss->shape[0] == B, "grad_loss: length must be B");
+    gl = dl_ptr<const float>(grad_loss);
+  }
+  return ctc_loss_grad(dl_ptr<const float>(logits), (int)T, (int)B, (int)C,
+                       dl_ptr<const int32_t>(label_values), dl_ptr<const int32_t>(label_offsets),
+                       max_label_len, dl_ptr<const int32_t>(seq_len), blank, dl_ptr<float>(loss), g, gl,
+                       dl_ptr<int32_t>(status), dl_ptr<void>(workspace), (size_t)dl_numel(workspace),
+                       static_cast<cudaStream_t>(stream));
+}
+
+int nasr_ctc_greedy_decode_i64(const float* logits, int T, int B, int C, const int32_t* seq_len,
+                               int blank, int merge_repeated, int64_t* hyp, int32_t* hyp_len,
+                               float* neg_sum_logits, void* stream) {
+  return greedy_decode(logits, T, B, C, seq_len, blank, merge_repeated, hyp, hyp_len, neg_sum_logits,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int nasr_hyp_to_sparse_i64(const int64_t* hyp, int hyp_stride, const int32_t* hyp_offsets, int B,
+                           int64_t* indices, int64_t* values, int64_t* dense_shape, void* stream) {
+  return hyp_to_sparse(hyp, hyp_stride, hyp_offsets, B, indices, values, dense_shape,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int nasr_edit_distance_i64(const int64_t* hyp, int hyp_stride, const int32_t* hyp_len,
+                           const int32_t* truth_values, const int32_t* truth_offsets,
+                           int max_truth_len, int B, int normalize, int32_t* dist, float* ler,
+                           void* stream) {
+  return edit_distance_dense(hyp, hyp_stride, hyp_len, truth_values, truth_offsets, max_truth_len, B,
+                             normalize, dist, ler, static_cast<cudaStream_t>(stream));
+}
+
+int nasr_edit_distance_csr_i64(const int64_t* hyp_values, const int32_t* hyp_offsets, int max_hyp_len,
+                               const int32_t* truth_values, const int32_t* truth_offsets,
+                               int max_truth_len, int B, int normalize, int32_t* dist, float* ler,
+                               void* stream) {
+  return edit_distance_csr(hyp_values, hyp_offsets, max_hyp_len, truth_values, truth_offsets,
+                           max_truth_len, B, normalize, dist, ler, static_cast<cudaStream_t>(stream));
+}
+
+int nasr_batch_sums_f64(const float* loss, const float* ler, const int32_t* dist, int B,
+                        double* sums, void* stream) {
+  return batch_sums(loss, ler, dist, B, sums, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// HOST-buffer context
+// ------------------------------------------------------------------------------------------------
+static size_t small_layout(int B, int N, size_t* o_vals, size_t* o_offs, size_t* o_seq, size_t* o_gl,
+                           size_t* o_loss, size_t* o_status, size_t* o_hl, size_t* o_nsl,
+                           size_t* o_dist, size_t* o_ler) {
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t r = o;
+    o = (o + bytes + 63) & ~(size_t)63;
+    return r;
+  };
+  *o_vals = take(sizeof(int32_t) * (size_t)(N + 1));
+  *o_offs = take(sizeof(int32_t) * (size_t)(B + 1));
+  *o_seq = take(sizeof(int32_t) * (size_t)B);
+  *o_gl = take(sizeof(float) * (size_t)B);
+  *o_loss = take(sizeof(float) * (size_t)B);
+  *o_status = take(sizeof(int32_t) * (size_t)B);
+  *o_hl = take(sizeof(int32_t) * (size_t)B);
+  *o_nsl = take(sizeof(float) * (size_t)B);
+  *o_dist = take(sizeof(int32_t) * (size_t)B);
+  *o_ler = take(sizeof(float) * (size_t)B);
+  return o;
+}
+
+void nasr_host_ctx_destroy(nasr_host_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_logits); cudaFree(c->d_grad); cudaFree(c->d_loss); cudaFree(c->d_grad_loss);
+  cudaFree(c->d_nsl); cudaFree(c->d_ler); cudaFree(c->d_lab_vals); cudaFree(c->d_lab_offs);
+  cudaFree(c->d_seq); cudaFree(c->d_status); cudaFree(c->d_hyp_len); cudaFree(c->d_dist);
+  cudaFree(c->d_hyp); cudaFree(c->d_ws);
+  cudaFreeHost(c->h_logits); cudaFreeHost(c->h_grad); cudaFreeHost(c->h_small); cudaFreeHost(c->h_hyp);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int nasr_host_ctx_create(int device, int max_T, int max_B, int max_C, int max_label_len,
+                         nasr_host_ctx** out) {
+  NASR_CHECK_ARG(out, "nasr_host_ctx_create: out is NULL");
+  NASR_CHECK_ARG(max_T >= 1 && max_B >= 1 && max_C >= 1 && max_label_len >= 0,
+                 "nasr_host_ctx_create: bad maxima");
+  NASR_CUDA(cudaSetDevice(device));
+  size_t ws = 0;
+  int rc = ctc_workspace_bytes(max_T, max_B, max_C, max_label_len, &ws);
+  if (rc != NASR_OK) return rc;
+  nasr_host_ctx* c = new (std::nothrow) nasr_host_ctx();
+  NASR_CHECK_ARG(c, "nasr_host_ctx_create: out of host memory");
+  memset(c, 0, sizeof(*c));
+  c->device = device; c->max_T = max_T; c->max_B = max_B; c->max_C = max_C; c->max_L = max_label_len;
+  c->ws_bytes = ws;
+  const size_t nlog = (size_t)max_T * max_B * max_C;
+  const size_t N = (size_t)max_B * max_label_len;
+  size_t o[10];
+  c->small_bytes = small_layout(max_B, (int)N, &o[0], &o[1], &o[2], &o[3], &o[4], &o[5], &o[6], &o[7], &o[8], &o[9]);
+#define NASR_CTX_TRY(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t e_ = (expr);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      set_error("nasr_host_ctx_create: %s failed: %s", #expr, cudaGetErrorString(e_));  \
+      nasr_host_ctx_destroy(c);                                                         \
+      return NASR_ERR_CUDA;                                                             \
+    }                                                                                   \
+  } while (0)
+  NASR_CTX_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  NASR_CTX_TRY(cudaMalloc(&c->d_logits, sizeof(float) * nlog));
+  NASR_CTX_TRY(cudaMalloc(&c->d_grad, sizeof(float) * nlog));
+  NASR_CTX_TRY(cudaMalloc(&c->d_loss, sizeof(float) * max_B));
+  NASR_CTX_TRY(cudaMalloc(&c->d_grad_loss, sizeof(float) * max_B));
+  NASR_CTX_TRY(cudaMalloc(&c->d_nsl, sizeof(float) * max_B));
+  NASR_CTX_TRY(cudaMalloc(&c->d_ler, sizeof(float) * max_B));
+  NASR_CTX_TRY(cudaMalloc(&c->d_lab_vals, sizeof(int32_t) * (N + 1)));
+  NASR_CTX_TRY(cudaMalloc(&c->d_lab_offs, sizeof(int32_t) * (max_B + 1)));
+  NASR_CTX_TRY(cudaMalloc(&c->d_seq, sizeof(int32_t) * max_B));
+  NASR_CTX_TRY(cudaMalloc(&c->d_status, sizeof(int32_t) * max_B));
+  NASR_CTX_TRY(cudaMalloc(&c->d_hyp_len, sizeof(int32_t) * max_B));
+  NASR_CTX_TRY(cudaMalloc(&c->d_dist, sizeof(int32_t) * max_B));
+  NASR_CTX_TRY(cudaMalloc(&c->d_hyp, sizeof(int64_t) * (size_t)max_B * max_T));
+  NASR_CTX_TRY(cudaMalloc(&c->d_ws, ws));
+  NASR_CTX_TRY(cudaMallocHost(&c->h_logits, sizeof(float) * nlog));
+  NASR_CTX_TRY(cudaMallocHost(&c->h_grad, sizeof(float) * nlog));
+  NASR_CTX_TRY(cudaMallocHost(&c->h_small, c->small_bytes));
+  NASR_CTX_TRY(cudaMallocHost(&c->h_hyp, sizeof(int64_t) * (size_t)max_B * max_T));
+#undef NASR_CTX_TRY
+  *out = c;
+  return NASR_OK;
+}
+
+float* nasr_host_ctx_pinned_logits(nasr_host_ctx* c) { return c ? c->h_logits : nullptr; }
+float* nasr_host_ctx_pinned_grad(nasr_host_ctx* c) { return c ? c->h_grad : nullptr; }
+
+int nasr_host_ctc_step(nasr_host_ctx* c, const float* logits, int T, int B, int C,
+                       const int32_t* label_values, const int32_t* label_offsets,
+                       const int32_t* seq_len, int blank, const float* grad_loss, float* loss,
+                       float* grad, int32_t* status, int64_t* hyp, int32_t* hyp_len,
+                       float* neg_sum_logits, int32_t* dist, float* ler) {
+  NASR_CHECK_ARG(c, "nasr_host_ctc_step: ctx is NULL");
+  NASR_CHECK_ARG(T >= 1 && B >= 1 && C >= 1 && T <= c->max_T && B <= c->max_B && C <= c->max_C &&
+                     (size_t)T * B * C <= (size_t)c->max_T * c->max_B * c->max_C,
+                 "nasr_host_ctc_step: shape T=%d B=%d C=%d exceeds the context maxima", T, B, C);
+  NASR_CHECK_ARG(logits && label_offsets && seq_len && loss && status, "nasr_host_ctc_step: NULL argument");
+  const int N = label_offsets[B];
+  NASR_CHECK_ARG(label_offsets[0] == 0 && N >= 0 && (size_t)N <= (size_t)c->max_B * c->max_L,
+                 "nasr_host_ctc_step: label_offsets inconsistent with the context maxima");
+  int Lmax = 0;
+  for (int b = 0; b < B; b++) {
+    const int l = label_offsets[b + 1] - label_offsets[b];
+    NASR_CHECK_ARG(l >= 0, "nasr_host_ctc_step: label_offsets not monotone at row %d", b);
+    Lmax = l > Lmax ? l : Lmax;
+  }
+  NASR_CHECK_ARG(Lmax <= c->max_L, "nasr_host_ctc_step: transcript of %d labels exceeds max_label_len=%d",
+                 Lmax, c->max_L);
+  NASR_CUDA(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  const size_t nlog = (size_t)T * B * C;
+  size_t o_vals, o_offs, o_seq, o_gl, o_loss, o_status, o_hl, o_nsl, o_dist, o_ler;
+  small_layout(c->max_B, c->max_B * c->max_L, &o_vals, &o_offs, &o_seq, &o_gl, &o_loss, &o_status,
+               &o_hl, &o_nsl, &o_dist, &o_ler);
+  // stage inputs in pinned memory (skipped for logits when the caller filled the pinned buffer)
+  if (logits != c->h_logits) memcpy(c->h_logits, logits, sizeof(float) * nlog);
+  if (N) memcpy(c->h_small + o_vals, label_values, sizeof(int32_t) * N);
+  memcpy(c->h_small + o_offs, label_offsets, sizeof(int32_t) * (B + 1));
+  memcpy(c->h_small + o_seq, seq_len, sizeof(int32_t) * B);
+  if (grad_loss) memcpy(c->h_small + o_gl, grad_loss, sizeof(float) * B);
+  NASR_CUDA(cudaMemcpyAsync(c->d_logits, c->h_logits, sizeof(float) * nlog, cudaMemcpyHostToDevice, s));
+  if (N) NASR_CUDA(cudaMemcpyAsync(c->d_lab_vals, c->h_small + o_vals, sizeof(int32_t) * N, cudaMemcpyHostToDevice, s));
+  NASR_CUDA(cudaMemcpyAsync(c->d_lab_offs, c->h_small + o_offs, sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, s));
+  NASR_CUDA(cudaMemcpyAsync(c->d_seq, c->h_small + o_seq, sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
+  if (grad_loss) NASR_CUDA(cudaMemcpyAsync(c->d_grad_loss, c->h_small + o_gl, sizeof(float) * B, cudaMemcpyHostToDevice, s));
+  int rc = ctc_loss_grad(c->d_logits, T, B, C, c->d_lab_vals, c->d_lab_offs, Lmax, c->d_seq, blank,
+                         c->d_loss, grad ? c->d_grad : nullptr, grad_loss ? c->d_grad_loss : nullptr,
+                         c->d_status, c->d_ws, c->ws_bytes, s);
+  if (rc != NASR_OK) return rc;
+  const bool want_decode = hyp || hyp_len || neg_sum_logits || dist || ler;
+  if (want_decode) {
+    rc = greedy_decode(c->d_logits, T, B, C, c->d_seq, blank, 1, c->d_hyp, c->d_hyp_len, c->d_nsl, s);
+    if (rc != NASR_OK) return rc;
+    if (dist || ler) {
+      rc = edit_distance_dense(c->d_hyp, T, c->d_hyp_len, c->d_lab_vals, c->d_lab_offs, Lmax, B, 1,
+                               c->d_dist, c->d_ler, s);
+      if (rc != NASR_OK) return rc;
+    }
+  }
+  if (grad) NASR_CUDA(cudaMemcpyAsync(c->h_grad, c->d_grad, sizeof(float) * nlog, cudaMemcpyDeviceToHost, s));
+  NASR_CUDA(cudaMemcpyAsync(c->h_small + o_loss, c->d_loss, sizeof(float) * B, cudaMemcpyDeviceToHost, s));
+  NASR_CUDA(cudaMemcpyAsync(c->h_small + o_status, c->d_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, s));
+  if (want_decode) {
+    NASR_CUDA(cudaMemcpyAsync(c->h_small + o_hl, c->d_hyp_len, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, s));
+    NASR_CUDA(cudaMemcpyAsync(c->h_small + o_nsl, c->d_nsl, sizeof(float) * B, cudaMemcpyDeviceToHost, s));
+    if (hyp) NASR_CUDA(cudaMemcpyAsync(c->h_hyp, c->d_hyp, sizeof(int64_t) * (size_t)B * T, cudaMemcpyDeviceToHost, s));
+    if (dist || ler) {
+      NASR_CUDA(cudaMemcpyAsync(c->h_small + o_dist, c->d_dist, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, s));
+      NASR_CUDA(cudaMemcpyAsync(c->h_small + o_ler, c->d_ler, sizeof(float) * B, cudaMemcpyDeviceToHost, s));
+    }
+  }
+  NASR_CUDA(cudaStreamSynchronize(s));
+  memcpy(loss, c->h_small + o_loss, sizeof(float) * B);
+  memcpy(status, c->h_small + o_status, sizeof(int32_t) * B);
+  if (grad && grad != c->h_grad) memcpy(grad, c->h_grad, sizeof(float) * nlog);
+  if (hyp_len) memcpy(hyp_len, c->h_small + o_hl, sizeof(int32_t) * B);
+  if (neg_sum_logits) memcpy(neg_sum_logits, c->h_small + o_nsl, sizeof(float) * B);
+  if (hyp) memcpy(hyp, c->h_hyp, sizeof(int64_t) * (size_t)B * T);
+  if (dist) memcpy(dist, c->h_small + o_dist, sizeof(int32_t) * B);
+  if (ler) memcpy(ler, c->h_small + o_ler, sizeof(float) * B);
+  return NASR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,53 @@
+// Shared host/device helpers for libnasr_ctc.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "nasr_ctc.h"
+
+namespace nasr {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+#define NASR_CHECK_ARG(cond, ...)            \
+  do {                                       \
+    if (!(cond)) {                           \
+      nasr::set_error(__VA_ARGS__);          \
+      return NASR_ERR_INVALID_ARGUMENT;      \
+    }                                        \
+  } while (0)
+
+#define NASR_CUDA(expr)                                                                   \
+  do {                                                                                    \
+    cudaError_t e_ = (expr);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      nasr::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__,   \
+                      __LINE__);                                                          \
+      return NASR_ERR_CUDA;                                                               \
+    }                                                                                     \
+  } while (0)
+
+constexpr int kWarp = 32;
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace nasr

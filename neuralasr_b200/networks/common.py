@@ -1,0 +1,390 @@
+"""Drop-in ``loss`` / ``decoding`` / ``label_error_rate`` backed by sm_100a CUDA kernels.
+
+Mirrors the three helpers every CTC model of the reference ends with
+(``networks/tfnetwork.py:58-70``; module-level names of the README-era ``networks/common.py``,
+``README.md:85-86,130``), same argument order minus ``self``:
+
+    loss(logits, labels, seq_len)        <- create_loss   : reduce_mean(tf.nn.ctc_loss(labels, logits, seq_len))
+    decoding(logits, seq_len)            <- create_model  : ctc_greedy_decoder(logits, seq_len) -> (decoded[0], log_prob)
+    label_error_rate(model, labels)      <- create_metric : reduce_mean(edit_distance(cast(model, int32), labels))
+
+``logits``: float32 CUDA tensor, time-major ``[T, B, C]``; ``labels``: the sparse triple
+``(indices, values, shape)`` that ``utils.sparse_tuple_from`` builds (numpy or torch), or a prepared
+:class:`LabelsCSR`; ``seq_len``: int32 ``[B]``.  Blank is ``C-1`` (reference convention,
+``preprocess_mfcc.py:81-92``).
+
+torch is used for device memory and streams only; all arithmetic happens in ``libnasr_ctc.so``
+(``include/nasr_ctc.h``).  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..utils import sparse_to_csr
+
+_WORKSPACES = {}
+
+
+# --------------------------------------------------------------------------------------------
+# inputs
+# --------------------------------------------------------------------------------------------
+class LabelsCSR:
+    """Device-resident CSR form of a label SparseTensor triple (values i32[N], offsets i32[B+1])."""
+
+    __slots__ = ("values", "offsets", "max_len", "batch", "host_values", "host_offsets")
+
+    def __init__(self, values, offsets, max_len, batch, host_values=None, host_offsets=None):
+        self.values, self.offsets, self.max_len, self.batch = values, offsets, int(max_len), int(batch)
+        self.host_values, self.host_offsets = host_values, host_offsets
+
+
+def _to_numpy(x):
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().numpy()
+    return np.asarray(x)
+
+
+def prepare_labels(labels, device):
+    """Sparse triple -> :class:`LabelsCSR` on ``device`` (host prefix sum + one small H2D copy)."""
+    if isinstance(labels, LabelsCSR):
+        return labels
+    if hasattr(labels, "indices") and hasattr(labels, "values") and hasattr(labels, "dense_shape"):
+        labels = (labels.indices, labels.values, labels.dense_shape)     # SparseTensorValue-like
+    indices, values, shape = labels
+    vals, offs, max_len = sparse_to_csr((_to_numpy(indices), _to_numpy(values), _to_numpy(shape)))
+    dvals = torch.from_numpy(vals if vals.size else np.zeros(1, np.int32)).to(device, non_blocking=True)
+    doffs = torch.from_numpy(offs).to(device, non_blocking=True)
+    return LabelsCSR(dvals, doffs, max_len, offs.size - 1, vals, offs)
+
+
+def _check_logits(logits):
+    if not isinstance(logits, torch.Tensor) or not logits.is_cuda:
+        raise ValueError("logits must be a CUDA torch.Tensor (there is no CPU path)")
+    if logits.dtype != torch.float32 or logits.dim() != 3:
+        raise ValueError("logits must be float32 [T, B, C] (time-major), got %s %s"
+                         % (logits.dtype, tuple(logits.shape)))
+    if not logits.is_contiguous():
+        raise ValueError("logits must be contiguous [T, B, C]; transpose the model output with "
+                         ".contiguous() (the reference transposes too: bilstm_ctc_net.py:48)")
+    return logits
+
+
+def _seq_len_tensor(seq_len, device, B):
+    if isinstance(seq_len, torch.Tensor):
+        t = seq_len.to(device=device, dtype=torch.int32, non_blocking=True).contiguous()
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(seq_len, dtype=np.int32)).to(device, non_blocking=True)
+    if t.dim() != 1 or t.numel() != B:
+        raise ValueError("seq_len must have shape [B=%d], got %s" % (B, tuple(t.shape)))
+    return t
+
+
+def _workspace(device, nbytes):
+    key = (device.type, device.index)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+# --------------------------------------------------------------------------------------------
+# errors: TF raises InvalidArgumentError out of sess.run; here per-utterance flags come back
+# --------------------------------------------------------------------------------------------
+def status_message(b, flags):
+    msgs = []
+    if flags & _lib.ST_LABEL_OUT_OF_RANGE:
+        msgs.append("Saw a non-null label (index >= num_classes - 1) following a null label, batch: %d" % b)
+    if flags & _lib.ST_SEQ_LEN_OUT_OF_RANGE:
+        msgs.append("sequence_length(%d) <= max_time violated" % b)
+    if flags & _lib.ST_NOT_ENOUGH_TIME:
+        msgs.append("Not enough time for target transition sequence, batch: %d" % b)
+    if flags & _lib.ST_NO_VALID_PATH and not msgs:
+        msgs.append("No valid path found, batch: %d (loss is +inf)" % b)
+    return "; ".join(msgs)
+
+
+def check_status(status, raise_on_no_valid_path=False):
+    """Raise ``ValueError`` with TF-like text if any utterance was flagged (synchronises)."""
+    st = status.detach().cpu().numpy()
+    mask = _lib.ST_LABEL_OUT_OF_RANGE | _lib.ST_SEQ_LEN_OUT_OF_RANGE | _lib.ST_NOT_ENOUGH_TIME
+    if raise_on_no_valid_path:
+        mask |= _lib.ST_NO_VALID_PATH
+    bad = np.nonzero(st & mask)[0]
+    if bad.size:
+        raise ValueError(status_message(int(bad[0]), int(st[bad[0]])))
+
+
+# --------------------------------------------------------------------------------------------
+# CTC loss + gradient
+# --------------------------------------------------------------------------------------------
+def ctc_loss_and_grad(logits, labels, seq_len, grad_loss=None, want_grad=True, out_grad=None,
+                      blank=None, use_dlpack=False):
+    """One fused launch: per-utterance loss ``[B]``, gradient ``[T,B,C]`` (scaled by ``grad_loss[b]``,
+    unit if None) and status flags ``[B]``.  Asynchronous on the current stream."""
+    lib = _lib.load()
+    logits = _check_logits(logits)
+    T, B, C = logits.shape
+    dev = logits.device
+    blank = C - 1 if blank is None else int(blank)
+    lab = prepare_labels(labels, dev)
+    if lab.batch != B:
+        raise ValueError("labels dense_shape[0]=%d but logits batch=%d" % (lab.batch, B))
+    sl = _seq_len_tensor(seq_len, dev, B)
+    loss_b = torch.empty(B, dtype=torch.float32, device=dev)
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    grad = None
+    if want_grad:
+        grad = out_grad if out_grad is not None else torch.empty_like(logits)
+        if grad.shape != logits.shape or grad.dtype != torch.float32 or not grad.is_contiguous():
+            raise ValueError("out_grad must be a contiguous float32 tensor shaped like logits")
+    gl = None
+    if grad_loss is not None:
+        gl = grad_loss.to(device=dev, dtype=torch.float32).contiguous()
+        if gl.numel() != B:
+            raise ValueError("grad_loss must have B elements")
+    need = ctypes.c_size_t(0)
+    _lib.check(lib.nasr_ctc_workspace_bytes(T, B, C, lab.max_len, ctypes.byref(need)), "ctc workspace")
+    ws = _workspace(dev, need.value)
+    with torch.cuda.device(dev):
+        if use_dlpack:
+            keep = []
+
+            def dl(t):
+                if t is None:
+                    return None
+                cap = t.__dlpack__()
+                keep.append(cap)
+                ctypes.pythonapi.PyCapsule_GetPointer.restype = ctypes.c_void_p
+                ctypes.pythonapi.PyCapsule_GetPointer.argtypes = [ctypes.py_object, ctypes.c_char_p]
+                return ctypes.c_void_p(ctypes.pythonapi.PyCapsule_GetPointer(cap, b"dltensor"))
+
+            rc = lib.nasr_ctc_loss_grad_dl(dl(logits), dl(lab.values), dl(lab.offsets), lab.max_len,
+                                           dl(sl), blank, dl(loss_b), dl(grad), dl(gl), dl(status),
+                                           dl(ws), _stream_ptr(dev))
+            for cap in keep:   # we never took ownership: run the producer's deleter ourselves
+                _release_capsule(cap)
+        else:
+            rc = lib.nasr_ctc_loss_grad_f32(_ptr(logits), T, B, C, _ptr(lab.values), _ptr(lab.offsets),
+                                            lab.max_len, _ptr(sl), blank, _ptr(loss_b), _ptr(grad),
+                                            _ptr(gl), _ptr(status), _ptr(ws), ws.numel(),
+                                            _stream_ptr(dev))
+    _lib.check(rc, "nasr_ctc_loss_grad")
+    return loss_b, grad, status
+
+
+class _DLManagedTensor(ctypes.Structure):
+    pass
+
+
+_DLManagedTensor._fields_ = [
+    ("data", ctypes.c_void_p), ("device_type", ctypes.c_int32), ("device_id", ctypes.c_int32),
+    ("ndim", ctypes.c_int32), ("dtype_code", ctypes.c_uint8), ("dtype_bits", ctypes.c_uint8),
+    ("dtype_lanes", ctypes.c_uint16), ("shape", ctypes.c_void_p), ("strides", ctypes.c_void_p),
+    ("byte_offset", ctypes.c_uint64), ("manager_ctx", ctypes.c_void_p),
+    ("deleter", ctypes.CFUNCTYPE(None, ctypes.c_void_p)),
+]
+
+
+def _release_capsule(cap):
+    """A DLPack capsule still named "dltensor" is unconsumed: call its deleter, then rename it so the
+    capsule destructor does not run the deleter a second time."""
+    api = ctypes.pythonapi
+    api.PyCapsule_GetPointer.restype = ctypes.c_void_p
+    api.PyCapsule_GetPointer.argtypes = [ctypes.py_object, ctypes.c_char_p]
+    api.PyCapsule_SetName.argtypes = [ctypes.py_object, ctypes.c_char_p]
+    p = api.PyCapsule_GetPointer(cap, b"dltensor")
+    mt = ctypes.cast(p, ctypes.POINTER(_DLManagedTensor)).contents
+    api.PyCapsule_SetName(cap, b"used_dltensor")
+    if mt.deleter:
+        mt.deleter(p)
+
+
+class _CtcLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, seq_len, check):
+        B = logits.shape[1]
+        # d(mean loss)/d(logits) = (1/B) * per-utterance gradient (tfnetwork.py:59 reduce_mean)
+        gl = torch.full((B,), 1.0 / B, dtype=torch.float32, device=logits.device)
+        loss_b, grad, status = ctc_loss_and_grad(logits.detach(), labels, seq_len, grad_loss=gl,
+                                                 want_grad=logits.requires_grad)
+        if check:
+            check_status(status)
+        ctx.save_for_backward(grad if grad is not None else torch.empty(0, device=logits.device))
+        sums = torch.empty(4, dtype=torch.float64, device=logits.device)
+        lib = _lib.load()
+        with torch.cuda.device(logits.device):
+            _lib.check(lib.nasr_batch_sums_f64(_ptr(loss_b), None, None, B, _ptr(sums),
+                                               _stream_ptr(logits.device)), "nasr_batch_sums")
+        mean = (sums[0] / B).to(torch.float32)
+        ctx.mark_non_differentiable(loss_b, status)
+        return mean, loss_b, status
+
+    @staticmethod
+    def backward(ctx, g_mean, _g_loss_b, _g_status):
+        (grad,) = ctx.saved_tensors
+        return grad * g_mean, None, None, None
+
+
+def loss(logits, labels, seq_len, check=True):
+    """Mean CTC loss over the batch — drop-in for ``create_loss`` (``networks/tfnetwork.py:58-59``).
+
+    Differentiable w.r.t. ``logits`` (the backward is the gradient the same launch already produced).
+    ``check=True`` reads the status flags back and raises ``ValueError`` for what TF reports as
+    ``InvalidArgumentError``; pass ``check=False`` on a hot loop to stay asynchronous.
+    """
+    mean, per_utt, status = _CtcLossFn.apply(_check_logits(logits), labels, seq_len, bool(check))
+    mean.per_utterance = per_utt      # float32 [B]
+    mean.status = status              # int32 [B] NASR_ST_* flags
+    return mean
+
+
+# --------------------------------------------------------------------------------------------
+# greedy decode
+# --------------------------------------------------------------------------------------------
+class DecodedSparse:
+    """``decoded[0]`` of ``tf.nn.ctc_greedy_decoder``: unpacks / indexes as
+    ``(indices i64[M,2], values i64[M], dense_shape i64[2])``; materialised lazily because M is
+    data dependent (one host sync).  ``hyp`` [B,T] / ``hyp_len`` [B] keep the dense device form."""
+
+    def __init__(self, hyp, hyp_len):
+        self.hyp, self.hyp_len = hyp, hyp_len
+        self._triple = None
+
+    def _materialise(self):
+        if self._triple is None:
+            lib = _lib.load()
+            B, T = self.hyp.shape
+            dev = self.hyp.device
+            offs = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+            torch.cumsum(self.hyp_len, 0, out=offs[1:])
+            M = int(offs[-1].item())
+            indices = torch.empty((M, 2), dtype=torch.int64, device=dev)
+            values = torch.empty(M, dtype=torch.int64, device=dev)
+            shape = torch.empty(2, dtype=torch.int64, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.nasr_hyp_to_sparse_i64(_ptr(self.hyp), T, _ptr(offs), B, _ptr(indices),
+                                                      _ptr(values), _ptr(shape), _stream_ptr(dev)),
+                           "nasr_hyp_to_sparse")
+            self._triple = (indices, values, shape)
+        return self._triple
+
+    indices = property(lambda self: self._materialise()[0])
+    values = property(lambda self: self._materialise()[1])
+    dense_shape = property(lambda self: self._materialise()[2])
+
+    def __iter__(self):
+        return iter(self._materialise())
+
+    def __getitem__(self, i):
+        return self._materialise()[i]
+
+    def __len__(self):
+        return 3
+
+
+def decoding(logits, seq_len, merge_repeated=True, blank=None):
+    """Greedy CTC decode — drop-in for ``create_model`` with the greedy op of
+    ``networks/tfnetwork.py:63``.  Returns ``(decoded, neg_sum_logits[B,1])`` like the reference's
+    ``(model[0], log_prob)``."""
+    lib = _lib.load()
+    logits = _check_logits(logits)
+    T, B, C = logits.shape
+    dev = logits.device
+    blank = C - 1 if blank is None else int(blank)
+    sl = _seq_len_tensor(seq_len, dev, B)
+    hyp = torch.empty((B, T), dtype=torch.int64, device=dev)
+    hyp_len = torch.empty(B, dtype=torch.int32, device=dev)
+    nsl = torch.empty((B, 1), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nasr_ctc_greedy_decode_i64(_ptr(logits), T, B, C, _ptr(sl), blank,
+                                                  int(bool(merge_repeated)), _ptr(hyp), _ptr(hyp_len),
+                                                  _ptr(nsl), _stream_ptr(dev)), "nasr_ctc_greedy_decode")
+    return DecodedSparse(hyp, hyp_len), nsl
+
+
+# --------------------------------------------------------------------------------------------
+# label error rate
+# --------------------------------------------------------------------------------------------
+def edit_distance(model, labels, normalize=True):
+    """Per-utterance ``(dist i32[B], ler f32[B])`` — ``tf.edit_distance(cast(model, int32), labels)``."""
+    lib = _lib.load()
+    if isinstance(model, DecodedSparse):
+        dev = model.hyp.device
+        B, T = model.hyp.shape
+        lab = prepare_labels(labels, dev)
+        if lab.batch != B:
+            raise ValueError("hypothesis batch %d != labels batch %d" % (B, lab.batch))
+        dist = torch.empty(B, dtype=torch.int32, device=dev)
+        ler = torch.empty(B, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.nasr_edit_distance_i64(_ptr(model.hyp), T, _ptr(model.hyp_len),
+                                                  _ptr(lab.values), _ptr(lab.offsets), lab.max_len, B,
+                                                  int(bool(normalize)), _ptr(dist), _ptr(ler),
+                                                  _stream_ptr(dev)), "nasr_edit_distance")
+        return dist, ler
+    # a raw SparseTensor triple (e.g. LAS's dense_to_sparse output, las.py:116-117)
+    indices, values, shape = model
+    if isinstance(labels, LabelsCSR):
+        dev = labels.values.device
+    elif isinstance(values, torch.Tensor) and values.is_cuda:
+        dev = values.device
+    else:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    hv, ho, hmax = sparse_to_csr((_to_numpy(indices), _to_numpy(values), _to_numpy(shape)))
+    lab = prepare_labels(labels, dev)
+    B = ho.size - 1
+    if lab.batch != B:
+        raise ValueError("hypothesis batch %d != labels batch %d" % (B, lab.batch))
+    dhv = torch.from_numpy((hv if hv.size else np.zeros(1, np.int32)).astype(np.int64)).to(dev)
+    dho = torch.from_numpy(ho).to(dev)
+    dist = torch.empty(B, dtype=torch.int32, device=dev)
+    ler = torch.empty(B, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nasr_edit_distance_csr_i64(_ptr(dhv), _ptr(dho), hmax, _ptr(lab.values),
+                                                  _ptr(lab.offsets), lab.max_len, B,
+                                                  int(bool(normalize)), _ptr(dist), _ptr(ler),
+                                                  _stream_ptr(dev)), "nasr_edit_distance_csr")
+    return dist, ler
+
+
+def batch_sums(loss_b=None, ler=None, dist=None):
+    """``float64[4]`` device vector ``[sum loss, sum ler, sum dist, B]`` (what each rank all-reduces)."""
+    lib = _lib.load()
+    ref = next(t for t in (loss_b, ler, dist) if t is not None)
+    B = ref.numel()
+    sums = torch.empty(4, dtype=torch.float64, device=ref.device)
+    with torch.cuda.device(ref.device):
+        _lib.check(lib.nasr_batch_sums_f64(_ptr(loss_b), _ptr(ler), _ptr(dist), B, _ptr(sums),
+                                           _stream_ptr(ref.device)), "nasr_batch_sums")
+    return sums
+
+
+def label_error_rate(model, labels):
+    """Mean normalised edit distance — drop-in for ``create_metric`` (``networks/tfnetwork.py:66-70``).
+    Returns a 0-dim float32 CUDA tensor with ``.per_utterance`` (ler[B]) and ``.distances`` (i32[B])."""
+    dist, ler = edit_distance(model, labels, normalize=True)
+    sums = batch_sums(ler=ler, dist=dist)
+    mean = (sums[1] / ler.numel()).to(torch.float32)
+    mean.per_utterance = ler
+    mean.distances = dist
+    return mean
+
+
+# reference-era aliases (the snapshot's method names, networks/tfnetwork.py:58,61,66)
+create_loss = loss
+create_model = decoding
+create_metric = label_error_rate
+model = decoding

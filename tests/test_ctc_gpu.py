@@ -1,0 +1,223 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle and the golden fixtures.
+
+Tolerances are the north star's: loss 1e-4 relative, gradient 1e-4 absolute (fp32 outputs compared
+with the float64 oracle), decoded sequences / hypothesis lengths / integer edit distances bit-exact.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import c_oracle, ctc_oracle as o  # noqa: E402  (the checker, never the thing under test)
+
+from conftest import make_batch  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-4
+GRAD_ATOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def common():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from neuralasr_b200.networks import common as c
+    return c
+
+
+def _triple(g):
+    from neuralasr_b200.utils import sparse_to_csr  # noqa: F401
+    offs = g["label_offsets"]
+    B = offs.size - 1
+    lens = np.diff(offs)
+    rows = np.repeat(np.arange(B), lens)
+    cols = np.arange(offs[-1]) - np.repeat(offs[:-1], lens)
+    return (np.stack([rows, cols], 1).astype(np.int64), g["label_values"].astype(np.int32),
+            np.asarray([B, max(int(lens.max()), 1)], np.int64))
+
+
+def _run_loss(common, g, grad_loss=None, use_dlpack=False):
+    x = torch.from_numpy(g["logits"]).cuda()
+    gl = None if grad_loss is None else torch.from_numpy(grad_loss).cuda()
+    loss, grad, status = common.ctc_loss_and_grad(x, _triple(g), g["seq_len"], grad_loss=gl,
+                                                  use_dlpack=use_dlpack)
+    torch.cuda.synchronize()
+    return loss.cpu().numpy(), grad.cpu().numpy(), status.cpu().numpy()
+
+
+def _assert_loss_grad(loss, grad, status, want_loss, want_grad, want_status=None):
+    if want_status is not None:
+        assert np.array_equal(status, want_status)
+    fin = np.isfinite(want_loss)
+    assert np.array_equal(np.isfinite(loss), fin)
+    np.testing.assert_allclose(loss[fin], want_loss[fin], rtol=LOSS_RTOL, atol=1e-5)
+    assert np.isfinite(grad).all()
+    assert np.abs(grad - want_grad).max() <= GRAD_ATOL
+
+
+def test_loss_grad_matches_golden(common, golden):
+    loss, grad, status = _run_loss(common, golden)
+    _assert_loss_grad(loss, grad, status, golden["loss"], golden["grad"], np.zeros_like(status))
+    for b, tb in enumerate(golden["seq_len"]):
+        assert not grad[tb:, b, :].any()            # padded frames: exactly zero
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("cfg1", dict(T=500, B=16, C=38, Lmax=100, mode="ragged")),
+    ("cfg2", dict(T=800, B=64, C=38, Lmax=150, mode="ragged")),
+    ("tight", dict(T=120, B=9, C=38, Lmax=50, mode="tight")),
+    ("peaky", dict(T=400, B=12, C=38, Lmax=60, mode="ragged", peaky=True)),
+    ("tiny_vocab", dict(T=64, B=7, C=2, Lmax=20, mode="ragged", repeat_p=0.0)),
+    ("wide_vocab", dict(T=200, B=6, C=1024, Lmax=40, mode="ragged")),
+    ("long", dict(T=1500, B=3, C=38, Lmax=300, mode="full")),
+    ("odd_sizes", dict(T=17, B=3, C=5, Lmax=3, mode="ragged")),
+])
+def test_loss_grad_matches_oracle(common, name, kw):
+    g = make_batch(hash(name) % 1000, **kw)
+    want_loss, want_grad, want_status = c_oracle.ctc_loss_grad(
+        g["logits"], g["label_values"], g["label_offsets"], g["seq_len"], precision="f64")
+    loss, grad, status = _run_loss(common, g)
+    _assert_loss_grad(loss, grad, status, want_loss, want_grad, want_status)
+    valid = grad[: g["seq_len"].min()]
+    assert np.abs(valid.sum(-1)).max() < 1e-5       # softmax - occupancy sums to 0 over classes
+
+
+def test_grad_loss_scaling_dlpack_and_repeatability(common):
+    g = make_batch(5, T=90, B=8, C=38, Lmax=20)
+    gl = np.linspace(0.05, 1.0, 8).astype(np.float32)
+    l0, g0, s0 = _run_loss(common, g)
+    l1, g1, s1 = _run_loss(common, g, grad_loss=gl)
+    np.testing.assert_allclose(g1, g0 * gl[None, :, None], atol=1e-6)
+    l2, g2, s2 = _run_loss(common, g, use_dlpack=True)
+    assert np.array_equal(l0, l2) and np.array_equal(g0, g2) and np.array_equal(s0, s2)
+    l3, g3, _ = _run_loss(common, g)
+    assert np.array_equal(l0, l3) and np.array_equal(g0, g3)      # deterministic, bit for bit
+
+
+def test_status_flags_and_infeasible(common):
+    C = 6
+    x = np.random.default_rng(3).normal(size=(5, 5, C)).astype(np.float32)
+    labs = [[0, 1], [5, 1], [2, 2, 2, 2], [1], []]     # row1: label == blank; row2 needs 7 frames
+    lens = [len(l) for l in labs]
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    vals = np.concatenate([np.asarray(l, np.int32) for l in labs])
+    seq = np.array([5, 5, 5, 9, 0], np.int32)          # row3: seq_len > T; row4: empty utterance
+    g = dict(logits=x, label_values=vals, label_offsets=offs, seq_len=seq)
+    want_loss, want_grad, want_status = c_oracle.ctc_loss_grad(x, vals, offs, seq)
+    loss, grad, status = _run_loss(common, g)
+    assert status.tolist() == want_status.tolist() == [0, 1, 4 | 8, 2, 0]
+    _assert_loss_grad(loss, grad, status, want_loss, want_grad)
+    assert loss[4] == 0.0 and not grad[:, 4].any()
+    with pytest.raises(ValueError, match="Not enough time|non-null label|sequence_length"):
+        common.loss(torch.from_numpy(x).cuda(), _triple(g), seq)
+
+
+def test_drop_in_loss_autograd_mean(common):
+    g = make_batch(21, T=60, B=4, C=11, Lmax=9, empty_row=False)
+    x = torch.from_numpy(g["logits"]).cuda().requires_grad_(True)
+    out = common.loss(x, _triple(g), torch.from_numpy(g["seq_len"]))
+    (out * 3.0).backward()
+    want_loss, want_grad, _ = c_oracle.ctc_loss_grad(g["logits"], g["label_values"],
+                                                     g["label_offsets"], g["seq_len"])
+    assert abs(float(out) - want_loss.mean()) <= LOSS_RTOL * want_loss.mean()
+    np.testing.assert_allclose(out.per_utterance.cpu().numpy(), want_loss, rtol=LOSS_RTOL)
+    assert np.abs(x.grad.cpu().numpy() - 3.0 * want_grad / 4).max() <= GRAD_ATOL
+
+
+@pytest.mark.parametrize("kw", [
+    dict(T=800, B=64, C=38, Lmax=150, mode="ragged", peaky=True),
+    dict(T=300, B=5, C=38, Lmax=60, mode="ragged"),
+    dict(T=2500, B=3, C=7, Lmax=40, mode="full"),
+    dict(T=33, B=4, C=1024, Lmax=8, mode="ragged"),
+])
+def test_decode_and_ler_match_oracle(common, kw):
+    g = make_batch(31, **kw)
+    x = torch.from_numpy(g["logits"]).cuda()
+    decoded, nsl = common.decoding(x, g["seq_len"])
+    hv, ho, want_nsl = c_oracle.greedy_decode(g["logits"], g["seq_len"])
+    idx, vals, shape = decoded
+    wi, wv, ws = o.csr_to_sparse(hv, ho)
+    assert np.array_equal(vals.cpu().numpy(), wv) and vals.dtype == torch.int64
+    assert np.array_equal(idx.cpu().numpy(), wi) and np.array_equal(shape.cpu().numpy(), ws)
+    assert np.array_equal(decoded.hyp_len.cpu().numpy(), np.diff(ho))
+    assert nsl.shape == (kw["B"], 1)
+    assert np.array_equal(nsl.cpu().numpy()[:, 0], want_nsl)       # same fp32 accumulation order
+    want_d, want_ler = c_oracle.edit_distance(hv, ho, g["label_values"], g["label_offsets"])
+    mean = common.label_error_rate(decoded, _triple(g))
+    assert np.array_equal(mean.distances.cpu().numpy(), want_d)
+    assert np.array_equal(mean.per_utterance.cpu().numpy(), want_ler)
+    fin = np.isfinite(want_ler)
+    if fin.all():
+        assert abs(float(mean) - want_ler.astype(np.float64).mean()) < 1e-6
+    else:
+        assert np.isinf(float(mean))
+    # same metric from the raw SparseTensor triple (the form LAS's caller holds, las.py:116-117)
+    mean2 = common.label_error_rate((idx, vals, shape), _triple(g))
+    assert np.array_equal(mean2.distances.cpu().numpy(), want_d)
+
+
+def test_decode_known_cases(common):
+    a, b, blank = 0, 1, 3
+    x = np.full((6, 2, 4), -1.0, np.float32)
+    for t, c in enumerate([a, a, blank, a, b, b]):
+        x[t, 0, c] = 2.0
+    x[:, 1, :] = 0.0
+    x[1, 1, 2] = x[1, 1, 3] = 5.0                       # tie between label 2 and blank: first index wins
+    xt = torch.from_numpy(x).cuda()
+    dec, nsl = common.decoding(xt, [6, 2])
+    idx, vals, shape = dec
+    assert vals.tolist() == [a, a, b, 0, 2] and shape.tolist() == [2, 3]
+    assert idx.tolist() == [[0, 0], [0, 1], [0, 2], [1, 0], [1, 1]]
+    assert nsl[:, 0].tolist() == [-12.0, -5.0]
+    dec2, _ = common.decoding(xt, [6, 2], merge_repeated=False)
+    assert dec2.values.tolist() == [a, a, a, b, b, 0, 2]
+    # edit-distance conventions: empty hypothesis -> 1.0; empty truth with non-empty hypothesis -> inf
+    from neuralasr_b200.networks.common import edit_distance
+    hyp = (np.array([[0, 0], [0, 1], [0, 2], [2, 0], [2, 1]], np.int64), np.array([1, 2, 3, 7, 7], np.int64),
+           np.array([4, 3], np.int64))
+    truth = (np.array([[0, 0], [0, 1], [1, 0], [1, 1]], np.int64), np.array([1, 3, 4, 5], np.int32),
+             np.array([4, 2], np.int64))
+    d, ler = edit_distance(hyp, truth)
+    assert d.tolist() == [1, 2, 2, 0]
+    ler = ler.cpu().numpy()
+    assert ler[0] == 0.5 and ler[1] == 1.0 and np.isinf(ler[2]) and ler[3] == 0.0
+
+
+def test_host_buffer_context_matches_device_path(common):
+    import ctypes
+    from neuralasr_b200 import host
+    g = make_batch(77, T=100, B=8, C=38, Lmax=25)
+    ctx = host.HostContext(0, 100, 8, 38, 25)
+    out = ctx.step(g["logits"], g["label_values"], g["label_offsets"], g["seq_len"])
+    loss, grad, status = _run_loss(common, g)
+    assert np.array_equal(out["loss"], loss) and np.array_equal(out["grad"], grad)
+    hv, ho, _ = c_oracle.greedy_decode(g["logits"], g["seq_len"])
+    want_d, want_ler = c_oracle.edit_distance(hv, ho, g["label_values"], g["label_offsets"])
+    assert np.array_equal(out["hyp_len"], np.diff(ho)) and np.array_equal(out["dist"], want_d)
+    assert np.array_equal(out["ler"], want_ler)
+    ctx.close()
+
+
+def test_full_size_properties(common):
+    """BASELINE headline shape: properties that need no oracle pass over the whole batch, plus a
+    sampled oracle check on a few utterances."""
+    g = make_batch(1234, T=1000, B=256, C=38, Lmax=200, mode="full", Lmin=100, empty_row=False)
+    loss, grad, status = _run_loss(common, g)
+    assert (status == 0).all() and np.isfinite(loss).all() and np.isfinite(grad).all()
+    assert np.abs(grad.sum(-1)).max() < 2e-5            # rows of softmax - occupancy sum to zero
+    # occupancy of the blank+labels is a distribution: softmax - grad lies in [0, 1]
+    x = torch.from_numpy(g["logits"]).cuda()
+    occ = torch.softmax(x, -1).cpu().numpy() - grad
+    assert occ.min() > -1e-5 and occ.max() < 1 + 1e-5
+    # expected label counts: sum_t occupancy[t, b, c != blank] >= number of label positions of c ... and
+    # total non-blank occupancy is at least L (each label is emitted at least once)
+    L = np.diff(g["label_offsets"])
+    assert (occ[:, :, :-1].sum((0, 2)) >= L - 1e-2).all()
+    pick = [0, 97, 255]
+    sub_off = np.concatenate([[0], np.cumsum(L[pick])]).astype(np.int32)
+    sub_val = np.concatenate([g["label_values"][g["label_offsets"][b]:g["label_offsets"][b + 1]] for b in pick])
+    wl, wg, _ = c_oracle.ctc_loss_grad(np.ascontiguousarray(g["logits"][:, pick]), sub_val, sub_off,
+                                       g["seq_len"][pick])
+    np.testing.assert_allclose(loss[pick], wl, rtol=LOSS_RTOL)
+    assert np.abs(grad[:, pick] - wg).max() <= GRAD_ATOL
