@@ -4,16 +4,17 @@
 // semantics per SURVEY.md Appendix A.1 (blank passed in, ctc_merge_repeated=True).
 //
 // Number representation ("log-space in the exponent, linear in the mantissa"):
-//   alpha and beta are carried as fp64 values times a power of two that is tracked as an exact
-//   integer (S): stored = true * 2^S.  Every kRescale frames the row is renormalised so its largest
-//   state lies in [1,2) and S absorbs the shift.  The recursion is then 2 adds + 1 multiply per state
-//   (no exp/log on the dependent chain), the dynamic range between states of one frame is 2^-1074..1
-//   (e^-744), and the rounding error does not grow with |loss| the way an fp32 log-space recursion's
-//   does (tests/test_oracle.py shows TF-style fp32 log-space drifting past 1e-4 at T=300).
+//   every alpha/beta state is an fp64 mantissa in [1,2) (or exactly 0) plus its own int32 binary
+//   exponent S (stored = true * 2^S).  A transition aligns its 2-3 inputs to the largest one
+//   (power-of-two multiplies, exact), adds, multiplies by the emission probability and renormalises.
+//   There is no exp/log on the recursion, no range limit (a per-row scale underflows fp64 on long
+//   utterances: at T=1500 the best alpha state and the states that carry the posterior are more than
+//   2^1074 apart), and the rounding error does not grow with |loss| the way an fp32 log-space
+//   recursion's does (tests/test_oracle.py: TF-style fp32 log-space drifts past 1e-4 by T=300).
 //
 // Memory plan (the [T,U] alpha lattice never goes to HBM):
 //   pass 1 (alpha, t ascending)  keeps two rows in shared memory and writes a checkpoint row every K
-//          frames to the workspace (B * ceil(T/K) * U doubles: 51 MB at B=256,T=1000,U=401 — L2 resident);
+//          frames to the workspace (B * ceil(T/K) * U * 12 bytes: 78 MB at B=256,T=1000,U=401 — L2 resident);
 //   pass 2 (beta, t descending, by segments of K frames) reloads the segment's checkpoint, recomputes
 //          its K alpha rows into shared memory, then walks beta backwards through the segment and
 //          emits grad[t,b,:] = grad_loss * (softmax - alpha*beta/p) row by row, coalesced.
@@ -27,7 +28,7 @@ namespace nasr {
 
 namespace {
 
-constexpr int kRescale = 8;           // frames between renormalisations (K is a multiple of it)
+constexpr int kZeroExp = 1 << 28;     // exponent tag of an exactly-zero state (smaller than anything)
 constexpr int kSkipBit = 1 << 30;     // meta[u]: state may take the u-2 transition
 constexpr int kLabelMask = kSkipBit - 1;
 
@@ -38,12 +39,12 @@ struct Plan {
   int Cpad;
   int threads;
   size_t smem;      // dynamic shared memory bytes
-  size_t ws_ckpt;   // bytes of checkpoint rows
-  size_t ws_scale;  // bytes of checkpoint scales
+  size_t ws_ckpt;   // bytes of checkpoint mantissa rows
+  size_t ws_scale;  // bytes of checkpoint exponent rows
 };
 
 struct SmemLayout {
-  size_t seg, row, post, yseg, meta, lab, cls_off, cls_idx, seg_s, red, total;
+  size_t seg, seg_e, row, row_e, post, yseg, meta, lab, cls_off, cls_idx, red, total;
 };
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -52,14 +53,15 @@ __host__ __device__ inline SmemLayout smem_layout(int K, int Upad, int Cpad, int
   SmemLayout s;
   size_t o = 0;
   s.seg = o;      o = align16(o + sizeof(double) * (size_t)K * Upad);
+  s.seg_e = o;    o = align16(o + sizeof(int) * (size_t)K * Upad);
   s.row = o;      o = align16(o + sizeof(double) * 2 * (size_t)Upad);
+  s.row_e = o;    o = align16(o + sizeof(int) * 2 * (size_t)Upad);
   s.post = o;     o = align16(o + sizeof(float) * 2 * (size_t)Upad);
   s.yseg = o;     o = align16(o + sizeof(float) * (size_t)K * Cpad);
   s.meta = o;     o = align16(o + sizeof(int) * (size_t)Upad);
   s.lab = o;      o = align16(o + sizeof(int) * (size_t)(Lmax + 1));
   s.cls_off = o;  o = align16(o + sizeof(int) * (size_t)(Cpad + 2));
   s.cls_idx = o;  o = align16(o + sizeof(int) * (size_t)(Lmax + 1));
-  s.seg_s = o;    o = align16(o + sizeof(int) * (size_t)K);
   s.red = o;      o = align16(o + sizeof(double) * 40);
   s.total = o;
   return s;
@@ -81,7 +83,7 @@ bool make_plan(int T, int B, int C, int Lmax, Plan* p) {
   p->threads = U > 256 ? 512 : (U > 128 ? 256 : 128);
   if (C > 512 && p->threads < 256) p->threads = 256;
   p->ws_ckpt = sizeof(double) * (size_t)B * p->nseg * p->Upad;
-  p->ws_scale = align16(sizeof(int) * (size_t)B * p->nseg);
+  p->ws_scale = align16(sizeof(int) * (size_t)B * p->nseg * p->Upad);
   return true;
 }
 
@@ -131,35 +133,50 @@ __device__ void softmax_rows(const Params& p, int b, int t0, int t1, float* yseg
   }
 }
 
-// Renormalise a row so that its largest element lies in [1,2); returns the exponent removed.
-// Contains one __syncthreads(); the caller must sync again before other threads read the row.
-__device__ int block_rescale(double* row, int U, int* red) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  int mx = 0;
-  for (int u = threadIdx.x; u < U; u += blockDim.x) mx = max(mx, __double2hiint(row[u]));
-  mx = __reduce_max_sync(0xffffffffu, mx);
-  if (lane == 0) red[warp] = mx;
-  __syncthreads();
-  mx = red[lane < nw ? lane : 0];
-  mx = __reduce_max_sync(0xffffffffu, mx);
-  if (mx == 0) return 0;  // all zero (or denormal dust): nothing to normalise
-  int e = ((mx >> 20) & 0x7ff) - 1023;
-  if (e == 0) return 0;
-  e = max(-1022, min(1022, e));
-  const double sc = pow2_double(-e);
-  for (int u = threadIdx.x; u < U; u += blockDim.x) row[u] *= sc;
-  return e;
+// 2^d for d <= 0; exactly 0 once the shift leaves the normal range (the addend is then < 2^-1022 of
+// the value it is aligned to, far below one ulp).
+__device__ __forceinline__ double pow2_down(int d) {
+  return d < -1022 ? 0.0 : __hiloint2double((1023 + d) << 20, 0);
 }
 
-__device__ __forceinline__ void alpha_step(const double* __restrict__ prev, double* __restrict__ cur,
+// Bring v (> 0, normal) into [1,2) and fold the removed exponent into S; zero gets the zero tag.
+__device__ __forceinline__ void renorm(double& v, int& S) {
+  if (v > 0.0) {
+    const int hi = __double2hiint(v);
+    const int e = ((hi >> 20) & 0x7ff) - 1023;
+    v = __hiloint2double((hi & 0x800fffff) | (1023 << 20), __double2loint(v));
+    S -= e;
+  } else {
+    v = 0.0;
+    S = kZeroExp;
+  }
+}
+
+// One alpha frame: cur(u) = y[l'_u] * (prev(u) + prev(u-1) + [skip] prev(u-2)), per-state exponents.
+__device__ __forceinline__ void alpha_step(const double* __restrict__ prev, const int* __restrict__ prevS,
+                                           double* __restrict__ cur, int* __restrict__ curS,
                                            const float* __restrict__ yrow,
                                            const int* __restrict__ meta, int U) {
   for (int u = threadIdx.x; u < U; u += blockDim.x) {
     const int m = meta[u];
-    double s = prev[u];
-    if (u >= 1) s += prev[u - 1];
-    if (m & kSkipBit) s += prev[u - 2];
-    cur[u] = s * (double)yrow[m & kLabelMask];
+    const double v0 = prev[u];
+    const int s0 = prevS[u];
+    double v1 = 0.0, v2 = 0.0;
+    int s1 = kZeroExp, s2 = kZeroExp;
+    if (u >= 1) {
+      v1 = prev[u - 1];
+      s1 = prevS[u - 1];
+    }
+    if (m & kSkipBit) {
+      v2 = prev[u - 2];
+      s2 = prevS[u - 2];
+    }
+    int S = min(s0, min(s1, s2));
+    double acc = v0 * pow2_down(S - s0) + v1 * pow2_down(S - s1) + v2 * pow2_down(S - s2);
+    acc *= (double)yrow[m & kLabelMask];
+    renorm(acc, S);
+    cur[u] = acc;
+    curS[u] = S;
   }
 }
 
@@ -167,16 +184,16 @@ __global__ void __launch_bounds__(512) ctc_loss_grad_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout sl = smem_layout(p.K, p.Upad, p.Cpad, p.Lmax);
   double* seg = reinterpret_cast<double*>(smem + sl.seg);
+  int* segS = reinterpret_cast<int*>(smem + sl.seg_e);
   double* row = reinterpret_cast<double*>(smem + sl.row);
+  int* rowS = reinterpret_cast<int*>(smem + sl.row_e);
   float* post = reinterpret_cast<float*>(smem + sl.post);
   float* yseg = reinterpret_cast<float*>(smem + sl.yseg);
   int* meta = reinterpret_cast<int*>(smem + sl.meta);
   int* lab = reinterpret_cast<int*>(smem + sl.lab);
   int* cls_off = reinterpret_cast<int*>(smem + sl.cls_off);
   int* cls_idx = reinterpret_cast<int*>(smem + sl.cls_idx);
-  int* seg_s = reinterpret_cast<int*>(smem + sl.seg_s);
   int* red = reinterpret_cast<int*>(smem + sl.red);
-  double* red_d = reinterpret_cast<double*>(smem + sl.red) + 20;
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -272,12 +289,13 @@ __global__ void __launch_bounds__(512) ctc_loss_grad_kernel(const Params p) {
   }
 
   double* ckpt = p.ckpt + (size_t)b * p.nseg * Upad;
-  int* ckpt_s = p.ckpt_s + (size_t)b * p.nseg;
+  int* ckptS = p.ckpt_s + (size_t)b * p.nseg * Upad;
 
   // ---- pass 1: alpha, ascending, checkpoints every K frames -----------------------------------
   double* prev = row;
   double* cur = row + Upad;
-  int S = 0;  // stored = true * 2^S
+  int* prevS = rowS;
+  int* curS = rowS + Upad;
   const int nseg = (Tb + K - 1) / K;
   for (int s = 0; s < nseg; s++) {
     const int t0 = s * K, t1 = min(Tb, t0 + K);
@@ -287,28 +305,36 @@ __global__ void __launch_bounds__(512) ctc_loss_grad_kernel(const Params p) {
     for (int t = t0; t < t1; t++) {
       const float* yrow = yseg + (size_t)(t - t0) * p.Cpad;
       if (t == 0) {
-        for (int u = tid; u < U; u += nt)
-          cur[u] = u < 2 ? (double)yrow[meta[u] & kLabelMask] : 0.0;
+        for (int u = tid; u < U; u += nt) {
+          double v = u < 2 ? (double)yrow[meta[u] & kLabelMask] : 0.0;
+          int S = 0;
+          renorm(v, S);
+          cur[u] = v;
+          curS[u] = S;
+        }
       } else {
-        alpha_step(prev, cur, yrow, meta, U);
+        alpha_step(prev, prevS, cur, curS, yrow, meta, U);
+      }
+      if (t == t0) {  // checkpoint = the row of the segment's first frame (own states: no sync needed)
+        for (int u = tid; u < U; u += nt) {
+          ckpt[(size_t)s * Upad + u] = cur[u];
+          ckptS[(size_t)s * Upad + u] = curS[u];
+        }
       }
       __syncthreads();
-      if ((t % kRescale) == kRescale - 1) {
-        S -= block_rescale(cur, U, red);
-        __syncthreads();
-      }
-      if (t == t0) {  // checkpoint = the row of the segment's first frame (after any rescale: none at t0)
-        for (int u = tid; u < U; u += nt) ckpt[(size_t)s * Upad + u] = cur[u];
-        if (tid == 0) ckpt_s[s] = S;
-      }
-      double* tmp = prev;
-      prev = cur;
-      cur = tmp;
+      double* tmp = prev; prev = cur; cur = tmp;
+      int* tmpS = prevS; prevS = curS; curS = tmpS;
     }
   }
-  // prev = alpha row of frame Tb-1
-  const double phat = prev[U - 1] + (U > 1 ? prev[U - 2] : 0.0);
-  const int S_T = S;
+  // prev = alpha row of frame Tb-1: p = alpha(U-1) + alpha(U-2)
+  int S_T = prevS[U - 1];
+  double phat = prev[U - 1];
+  if (U > 1) {
+    const int sb = prevS[U - 2];
+    const int S = min(S_T, sb);
+    phat = phat * pow2_down(S - S_T) + prev[U - 2] * pow2_down(S - sb);
+    S_T = S;
+  }
   __syncthreads();
   if (!(phat > 0.0)) {
     // no valid path: loss = +inf, gradient = softmax
@@ -343,47 +369,62 @@ __global__ void __launch_bounds__(512) ctc_loss_grad_kernel(const Params p) {
   // ---- pass 2: beta, descending by segments, with alpha recompute and gradient emission -----------
   double* bprev = row;
   double* bcur = row + Upad;
-  int Sb = 0;
+  int* bprevS = rowS;
+  int* bcurS = rowS + Upad;
   for (int s = nseg - 1; s >= 0; s--) {
     const int t0 = s * K, t1 = min(Tb, t0 + K);
     __syncthreads();
     softmax_rows(p, b, t0, t1, yseg);
-    for (int u = tid; u < U; u += nt) seg[u] = ckpt[(size_t)s * Upad + u];
-    if (tid == 0) seg_s[0] = ckpt_s[s];
+    for (int u = tid; u < U; u += nt) {
+      seg[u] = ckpt[(size_t)s * Upad + u];
+      segS[u] = ckptS[(size_t)s * Upad + u];
+    }
     __syncthreads();
-    {
-      int Sa = seg_s[0];
-      for (int t = t0 + 1; t < t1; t++) {
-        double* ar = seg + (size_t)(t - t0) * Upad;
-        alpha_step(ar - Upad, ar, yseg + (size_t)(t - t0) * p.Cpad, meta, U);
-        __syncthreads();
-        if ((t % kRescale) == kRescale - 1) {
-          Sa -= block_rescale(ar, U, red);
-          __syncthreads();
-        }
-        if (tid == 0) seg_s[t - t0] = Sa;
-      }
+    for (int t = t0 + 1; t < t1; t++) {
+      const size_t r = (size_t)(t - t0) * Upad;
+      alpha_step(seg + r - Upad, segS + r - Upad, seg + r, segS + r,
+                 yseg + (size_t)(t - t0) * p.Cpad, meta, U);
       __syncthreads();
     }
     for (int t = t1 - 1; t >= t0; t--) {
       const float* yrow = yseg + (size_t)(t - t0) * p.Cpad;
       const double* ar = seg + (size_t)(t - t0) * Upad;
+      const int* arS = segS + (size_t)(t - t0) * Upad;
       float* pt = post + (size_t)(t & 1) * Upad;
-      // factor = 2^(S_T - Sa(t) - Sb) / phat, exponent clamped to the representable range
-      int q = S_T - seg_s[t - t0] - Sb - ep;
-      q = max(-1000, min(1000, q));
-      const double factor = inv_mp * pow2_double(q);
       for (int u = tid; u < U; u += nt) {
         double bv;
+        int S;
         if (t == Tb - 1) {
           bv = (u >= U - 2) ? 1.0 : 0.0;
+          S = (u >= U - 2) ? 0 : kZeroExp;
         } else {
-          bv = bprev[u];
-          if (u + 1 < U) bv += bprev[u + 1];
-          if (u + 2 < U && (meta[u + 2] & kSkipBit)) bv += bprev[u + 2];
+          const double v0 = bprev[u];
+          const int s0 = bprevS[u];
+          double v1 = 0.0, v2 = 0.0;
+          int s1 = kZeroExp, s2 = kZeroExp;
+          if (u + 1 < U) {
+            v1 = bprev[u + 1];
+            s1 = bprevS[u + 1];
+          }
+          if (u + 2 < U && (meta[u + 2] & kSkipBit)) {
+            v2 = bprev[u + 2];
+            s2 = bprevS[u + 2];
+          }
+          S = min(s0, min(s1, s2));
+          bv = v0 * pow2_down(S - s0) + v1 * pow2_down(S - s1) + v2 * pow2_down(S - s2);
         }
-        pt[u] = (float)(ar[u] * bv * factor);
-        bcur[u] = bv * (double)yrow[meta[u] & kLabelMask];
+        // posterior = alpha*beta/p = ar*bv/mp * 2^(S_T - ep - Sa - Sb); it is <= 1, so q <= ~3
+        const int sa = arS[u];
+        float po = 0.f;
+        if (bv > 0.0 && sa != kZeroExp) {
+          const int q = S_T - ep - sa - S;
+          po = (float)(ar[u] * bv * inv_mp * (q > 0 ? pow2_double(min(q, 1000)) : pow2_down(q)));
+        }
+        pt[u] = po;
+        double nb = bv * (double)yrow[meta[u] & kLabelMask];
+        renorm(nb, S);
+        bcur[u] = nb;
+        bcurS[u] = S;
       }
       // gradient row of the previous iteration's frame (t+1): its posteriors are complete
       if (t < t1 - 1) {
@@ -405,13 +446,8 @@ __global__ void __launch_bounds__(512) ctc_loss_grad_kernel(const Params p) {
         }
       }
       __syncthreads();
-      if (((Tb - 1 - t) % kRescale) == kRescale - 1) {
-        Sb -= block_rescale(bcur, U, red);
-        __syncthreads();
-      }
-      double* tmp = bprev;
-      bprev = bcur;
-      bcur = tmp;
+      double* tmp = bprev; bprev = bcur; bcur = tmp;
+      int* tmpS = bprevS; bprevS = bcurS; bcurS = tmpS;
     }
     {  // flush the gradient row of frame t0 before yseg is overwritten
       const int tg = t0;
@@ -432,7 +468,6 @@ __global__ void __launch_bounds__(512) ctc_loss_grad_kernel(const Params p) {
       }
     }
   }
-  (void)red_d;
 }
 
 }  // namespace
@@ -476,7 +511,7 @@ int ctc_loss_grad(const float* logits, int T, int B, int C, const int32_t* label
   p.blank = blank; p.Lmax = Lmax;
   p.loss = loss; p.grad = grad; p.grad_loss = grad_loss; p.status = status;
   p.ckpt_s = reinterpret_cast<int*>(base);
-  p.ckpt = reinterpret_cast<double*>(base + pl.ws_scale);
+  p.ckpt = reinterpret_cast<double*>(base + pl.ws_scale);  // ws_scale is a multiple of 16
   p.K = pl.K; p.nseg = pl.nseg; p.Upad = pl.Upad; p.Cpad = pl.Cpad;
   static bool attr_set = false;
   if (!attr_set) {
