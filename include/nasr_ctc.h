@@ -189,6 +189,16 @@ int nasr_host_ctc_step(nasr_host_ctx* ctx, const float* logits, int T, int B, in
 /* Number of kernel launches this library has enqueued since load (for bench.py's gpu_launches). */
 uint64_t nasr_launch_count(void);
 
+/* Test hook (process-wide, not thread-safe; production code never calls it).
+ * nasr_ctc_loss_grad_* normally runs the throughput kernel and then redoes, with the robust kernel, every
+ * utterance the first one flagged (the flags are the first B int32 of the workspace, 256-byte aligned).
+ *   path 0: that default;  path 1: robust kernel for everything;  path 2: throughput kernel only —
+ *           flagged utterances are left unwritten so a test can see which ones it would have handed over.
+ *   split_frames: 0 = the throughput kernel splits each utterance in the middle; otherwise the number of
+ *           frames its forward half covers (rounded to the chunk size), to exercise uneven splits.
+ * Change it only between calls, and query nasr_ctc_workspace_bytes again afterwards. */
+int nasr_debug_config(int path, int split_frames);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,827 @@
+// Fast CTC loss + d(loss)/d(logits) for sm_100a: one CTA per utterance, eight specialised warps, one launch.
+//
+// Replaces tf.nn.ctc_loss + _CTCLossGrad behind create_loss (reference networks/tfnetwork.py:58-59);
+// semantics per SURVEY.md Appendix A.1.  This is the throughput path; ctc_loss.cu holds the robust
+// kernel (per-state exponents) that redoes any utterance this kernel flags in retry[].
+//
+// Arithmetic (checked on the CPU by tests/model_bfp.py against the oracle):
+//   * linear-domain recursion in "ratio units": every emission is divided by the frame's blank
+//     probability, R[t][c] = y[t][c] / y[t][blank], so blank states need no multiply;
+//     log p gets sum_t log y_blank(t) added back at the end;
+//   * pairs: slot i holds (blank state 2(i-1), label state 2(i-1)+1); lane l of a recursion warp owns the
+//     NL consecutive slots [l*NL, (l+1)*NL) in registers, the s-1/s-2 neighbours of a lane's first slot
+//     arrive by one warp shuffle per frame;
+//   * the backward recursion is the same code on the reversed label string over descending frames;
+//   * block floating point: fp64 values with one int exponent per lane, renormalised at every chunk of
+//     KC frames (fp64 is used for its exponent range, not its mantissa: tools/range_study.py shows states
+//     that carry posterior mass sit up to 2^-170 below their lane maximum on random logits);
+//   * meet in the middle: the forward warp covers frames [0,M) while the backward warp covers [M,Tb);
+//     then each continues through the other half, multiplying its pre-emission sums with the other
+//     direction's rows, which a recompute warp regenerates chunk by chunk from checkpoints
+//     (the [T,U] lattice never goes to memory; a checkpoint is one row per KC frames);
+//   * posterior of a label state = pre-emission sum * other direction's value / p; the blank's occupancy
+//     is 1 - sum of the label occupancies; grad = grad_loss * (softmax - occupancy).
+//   Any event that could invalidate the result (a value flushed below 2^-1022 of its lane scale that may
+//   carry mass, overflow, p = 0, shapes outside the compiled range) raises retry[b] instead.
+//
+// Schedule: all eight warps run one loop of "iterations" separated by __syncthreads; in iteration I
+//   producer warps   turn the logits rows of the chunk used in iteration I+2 into R (double) and softmax
+//                    (float) rows in shared memory, and issue the global loads for iteration I+3;
+//   recompute warps  regenerate the other direction's rows for the chunk consumed in iteration I+1;
+//   recursion warps  advance alpha / beta over the chunk of iteration I (phase 2: emit posteriors);
+//   gradient warps   reduce the posteriors of iteration I-1 by class and write grad rows.
+#include <math.h>
+
+#include "nasr_common.cuh"
+
+namespace nasr {
+namespace fast {
+
+constexpr int KC = 8;            // frames per chunk (= rescale and checkpoint interval)
+constexpr int NTHREADS = 256;    // 8 warps
+constexpr int GCAP = 200;        // a lane with mass sits at most this far below the nearest lane with mass beneath it
+constexpr int GROWTH = 550;      // bits a lane maximum may grow inside one chunk (GCAP of inflow + 350 of emissions)
+// Certificate: a value flushed in a lane of exponent Ea is < 2^(Ea-1022); its partner in the other direction is
+// < 2^(Eb+1+GROWTH); so whatever a flush removes from any posterior (or from p) is below 2^(Ea+Eb-e_p-471),
+// and with at most 2^20 flush events per utterance ZALARM = 400 keeps the total under 2^-50.
+constexpr int ZALARM = 400;
+constexpr int ENEG = -(1 << 24); // exponent tag of a lane that can never receive mass
+
+enum Role { H_F = 0, H_B = 1, RC_F = 2, RC_B = 3, P_F = 4, P_B = 5, G_F = 6, G_B = 7 };
+
+struct Params {
+  const float* logits;
+  int T, B, C;
+  const int32_t* lab_vals;
+  const int32_t* lab_offs;
+  const int32_t* seq_len;
+  int blank;
+  float* loss;
+  float* grad;
+  const float* grad_loss;
+  int32_t* status;
+  int32_t* retry;      // [B] out: 1 = redo this utterance with the robust kernel
+  uint32_t* ckpt;      // [B][2][maxch][(2*NL+1)*32]
+  int maxch;
+  int num_sms;
+  int split;           // debug: frames of the forward half (multiple of KC), 0 = automatic
+};
+
+struct Smem {
+  size_t rows, obuf, gbuf, oexp, meet_nb, meet_pre, meet_e, lab, pos, cls_off, psum, scal, total;
+  int rowbytes;
+  int gstride;  // floats per posterior row: NL*32 cells + one zero cell (+ padding)
+};
+
+__host__ __device__ inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// Row record of one frame: uint32 R_hi[C+1] (high words of the double ratio emissions, last entry 0 for dead
+// slots), then float y[C] (softmax, for the gradient).
+__host__ __device__ inline Smem smem_layout(int NL, int C) {
+  Smem s;
+  s.rowbytes = (int)al16((size_t)(2 * C + 1) * 4);
+  s.gstride = NL * 32 + 4;
+  const int Lcap = NL * 32;
+  size_t o = 0;
+  s.rows = o;      o = al16(o + (size_t)2 * 4 * KC * s.rowbytes);            // [side][4 slots][KC] records
+  s.obuf = o;      o = al16(o + (size_t)2 * 2 * KC * NL * 32 * 4);           // [side][2][KC][NL][32] high words
+  s.gbuf = o;      o = al16(o + (size_t)2 * 2 * KC * s.gstride * 4);         // [side][2][KC][gstride] posteriors
+  s.oexp = o;      o = al16(o + (size_t)2 * 2 * 32 * 4);
+  s.meet_nb = o;   o = al16(o + (size_t)NL * 32 * 8);
+  s.meet_pre = o;  o = al16(o + (size_t)NL * 32 * 8);
+  s.meet_e = o;    o = al16(o + 32 * 4);
+  s.lab = o;       o = al16(o + (size_t)Lcap * 4);
+  s.pos = o;       o = al16(o + (size_t)Lcap * 2);                           // class-sorted rank of label j
+  s.cls_off = o;   o = al16(o + (size_t)(C + 2) * 4);
+  s.psum = o;      o = al16(o + 8 * 8);
+  s.scal = o;      o = al16(o + 64);
+  s.total = o;
+  return s;
+}
+
+// scalars block: [0] alarm (int) [1] e_p (int) [2] rep count (int) [4..5] 1/m_p (double)
+struct Sched {
+  int Tb;
+  int n1[2];    // frames each direction covers in phase 1
+  int nch1[2];  // chunks of phase 1
+  int offB;     // iteration at which the backward warp starts phase 1
+  int P1;       // iteration of the meeting; phase 2 starts at P1 + 1
+  int last;     // last iteration (gradient of the last phase-2 chunk)
+};
+
+struct Chunk {
+  int phase;  // 0 none, 1, 2
+  int idx;    // phase 1: own chunk index; phase 2: the other direction's chunk index
+  int len;    // frames
+  int base;   // frame of position 0; position f is frame base + f (forward) or base - f (backward)
+};
+
+__device__ __forceinline__ Chunk chunk_at(const Sched& S, int d, int J) {
+  Chunk c;
+  c.phase = 0; c.idx = 0; c.len = 0; c.base = 0;
+  const int k = J - (d ? S.offB : 0);
+  if (J >= 0 && k >= 0 && k < S.nch1[d]) {
+    const int tau0 = k * KC;
+    c.phase = 1;
+    c.idx = k;
+    c.len = min(KC, S.n1[d] - tau0);
+    c.base = d ? S.Tb - 1 - tau0 : tau0;
+  } else if (J > S.P1) {
+    const int q = J - S.P1 - 1;
+    const int o = d ^ 1;
+    if (q < S.nch1[o]) {
+      const int j = S.nch1[o] - 1 - q;
+      const int tau0 = j * KC;
+      const int e = min(S.n1[o], tau0 + KC);
+      c.phase = 2;
+      c.idx = j;
+      c.len = e - tau0;
+      c.base = d ? e - 1 : S.Tb - e;
+    }
+  }
+  return c;
+}
+
+__device__ __forceinline__ double pow2d(int e) {  // 2^e, e clamped to the normal range
+  e = max(-1022, min(1023, e));
+  return __hiloint2double((1023 + e) << 20, 0);
+}
+__device__ __forceinline__ double hi2d(uint32_t hi) { return __hiloint2double((int)hi, 0); }
+
+template <int NL>
+struct Dir {
+  double Ab[NL], Al[NL];
+  int E;
+  uint32_t coloff[NL];  // byte offset of R_hi[class of slot k] inside a row record (dead slot: the zero entry)
+  uint32_t mask[NL];    // all-ones if slot k may take the skip transition
+};
+
+// Slot tables and the virtual row before the first frame, for direction d (0 forward, 1 mirrored).
+template <int NL>
+__device__ __forceinline__ void dir_setup(Dir<NL>& s, int d, int lane, const int* lab, int L, int C) {
+  const int N = NL * 32;
+  const int pad = N - L - 1;
+#pragma unroll
+  for (int k = 0; k < NL; k++) {
+    const int i = lane * NL + k;
+    int col = C;  // zero entry
+    bool skip = false;
+    if (d == 0) {
+      const int j = i - 1;
+      if (j >= 0 && j < L) {
+        col = lab[j];
+        skip = j >= 1 && lab[j] != lab[j - 1];
+      }
+    } else {
+      const int m = i - pad;
+      if (m >= 0 && m < L) {
+        col = lab[L - 1 - m];
+        skip = m >= 1 && lab[L - 1 - m] != lab[L - m];
+      }
+    }
+    s.coloff[k] = (uint32_t)col * 4u;
+    s.mask[k] = skip ? 0xffffffffu : 0u;
+    s.Ab[k] = (i == (d == 0 ? 1 : pad)) ? 1.0 : 0.0;
+    s.Al[k] = 0.0;
+  }
+  s.E = 0;
+}
+
+// Alarm reasons (bit mask written to retry[b]; any non-zero value sends the utterance to the robust kernel)
+enum Alarm { AL_SHAPE = 1, AL_EMISSION = 2, AL_NONFINITE = 4, AL_GROWTH = 8, AL_TAG = 16, AL_P = 32, AL_RANGE = 64 };
+
+// Bring the lane maximum back to [1,2) and fold the shift into E.  Two rules keep the factor that carries
+// a value from lane l-1 into lane l representable: a lane with mass sits at most GCAP below the nearest
+// lane with mass beneath it, and a lane without mass adopts that lane's exponent unchanged.
+template <int NL>
+__device__ __forceinline__ void rescale(Dir<NL>& s, int lane, int& alarm) {
+  int mh = 0;
+#pragma unroll
+  for (int k = 0; k < NL; k++) {
+    mh = max(mh, __double2hiint(s.Ab[k]));
+    mh = max(mh, __double2hiint(s.Al[k]));
+  }
+  const int ex = (mh >> 20) & 0x7ff;
+  if (ex == 0x7ff) alarm |= AL_NONFINITE;           // inf / nan: arithmetic broke
+  const bool nz = ex != 0;
+  const int e = ex - 1023;
+  if (nz && e > GROWTH) alarm |= AL_GROWTH;
+  if (nz && s.E == ENEG) alarm |= AL_TAG;           // mass in a lane tagged unreachable: cannot happen
+  const unsigned below = __ballot_sync(0xffffffffu, nz) & (0xffffffffu >> (31 - lane));
+  const int hops = GCAP * __popc(below);            // GCAP per lane with mass at or below this one
+  int v = (nz && s.E != ENEG) ? s.E + e + hops : INT_MIN / 2;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v = max(v, u);
+  }
+  int En = v - hops;
+  if (v < -(1 << 28)) En = ENEG;                    // no mass at or below this lane, ever
+  const double f = (En == ENEG || s.E == ENEG) ? 1.0 : pow2d(s.E - En);
+#pragma unroll
+  for (int k = 0; k < NL; k++) {
+    s.Ab[k] *= f;
+    s.Al[k] *= f;
+  }
+  s.E = En;
+}
+
+// 2^(E[lane-1] - E[lane]): the factor that brings the lower neighbour's last label value into this
+// lane's scale (0 for lane 0 and for neighbours that hold no mass).
+__device__ __forceinline__ double inflow_factor(int E, int lane) {
+  const int Eb = __shfl_up_sync(0xffffffffu, E, 1);
+  if (lane == 0 || Eb == ENEG || E == ENEG) return 0.0;
+  return pow2d(Eb - E);
+}
+
+enum Mode { PLAIN = 0, STORE_O = 1, COMBINE = 2 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v));
+}
+
+// One frame of one direction.  erow: shared address of the frame's row record; orow: shared address of the
+// frame's row of high words ([k][lane]); grow: shared address of the frame's posterior row.
+//   STORE_O : write the high words of the new label values to orow[k][lane]
+//   COMBINE : posterior = pre-emission sum * (other direction's high word at the mirrored slot, shifted by
+//             kshift in the exponent field) -> grow[gphys[k]]
+template <int NL, int MODE>
+__device__ __forceinline__ void step(Dir<NL>& s, uint32_t erow, uint32_t orow, uint32_t grow, double fin,
+                                     int kshift, const uint32_t (&gphys)[NL], int lane) {
+  double a_in = __shfl_up_sync(0xffffffffu, s.Al[NL - 1], 1);
+  a_in = lane ? a_in * fin : 0.0;
+#pragma unroll
+  for (int k = NL - 1; k >= 0; k--) {
+    const double alp = k > 0 ? s.Al[k - 1] : a_in;
+    const double nb = s.Ab[k] + alp;
+    const uint32_t m = s.mask[k];
+    const double w = __hiloint2double(
+        (int)(((uint32_t)__double2hiint(nb) & m) | ((uint32_t)__double2hiint(s.Ab[k]) & ~m)),
+        (int)(((uint32_t)__double2loint(nb) & m) | ((uint32_t)__double2loint(s.Ab[k]) & ~m)));
+    const double q = s.Al[k] + w;
+    const double r = hi2d(lds32(erow + s.coloff[k]));
+    if (MODE == COMBINE) {
+      const int oh = (int)lds32(orow + (uint32_t)(((NL - 1 - k) * 32 + 31) * 4) - (uint32_t)lane * 4u);
+      const double od = __hiloint2double(max(oh + kshift, 0), 0);
+      sts32(grow + gphys[k], __float_as_uint((float)(q * od)));
+    }
+    s.Al[k] = q * r;
+    if (MODE == STORE_O) sts32(orow + (uint32_t)(k * 32) * 4u + (uint32_t)lane * 4u, (uint32_t)__double2hiint(s.Al[k]));
+    s.Ab[k] = nb;
+  }
+}
+
+// Advance one direction over a chunk of `len` frames whose row records start at erows (consumer order).
+// reverse: walk the records backwards (recompute warps run against the consumer's order).
+template <int NL, int MODE>
+__device__ __forceinline__ void run_chunk(Dir<NL>& s, uint32_t erows, int rowbytes, int len, bool reverse,
+                                          uint32_t obuf, uint32_t gbuf, int gstride, double fin, int kshift,
+                                          const uint32_t (&gphys)[NL], int lane) {
+  if (len == KC) {
+#pragma unroll
+    for (int g = 0; g < KC; g++) {
+      const int f = reverse ? KC - 1 - g : g;
+      step<NL, MODE>(s, erows + f * rowbytes, obuf + f * (NL * 32 * 4), gbuf + f * gstride * 4, fin, kshift, gphys,
+                     lane);
+    }
+  } else {
+#pragma unroll 1
+    for (int g = 0; g < len; g++) {
+      const int f = reverse ? len - 1 - g : g;
+      step<NL, MODE>(s, erows + f * rowbytes, obuf + f * (NL * 32 * 4), gbuf + f * gstride * 4, fin, kshift, gphys,
+                     lane);
+    }
+  }
+}
+
+template <int NL>
+__device__ __forceinline__ uint32_t* ckpt_ptr(const Params& p, int b, int d, int c) {
+  return p.ckpt + (((size_t)b * 2 + d) * p.maxch + c) * (size_t)((2 * NL + 1) * 32);
+}
+
+// physical cell of class-sorted position pos in a posterior row: [pos % NL][pos / NL], so that the gradient
+// warp's lane l finds its NL consecutive positions l*NL .. l*NL+NL-1 at stride 32 (no bank conflicts)
+template <int NL>
+__device__ __forceinline__ uint32_t gcell(int pos) {
+  return (uint32_t)((pos % NL) * 32 + pos / NL);
+}
+
+template <int NL, int EPL>
+__global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(const Params p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Smem sl = smem_layout(NL, p.C);
+  unsigned char* s_rows = smem + sl.rows;
+  uint32_t* s_obuf = reinterpret_cast<uint32_t*>(smem + sl.obuf);
+  float* s_gbuf = reinterpret_cast<float*>(smem + sl.gbuf);
+  int* s_oexp = reinterpret_cast<int*>(smem + sl.oexp);
+  double* s_meet_nb = reinterpret_cast<double*>(smem + sl.meet_nb);
+  double* s_meet_pre = reinterpret_cast<double*>(smem + sl.meet_pre);
+  int* s_meet_e = reinterpret_cast<int*>(smem + sl.meet_e);
+  int* s_lab = reinterpret_cast<int*>(smem + sl.lab);
+  uint16_t* s_pos = reinterpret_cast<uint16_t*>(smem + sl.pos);
+  int* s_cls_off = reinterpret_cast<int*>(smem + sl.cls_off);
+  double* s_psum = reinterpret_cast<double*>(smem + sl.psum);
+  int* s_scal = reinterpret_cast<int*>(smem + sl.scal);
+  double* s_inv_mp = reinterpret_cast<double*>(smem + sl.scal + 16);
+
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = p.T, B = p.B, C = p.C, blank = p.blank;
+  const int rowbytes = sl.rowbytes;
+  const int gstride = sl.gstride;
+  constexpr int N = NL * 32;
+  constexpr int Lcap = N - 2;
+  constexpr int OBUF = KC * NL * 32;  // words per buffer of high words
+  const int GBUF = KC * gstride;      // floats per posterior buffer
+
+  const int Tb = p.seq_len[b];
+  const int l0 = p.lab_offs[b];
+  const int L = p.lab_offs[b + 1] - l0;
+
+  // ---- can this kernel take the utterance? everything unusual goes to the robust kernel -----------
+  int bad = (Tb < 2 * KC) | (Tb > T) | (L < 0) | (L > Lcap);
+  if (tid < 8) {
+    s_scal[tid] = 0;
+    s_psum[tid] = 0.0;
+  }
+  for (int c = tid; c < C + 2; c += NTHREADS) s_cls_off[c] = 0;
+  __syncthreads();
+  int rep = 0;
+  if (!bad) {
+    for (int i = tid; i < L; i += NTHREADS) {
+      const int v = p.lab_vals[l0 + i];
+      s_lab[i] = v;
+      if (v < 0 || v >= C || v == blank) {
+        bad = 1;
+      } else {
+        atomicAdd(&s_cls_off[v + 1], 1);
+        if (i > 0 && v == p.lab_vals[l0 + i - 1]) rep++;
+      }
+    }
+  }
+  if (rep) atomicAdd(&s_scal[2], rep);
+  bad = __syncthreads_or(bad);
+  if (!bad && Tb < L + s_scal[2]) bad = 1;
+  if (bad) {
+    if (tid == 0) p.retry[b] = AL_SHAPE;
+    return;
+  }
+
+  // ---- class-sorted rank of every label (the order the gradient warps reduce in) -----------------
+  if (warp == 0) {
+    const int per = (C + 1 + 31) / 32;
+    const int lo = min(C + 1, lane * per), hi = min(C + 1, lo + per);
+    int s = 0;
+    for (int i = lo; i < hi; i++) s += s_cls_off[i];
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    int run = incl - s;
+    for (int i = lo; i < hi; i++) {
+      run += s_cls_off[i];
+      s_cls_off[i] = run;
+    }
+  }
+  __syncthreads();
+  // s_cls_off[c] = number of labels with class < c
+  for (int j = tid; j < L; j += NTHREADS) {
+    const int v = s_lab[j];
+    int r = 0;
+    for (int i = 0; i < j; i++) r += (s_lab[i] == v);
+    s_pos[j] = (uint16_t)(s_cls_off[v] + r);
+  }
+  // the zero cell of every posterior row (prefix "before position 0")
+  for (int i = tid; i < 2 * 2 * KC; i += NTHREADS) {
+    float* row = s_gbuf + (size_t)i * gstride;
+    row[N] = 0.f;
+  }
+
+  // ---- gradient rows of padded frames are exactly zero -----------------------------------------
+  const size_t rstride = (size_t)B * C;
+  float* gbase = p.grad ? p.grad + (size_t)b * C : nullptr;
+  if (gbase) {
+    const size_t n = (size_t)(T - Tb) * C;
+    for (size_t i = tid; i < n; i += NTHREADS) {
+      const size_t t = Tb + i / C;
+      gbase[t * rstride + (i % C)] = 0.f;
+    }
+  }
+
+  // ---- schedule -----------------------------------------------------------------------------
+  Sched S;
+  S.Tb = Tb;
+  {
+    int nf = KC * ((Tb + 2 * KC - 1) / (2 * KC));
+    if (p.split > 0) nf = min(max(KC, (p.split / KC) * KC), ((Tb - 1) / KC) * KC);
+    S.n1[0] = nf;
+    S.n1[1] = Tb - nf;
+    S.nch1[0] = (S.n1[0] + KC - 1) / KC;
+    S.nch1[1] = (S.n1[1] + KC - 1) / KC;
+    S.P1 = max(S.nch1[0], S.nch1[1]);
+    S.offB = S.P1 - S.nch1[1];
+    S.last = gbase ? S.P1 + 1 + max(S.nch1[0], S.nch1[1]) : S.P1;
+  }
+  const bool want_grad = gbase != nullptr;
+  const float gs = p.grad_loss ? p.grad_loss[b] : 1.0f;
+
+  // roles: the second CTA that lands on an SM swaps recursion and recompute warps (and producer and
+  // gradient warps) so that the four heavy warps of phase 1 sit on four different schedulers
+  const int perm = (blockIdx.x / max(1, p.num_sms)) & 1;
+  const int role = warp ^ (perm << 1);
+  const int d = role & 1;  // direction / side this warp works for
+  __syncthreads();
+
+  Dir<NL> st;
+  uint32_t gphys[NL];  // recursion warps: byte offset of slot k's posterior inside a posterior row
+  if (role <= RC_B) {
+    dir_setup<NL>(st, d, lane, s_lab, L, C);
+    const int pad = N - L - 1;
+#pragma unroll
+    for (int k = 0; k < NL; k++) {
+      const int i = lane * NL + k;
+      int pos;
+      if (d == 0) {
+        const int j = i - 1;
+        pos = (j >= 0 && j < L) ? (int)s_pos[j] : (i == 0 ? L : i);
+      } else {
+        const int m = i - pad;
+        pos = (m >= 0 && m < L) ? (int)s_pos[L - 1 - m] : (i < pad ? L + i : N - 1);
+      }
+      gphys[k] = gcell<NL>(pos) * 4u;
+    }
+  }
+  // gradient warps: cells holding the inclusive prefix at the end of each of this lane's two classes
+  uint32_t pc_lo0 = N * 4u, pc_hi0 = N * 4u, pc_lo1 = N * 4u, pc_hi1 = N * 4u, pc_tot = N * 4u;
+  if (role >= G_F) {
+    const int c0 = lane, c1 = lane + 32;
+    if (c0 < C && c0 != blank) {
+      const int lo = s_cls_off[c0], hi = s_cls_off[c0 + 1];
+      if (lo > 0) pc_lo0 = gcell<NL>(lo - 1) * 4u;
+      if (hi > 0) pc_hi0 = gcell<NL>(hi - 1) * 4u;
+    }
+    if (c1 < C && c1 != blank) {
+      const int lo = s_cls_off[c1], hi = s_cls_off[c1 + 1];
+      if (lo > 0) pc_lo1 = gcell<NL>(lo - 1) * 4u;
+      if (hi > 0) pc_hi1 = gcell<NL>(hi - 1) * 4u;
+    }
+    if (L > 0) pc_tot = gcell<NL>(L - 1) * 4u;
+  }
+  int alarm = 0;
+  bool scaled = false;     // recursion warps: state already divided by the mantissa of p
+  float xr[KC / 4][EPL];   // producer: raw logits of the chunk in flight
+#pragma unroll
+  for (int g = 0; g < KC / 4; g++)
+#pragma unroll
+    for (int e = 0; e < EPL; e++) xr[g][e] = 0.f;
+  double lsum = 0.0;        // producer: sum of log y_blank over the phase-1 rows this lane group owned
+
+#pragma unroll 1
+  for (int I = -3; I <= S.last; I++) {
+    if (role == H_F || role == H_B) {
+      // ======================= recursion warps =======================
+      const Chunk ci = chunk_at(S, d, I);
+      const uint32_t erows = smem_u32(s_rows + (size_t)(d * 4 + (I & 3)) * KC * rowbytes);
+      if (ci.phase == 1) {
+        rescale<NL>(st, lane, alarm);
+        uint32_t* ck = ckpt_ptr<NL>(p, b, d, ci.idx);
+#pragma unroll
+        for (int k = 0; k < NL; k++) {
+          ck[k * 32 + lane] = (uint32_t)__double2hiint(st.Ab[k]);
+          ck[(NL + k) * 32 + lane] = (uint32_t)__double2hiint(st.Al[k]);
+        }
+        ck[2 * NL * 32 + lane] = (uint32_t)st.E;
+        const double fin = inflow_factor(st.E, lane);
+        run_chunk<NL, PLAIN>(st, erows, rowbytes, ci.len, false, 0u, 0u, gstride, fin, 0, gphys, lane);
+        if (d == 1 && I == S.P1 - 1) {
+          // pre-emission sums of the frame below the meeting point, for the forward warp
+          rescale<NL>(st, lane, alarm);
+          const double fin2 = inflow_factor(st.E, lane);
+          double a_in = __shfl_up_sync(0xffffffffu, st.Al[NL - 1], 1);
+          a_in = lane ? a_in * fin2 : 0.0;
+#pragma unroll
+          for (int k = NL - 1; k >= 0; k--) {
+            const double alp = k > 0 ? st.Al[k - 1] : a_in;
+            const double nb = st.Ab[k] + alp;
+            const double pre = st.Al[k] + (st.mask[k] ? nb : st.Ab[k]);
+            s_meet_nb[k * 32 + lane] = nb;
+            s_meet_pre[k * 32 + lane] = pre;
+          }
+          s_meet_e[lane] = st.E;
+        }
+      } else if (I == S.P1 && d == 0) {
+        // ---- meeting: p = sum over states of alpha(M-1) * beta(M-1) ----
+        rescale<NL>(st, lane, alarm);
+        const int lm = 31 - lane;
+        const int Eb1 = s_meet_e[lm];
+        double S1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < NL; k++) S1 += st.Al[k] * s_meet_pre[(NL - 1 - k) * 32 + lm];
+#pragma unroll
+        for (int k = 1; k < NL; k++) S1 += st.Ab[k] * s_meet_nb[(NL - k) * 32 + lm];
+        double S2 = 0.0;
+        int Eb2 = ENEG;
+        if (lane >= 1) {
+          S2 = st.Ab[0] * s_meet_nb[32 - lane];
+          Eb2 = s_meet_e[32 - lane];
+        }
+        const bool ok1 = S1 > 0.0 && st.E != ENEG && Eb1 != ENEG;
+        const bool ok2 = S2 > 0.0 && st.E != ENEG && Eb2 != ENEG;
+        const int K1 = st.E + Eb1, K2 = st.E + Eb2;
+        const int X1 = ok1 ? K1 + (((__double2hiint(S1) >> 20) & 0x7ff) - 1023) : INT_MIN / 2;
+        const int X2 = ok2 ? K2 + (((__double2hiint(S2) >> 20) & 0x7ff) - 1023) : INT_MIN / 2;
+        int Xm = max(X1, X2);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) Xm = max(Xm, __shfl_xor_sync(0xffffffffu, Xm, o));
+        double tot = 0.0;
+        if (ok1) tot += S1 * pow2d(K1 - Xm);
+        if (ok2) tot += S2 * pow2d(K2 - Xm);
+        tot = warp_sum(tot);
+        if (!(tot > 0.0) || !(tot < 1e300) || Xm < -(1 << 28)) {
+          alarm |= AL_P;
+          tot = 1.0;
+          Xm = 0;
+        }
+        const int et = ((__double2hiint(tot) >> 20) & 0x7ff) - 1023;
+        const double mp = tot * pow2d(-et);
+        double ls = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) ls += s_psum[i];
+        if (lane == 0) {
+          s_scal[1] = Xm + et;
+          *s_inv_mp = 1.0 / mp;
+          p.loss[b] = (float)(-((double)Xm * 0.6931471805599453 + log(tot) + ls));
+          p.status[b] = 0;
+        }
+      } else if (ci.phase == 2 && want_grad) {
+        if (!scaled) {
+          // the recursion is linear: dividing the state by the mantissa of p once makes every later
+          // pre-emission sum carry the 1/m_p factor of the posterior
+          const double im = *s_inv_mp;
+#pragma unroll
+          for (int k = 0; k < NL; k++) {
+            st.Ab[k] *= im;
+            st.Al[k] *= im;
+          }
+          scaled = true;
+        }
+        rescale<NL>(st, lane, alarm);
+        const double fin = inflow_factor(st.E, lane);
+        const int buf = I & 1;
+        const int Eo = s_oexp[(d * 2 + buf) * 32 + (31 - lane)];
+        int ks = -2047;
+        if (Eo != ENEG && st.E != ENEG) {
+          ks = st.E + Eo - s_scal[1];
+          if (ks > ZALARM) alarm |= AL_RANGE;
+          ks = max(-2047, min(ks, 600));
+        }
+        run_chunk<NL, COMBINE>(st, erows, rowbytes, ci.len, false, smem_u32(s_obuf + (size_t)(d * 2 + buf) * OBUF),
+                               smem_u32(s_gbuf + (size_t)(d * 2 + buf) * GBUF), gstride, fin, ks * (1 << 20), gphys,
+                               lane);
+      }
+    } else if (role == RC_F || role == RC_B) {
+      // ======================= recompute warps =======================
+      // this warp computes direction d's rows; they are consumed by the other direction (side d^1)
+      const int side = d ^ 1;
+      const Chunk ci = chunk_at(S, side, I + 1);
+      if (ci.phase == 2 && want_grad) {
+        const uint32_t* ck = ckpt_ptr<NL>(p, b, d, ci.idx);
+#pragma unroll
+        for (int k = 0; k < NL; k++) {
+          st.Ab[k] = hi2d(__ldcg(ck + k * 32 + lane));
+          st.Al[k] = hi2d(__ldcg(ck + (NL + k) * 32 + lane));
+        }
+        st.E = (int)__ldcg(ck + 2 * NL * 32 + lane);
+        const double fin = inflow_factor(st.E, lane);
+        const int buf = (I + 1) & 1;
+        s_oexp[(side * 2 + buf) * 32 + lane] = st.E;
+        const uint32_t erows = smem_u32(s_rows + (size_t)(side * 4 + ((I + 1) & 3)) * KC * rowbytes);
+        run_chunk<NL, STORE_O>(st, erows, rowbytes, ci.len, true, smem_u32(s_obuf + (size_t)(side * 2 + buf) * OBUF),
+                               0u, gstride, fin, 0, gphys, lane);
+      }
+    } else if (role == P_F || role == P_B) {
+      // ======================= producer warps =======================
+      const int sub = lane & 7, rl = lane >> 3;
+      {  // rows loaded in the previous iteration -> shared memory (chunk of iteration I+2)
+        const Chunk ci = chunk_at(S, d, I + 2);
+        if (ci.phase != 0 && (ci.phase == 1 || want_grad)) {
+          unsigned char* rows = s_rows + (size_t)(d * 4 + ((I + 2) & 3)) * KC * rowbytes;
+#pragma unroll
+          for (int g = 0; g < KC / 4; g++) {
+            const int f = g * 4 + rl;
+            const bool valid = f < ci.len;
+            float m = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < EPL; e++)
+              if (sub + 8 * e < C) m = fmaxf(m, xr[g][e]);
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            float n[EPL];
+            float ssum = 0.f, nbl = 0.f, xbl = 0.f;
+#pragma unroll
+            for (int e = 0; e < EPL; e++) {
+              const int c = sub + 8 * e;
+              n[e] = c < C ? __expf(xr[g][e] - m) : 0.f;
+              ssum += n[e];
+              if (c == blank) {
+                nbl = n[e];
+                xbl = xr[g][e];
+              }
+            }
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, 4);
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
+            const int src = (lane & ~7) | (blank & 7);
+            nbl = __shfl_sync(0xffffffffu, nbl, src);
+            const float inv_s = __fdividef(1.0f, ssum);
+            const float inv_nb = 1.0f / nbl;
+            unsigned char* row = rows + (size_t)f * rowbytes;
+            uint32_t* Rrow = reinterpret_cast<uint32_t*>(row);
+            float* yrow = reinterpret_cast<float*>(row + (size_t)(C + 1) * 4);
+            if (valid) {
+#pragma unroll
+              for (int e = 0; e < EPL; e++) {
+                const int c = sub + 8 * e;
+                if (c < C) {
+                  const float r = n[e] * inv_nb;
+                  // the recursion needs a normal float: anything else (blank or class probability
+                  // underflowed, inf, nan) is the robust kernel's business
+                  if (!(r >= 1.1754944e-38f && r <= 1.0e38f)) alarm |= AL_EMISSION;
+                  // high word of (double)r, rounded to nearest at the 20 mantissa bits it keeps
+                  Rrow[c] = ((__float_as_uint(r) + 4u) >> 3) + (896u << 20);
+                  yrow[c] = n[e] * inv_s;
+                }
+              }
+              if (sub == 0) Rrow[C] = 0u;
+              if (ci.phase == 1 && sub == (blank & 7)) lsum += (double)((xbl - m) - __logf(ssum));
+            }
+          }
+          if (sub == (blank & 7)) s_psum[d * 4 + rl] = lsum;
+        }
+      }
+      {  // issue the loads for the chunk of iteration I+3
+        const Chunk ci = chunk_at(S, d, I + 3);
+        if (ci.phase != 0 && (ci.phase == 1 || want_grad)) {
+#pragma unroll
+          for (int g = 0; g < KC / 4; g++) {
+            const int f = g * 4 + rl;
+            if (f < ci.len) {
+              const int t = d ? ci.base - f : ci.base + f;
+              const float* x = p.logits + ((size_t)t * B + b) * C;
+#pragma unroll
+              for (int e = 0; e < EPL; e++) {
+                const int c = sub + 8 * e;
+                xr[g][e] = c < C ? __ldg(x + c) : 0.f;
+              }
+            }
+          }
+        }
+      }
+    } else {
+      // ======================= gradient warps =======================
+      // posterior rows are in class-sorted order: an inclusive prefix sum turns "occupancy of class c" into
+      // the difference of two prefixes
+      const Chunk ci = chunk_at(S, d, I - 1);
+      if (ci.phase == 2 && want_grad) {
+        const int buf = (I - 1) & 1;
+        const uint32_t G = smem_u32(s_gbuf + (size_t)(d * 2 + buf) * GBUF);
+        const unsigned char* rows = s_rows + (size_t)(d * 4 + ((I - 1) & 3)) * KC * rowbytes;
+        const int c0 = lane, c1 = lane + 32;
+#pragma unroll 2
+        for (int f = 0; f < ci.len; f++) {
+          const int t = d ? ci.base - f : ci.base + f;
+          const uint32_t Gr = G + (uint32_t)(f * gstride * 4);
+          const float* yrow = reinterpret_cast<const float*>(rows + (size_t)f * rowbytes + (size_t)(C + 1) * 4);
+          float v[NL];
+#pragma unroll
+          for (int i = 0; i < NL; i++) v[i] = __uint_as_float(lds32(Gr + (uint32_t)(i * 32 * 4) + (uint32_t)lane * 4u));
+#pragma unroll
+          for (int i = 1; i < NL; i++) v[i] += v[i - 1];
+          float inc = v[NL - 1];
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const float u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+          }
+          const float base = inc - v[NL - 1];
+#pragma unroll
+          for (int i = 0; i < NL; i++) sts32(Gr + (uint32_t)(i * 32 * 4) + (uint32_t)lane * 4u, __float_as_uint(v[i] + base));
+          __syncwarp();
+          const float o0 = __uint_as_float(lds32(Gr + pc_hi0)) - __uint_as_float(lds32(Gr + pc_lo0));
+          const float o1 = __uint_as_float(lds32(Gr + pc_hi1)) - __uint_as_float(lds32(Gr + pc_lo1));
+          const float tot = __uint_as_float(lds32(Gr + pc_tot));
+          float* g = gbase + (size_t)t * rstride;
+          if (c0 < C) g[c0] = gs * (yrow[c0] - (c0 == blank ? 1.0f - tot : o0));
+          if (c1 < C) g[c1] = gs * (yrow[c1] - (c1 == blank ? 1.0f - tot : o1));
+          __syncwarp();
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (alarm) atomicOr(&s_scal[0], alarm);
+  __syncthreads();
+  if (tid == 0) p.retry[b] = s_scal[0];
+}
+
+}  // namespace fast
+
+// ---- host side -------------------------------------------------------------------------------
+
+namespace {
+
+int pick_nl(int Lmax) {
+  static const int kNL[] = {2, 4, 5, 7, 10, 20};
+  for (int nl : kNL)
+    if (Lmax <= nl * 32 - 2) return nl;
+  return 0;
+}
+
+template <int NL, int EPL>
+int launch_fast(const fast::Params& p, cudaStream_t stream) {
+  const fast::Smem sl = fast::smem_layout(NL, p.C);
+  static bool attr_set = false;
+  if (!attr_set) {
+    NASR_CUDA(cudaFuncSetAttribute(fast::ctc_fast_kernel<NL, EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   200 * 1024));
+    attr_set = true;
+  }
+  if (sl.total > 200 * 1024) {
+    set_error("nasr_ctc: fast kernel shared memory %zu too large", sl.total);
+    return NASR_ERR_UNSUPPORTED;
+  }
+  fast::ctc_fast_kernel<NL, EPL><<<p.B, fast::NTHREADS, sl.total, stream>>>(p);
+  count_launch();
+  NASR_CUDA(cudaGetLastError());
+  return NASR_OK;
+}
+
+template <int NL>
+int launch_fast_c(const fast::Params& p, cudaStream_t stream) {
+  if (p.C <= 40) return launch_fast<NL, 5>(p, stream);
+  return launch_fast<NL, 8>(p, stream);
+}
+
+}  // namespace
+
+int g_debug_split = 0;  // test hook (nasr_debug_config): frames of the forward half, 0 = automatic
+
+static int max_chunks(int T) {
+  // chunks one direction can own in phase 1: half the frames normally, all of them under a split override
+  const int half = (T + 2 * fast::KC - 1) / (2 * fast::KC) + 2;
+  return g_debug_split ? (T + fast::KC - 1) / fast::KC + 2 : half;
+}
+
+bool ctc_fast_supported(int T, int C, int Lmax) {
+  return T >= 2 * fast::KC && C <= 64 && pick_nl(Lmax) != 0;
+}
+
+size_t ctc_fast_workspace_bytes(int T, int B, int C, int Lmax) {
+  if (!ctc_fast_supported(T, C, Lmax)) return 0;
+  const int NL = pick_nl(Lmax);
+  return (size_t)B * 2 * max_chunks(T) * (2 * NL + 1) * 32 * sizeof(uint32_t);
+}
+
+int ctc_fast_launch(const float* logits, int T, int B, int C, const int32_t* label_values,
+                    const int32_t* label_offsets, int Lmax, const int32_t* seq_len, int blank, float* loss,
+                    float* grad, const float* grad_loss, int32_t* status, int32_t* retry, void* ckpt,
+                    cudaStream_t stream) {
+  fast::Params p;
+  p.logits = logits; p.T = T; p.B = B; p.C = C;
+  p.lab_vals = label_values; p.lab_offs = label_offsets; p.seq_len = seq_len;
+  p.blank = blank; p.loss = loss; p.grad = grad; p.grad_loss = grad_loss; p.status = status;
+  p.retry = retry;
+  p.ckpt = static_cast<uint32_t*>(ckpt);
+  p.maxch = max_chunks(T);
+  p.split = g_debug_split;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    NASR_CUDA(cudaGetDevice(&dev));
+    NASR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  p.num_sms = num_sms;
+  switch (pick_nl(Lmax)) {
+    case 2: return launch_fast_c<2>(p, stream);
+    case 4: return launch_fast_c<4>(p, stream);
+    case 5: return launch_fast_c<5>(p, stream);
+    case 7: return launch_fast_c<7>(p, stream);
+    case 10: return launch_fast_c<10>(p, stream);
+    case 20: return launch_fast_c<20>(p, stream);
+  }
+  set_error("nasr_ctc: fast kernel does not support max_label_len=%d", Lmax);
+  return NASR_ERR_UNSUPPORTED;
+}
+
+}  // namespace nasr

@@ -1,4 +1,7 @@
-// CTC loss + d(loss)/d(logits) for sm_100a: one CTA per utterance, one launch per batch.
+// CTC loss + d(loss)/d(logits) for sm_100a — the ROBUST kernel and the dispatcher.
+// One CTA per utterance.  The throughput path is ctc_fast.cu; this kernel takes what that one cannot
+// (shapes outside its compiled range, TF's error cases, and every utterance it flags in retry[]):
+// per-state exponents make it immune to any dynamic range.
 //
 // Replaces tf.nn.ctc_loss + _CTCLossGrad behind create_loss (reference networks/tfnetwork.py:58-59);
 // semantics per SURVEY.md Appendix A.1 (blank passed in, ctc_merge_repeated=True).
@@ -102,6 +105,7 @@ struct Params {
   double* ckpt;
   int* ckpt_s;
   int K, nseg, Upad, Cpad;
+  const int32_t* only_if;  // non-NULL: process utterance b only if only_if[b] != 0 (retry pass)
 };
 
 __device__ __forceinline__ double pow2_double(int e) {  // 2^e for e in [-1022, 1023]
@@ -180,8 +184,9 @@ __device__ __forceinline__ void alpha_step(const double* __restrict__ prev, cons
   }
 }
 
-__global__ void __launch_bounds__(512) ctc_loss_grad_kernel(const Params p) {
+__global__ void __launch_bounds__(512) ctc_robust_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem[];
+  if (p.only_if && p.only_if[blockIdx.x] == 0) return;
   const SmemLayout sl = smem_layout(p.K, p.Upad, p.Cpad, p.Lmax);
   double* seg = reinterpret_cast<double*>(smem + sl.seg);
   int* segS = reinterpret_cast<int*>(smem + sl.seg_e);
@@ -472,6 +477,19 @@ __global__ void __launch_bounds__(512) ctc_loss_grad_kernel(const Params p) {
 
 }  // namespace
 
+// implemented in ctc_fast.cu
+bool ctc_fast_supported(int T, int C, int Lmax);
+size_t ctc_fast_workspace_bytes(int T, int B, int C, int Lmax);
+int ctc_fast_launch(const float* logits, int T, int B, int C, const int32_t* label_values,
+                    const int32_t* label_offsets, int Lmax, const int32_t* seq_len, int blank, float* loss,
+                    float* grad, const float* grad_loss, int32_t* status, int32_t* retry, void* ckpt,
+                    cudaStream_t stream);
+
+int g_debug_path = 0;  // test hook (nasr_debug_config): 0 fast + retry, 1 robust only, 2 fast only
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// workspace = [retry flags int32[B]] [fast checkpoints] [robust exponents] [robust mantissas]
 int ctc_workspace_bytes(int T, int B, int C, int Lmax, size_t* out) {
   Plan pl;
   if (!make_plan(T, B, C, Lmax, &pl)) {
@@ -479,7 +497,8 @@ int ctc_workspace_bytes(int T, int B, int C, int Lmax, size_t* out) {
               T, C, Lmax);
     return NASR_ERR_UNSUPPORTED;
   }
-  *out = pl.ws_ckpt + pl.ws_scale + 256;
+  *out = 256 + align256(sizeof(int32_t) * (size_t)B) + align256(ctc_fast_workspace_bytes(T, B, C, Lmax)) +
+         pl.ws_ckpt + pl.ws_scale;
   return NASR_OK;
 }
 
@@ -499,12 +518,25 @@ int ctc_loss_grad(const float* logits, int T, int B, int C, const int32_t* label
     set_error("nasr_ctc_loss_grad: shapes T=%d C=%d max_label_len=%d exceed shared memory", T, C, Lmax);
     return NASR_ERR_UNSUPPORTED;
   }
-  const size_t need = pl.ws_ckpt + pl.ws_scale + 256;
+  size_t need = 0;
+  ctc_workspace_bytes(T, B, C, Lmax, &need);
   if (workspace_bytes < need || !workspace) {
     set_error("nasr_ctc_loss_grad: workspace too small (%zu < %zu)", workspace_bytes, need);
     return NASR_ERR_WORKSPACE_TOO_SMALL;
   }
   uintptr_t base = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
+  int32_t* retry = reinterpret_cast<int32_t*>(base);
+  base += align256(sizeof(int32_t) * (size_t)B);
+  void* fast_ckpt = reinterpret_cast<void*>(base);
+  base += align256(ctc_fast_workspace_bytes(T, B, C, Lmax));
+
+  const bool use_fast = g_debug_path != 1 && ctc_fast_supported(T, C, Lmax);
+  if (use_fast) {
+    int rc = ctc_fast_launch(logits, T, B, C, label_values, label_offsets, Lmax, seq_len, blank, loss, grad,
+                             grad_loss, status, retry, fast_ckpt, stream);
+    if (rc != NASR_OK) return rc;
+    if (g_debug_path == 2) return NASR_OK;  // test hook: leave flagged utterances alone (retry[] tells which)
+  }
   Params p;
   p.logits = logits; p.T = T; p.B = B; p.C = C;
   p.lab_vals = label_values; p.lab_offs = label_offsets; p.seq_len = seq_len;
@@ -513,16 +545,22 @@ int ctc_loss_grad(const float* logits, int T, int B, int C, const int32_t* label
   p.ckpt_s = reinterpret_cast<int*>(base);
   p.ckpt = reinterpret_cast<double*>(base + pl.ws_scale);  // ws_scale is a multiple of 16
   p.K = pl.K; p.nseg = pl.nseg; p.Upad = pl.Upad; p.Cpad = pl.Cpad;
+  p.only_if = use_fast ? retry : nullptr;
   static bool attr_set = false;
   if (!attr_set) {
-    NASR_CUDA(cudaFuncSetAttribute(ctc_loss_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NASR_CUDA(cudaFuncSetAttribute(ctc_robust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)kSmemBudget));
     attr_set = true;
   }
-  ctc_loss_grad_kernel<<<B, pl.threads, pl.smem, stream>>>(p);
+  ctc_robust_kernel<<<B, pl.threads, pl.smem, stream>>>(p);
   count_launch();
   NASR_CUDA(cudaGetLastError());
   return NASR_OK;
+}
+
+// Test hook: copy of the retry flags of the last fast launch lives at the start of the workspace.
+const int32_t* ctc_retry_flags(void* workspace) {
+  return reinterpret_cast<const int32_t*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
 }
 
 }  // namespace nasr

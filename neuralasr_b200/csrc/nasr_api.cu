@@ -39,6 +39,8 @@ int hyp_to_sparse(const int64_t* hyp, int hyp_stride, const int32_t* hyp_offsets
                   int64_t* indices, int64_t* values, int64_t* dense_shape, cudaStream_t stream);
 int batch_sums(const float* loss, const float* ler, const int32_t* dist, int B, double* sums,
                cudaStream_t stream);
+extern int g_debug_path;   // ctc_loss.cu
+extern int g_debug_split;  // ctc_fast.cu
 
 namespace {
 
@@ -119,6 +121,13 @@ int nasr_abi_version(void) { return NASR_ABI_VERSION; }
 const char* nasr_last_error(void) { return t_err; }
 
 uint64_t nasr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int nasr_debug_config(int path, int split_frames) {
+  NASR_CHECK_ARG(path >= 0 && path <= 2 && split_frames >= 0, "nasr_debug_config: bad arguments");
+  g_debug_path = path;
+  g_debug_split = split_frames;
+  return NASR_OK;
+}
 
 int nasr_ctc_workspace_bytes(int T, int B, int C, int max_label_len, size_t* out_bytes) {
   NASR_CHECK_ARG(out_bytes, "nasr_ctc_workspace_bytes: out_bytes is NULL");

@@ -92,6 +92,20 @@ def _workspace(device, nbytes):
     return ws
 
 
+def debug_config(path=0, split_frames=0):
+    """Test hook (``nasr_debug_config``): 0 = throughput kernel + robust retry (default), 1 = robust
+    kernel only, 2 = throughput kernel only; ``split_frames`` forces the forward half's length."""
+    _lib.check(_lib.load().nasr_debug_config(int(path), int(split_frames)), "nasr_debug_config")
+
+
+def retry_flags(device, B):
+    """Test hook: which utterances of the last loss call the throughput kernel handed to the robust one
+    (the first B int32 of the workspace; undefined if the throughput kernel did not run)."""
+    ws = _WORKSPACES[(device.type, device.index)]
+    off = (-ws.data_ptr()) % 256
+    return ws[off:off + 4 * B].view(torch.int32).clone()
+
+
 def _stream_ptr(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
