@@ -199,6 +199,11 @@ uint64_t nasr_launch_count(void);
  * Change it only between calls, and query nasr_ctc_workspace_bytes again afterwards. */
 int nasr_debug_config(int path, int split_frames);
 
+/* Test/tuning hook: when device_buffer is non-NULL the throughput kernel writes, per utterance and warp,
+ * int64[4] = {cycles of work before the meeting, cycles of work after it, total cycles, warp role} to
+ * device_buffer[(b*8 + warp)*4 ...] (B*8*4 int64).  NULL switches it off (the default). */
+int nasr_debug_profile(void* device_buffer);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,7 @@ namespace nasr {
 namespace fast {
 
 constexpr int KC = 8;            // frames per chunk (= rescale and checkpoint interval)
+constexpr int IFIRST = -5;       // first iteration: the producers' copies run five iterations ahead of the recursion
 constexpr int NTHREADS = 256;    // 8 warps
 constexpr int GCAP = 200;        // a lane with mass sits at most this far below the nearest lane with mass beneath it
 constexpr int GROWTH = 550;      // bits a lane maximum may grow inside one chunk (GCAP of inflow + 350 of emissions)
@@ -65,25 +66,30 @@ struct Params {
   int maxch;
   int num_sms;
   int split;           // debug: frames of the forward half (multiple of KC), 0 = automatic
+  long long* prof;     // debug: [B][8 warps][4] cycles of work in phase 1 / phase 2, total, role (or NULL)
 };
 
 struct Smem {
-  size_t rows, obuf, gbuf, oexp, meet_nb, meet_pre, meet_e, lab, pos, cls_off, psum, scal, total;
-  int rowbytes;
+  size_t rows, raw, obuf, gbuf, oexp, meet_nb, meet_pre, meet_e, lab, pos, cls_off, psum, scal, total;
   int gstride;  // floats per posterior row: NL*32 cells + one zero cell (+ padding)
 };
 
-__host__ __device__ inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
+__host__ __device__ constexpr size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-// Row record of one frame: uint32 R_hi[C+1] (high words of the double ratio emissions, last entry 0 for dead
-// slots), then float y[C] (softmax, for the gradient).
-__host__ __device__ inline Smem smem_layout(int NL, int C) {
+// Row record of one frame, sized for the largest class count the instantiation takes (CMAX = 8*EPL):
+// double R[CMAX+1] (ratio emissions; entry C is 0.0, the "emission" of dead slots), then float y[CMAX]
+// (softmax, for the gradient).  Compile-time so that frame offsets are immediates.
+__host__ __device__ constexpr int row_bytes(int cmax) { return (int)al16((size_t)(cmax + 1) * 8 + (size_t)cmax * 4); }
+__host__ __device__ constexpr int row_yoff(int cmax) { return (cmax + 1) * 8; }
+
+__host__ __device__ inline Smem smem_layout(int NL, int cmax) {
   Smem s;
-  s.rowbytes = (int)al16((size_t)(2 * C + 1) * 4);
+  const int rowbytes = row_bytes(cmax);
   s.gstride = NL * 32 + 4;
   const int Lcap = NL * 32;
   size_t o = 0;
-  s.rows = o;      o = al16(o + (size_t)2 * 4 * KC * s.rowbytes);            // [side][4 slots][KC] records
+  s.rows = o;      o = al16(o + (size_t)2 * 4 * KC * rowbytes);              // [side][4 slots][KC] records
+  s.raw = o;       o = al16(o + (size_t)2 * 4 * KC * cmax * 4);              // [side][4 slots][KC][cmax] raw logits
   s.obuf = o;      o = al16(o + (size_t)2 * 2 * KC * NL * 32 * 4);           // [side][2][KC][NL][32] high words
   s.gbuf = o;      o = al16(o + (size_t)2 * 2 * KC * s.gstride * 4);         // [side][2][KC][gstride] posteriors
   s.oexp = o;      o = al16(o + (size_t)2 * 2 * 32 * 4);
@@ -92,8 +98,8 @@ __host__ __device__ inline Smem smem_layout(int NL, int C) {
   s.meet_e = o;    o = al16(o + 32 * 4);
   s.lab = o;       o = al16(o + (size_t)Lcap * 4);
   s.pos = o;       o = al16(o + (size_t)Lcap * 2);                           // class-sorted rank of label j
-  s.cls_off = o;   o = al16(o + (size_t)(C + 2) * 4);
-  s.psum = o;      o = al16(o + 8 * 8);
+  s.cls_off = o;   o = al16(o + (size_t)(cmax + 2) * 4);
+  s.psum = o;      o = al16(o + 16 * 8);
   s.scal = o;      o = al16(o + 64);
   s.total = o;
   return s;
@@ -102,11 +108,11 @@ __host__ __device__ inline Smem smem_layout(int NL, int C) {
 // scalars block: [0] alarm (int) [1] e_p (int) [2] rep count (int) [4..5] 1/m_p (double)
 struct Sched {
   int Tb;
-  int n1[2];    // frames each direction covers in phase 1
-  int nch1[2];  // chunks of phase 1
-  int offB;     // iteration at which the backward warp starts phase 1
-  int P1;       // iteration of the meeting; phase 2 starts at P1 + 1
-  int last;     // last iteration (gradient of the last phase-2 chunk)
+  int n1F, n1B;      // frames each direction covers in phase 1
+  int nch1F, nch1B;  // chunks of phase 1
+  int offB;          // iteration at which the backward warp starts phase 1
+  int P1;            // iteration of the meeting; phase 2 starts at P1 + 1
+  int last;          // last iteration (gradient of the last phase-2 chunk)
 };
 
 struct Chunk {
@@ -120,19 +126,20 @@ __device__ __forceinline__ Chunk chunk_at(const Sched& S, int d, int J) {
   Chunk c;
   c.phase = 0; c.idx = 0; c.len = 0; c.base = 0;
   const int k = J - (d ? S.offB : 0);
-  if (J >= 0 && k >= 0 && k < S.nch1[d]) {
+  const int own_n = d ? S.n1B : S.n1F, own_ch = d ? S.nch1B : S.nch1F;
+  const int oth_n = d ? S.n1F : S.n1B, oth_ch = d ? S.nch1F : S.nch1B;
+  if (J >= 0 && k >= 0 && k < own_ch) {
     const int tau0 = k * KC;
     c.phase = 1;
     c.idx = k;
-    c.len = min(KC, S.n1[d] - tau0);
+    c.len = min(KC, own_n - tau0);
     c.base = d ? S.Tb - 1 - tau0 : tau0;
   } else if (J > S.P1) {
     const int q = J - S.P1 - 1;
-    const int o = d ^ 1;
-    if (q < S.nch1[o]) {
-      const int j = S.nch1[o] - 1 - q;
+    if (q < oth_ch) {
+      const int j = oth_ch - 1 - q;
       const int tau0 = j * KC;
-      const int e = min(S.n1[o], tau0 + KC);
+      const int e = min(oth_n, tau0 + KC);
       c.phase = 2;
       c.idx = j;
       c.len = e - tau0;
@@ -141,6 +148,9 @@ __device__ __forceinline__ Chunk chunk_at(const Sched& S, int d, int J) {
   }
   return c;
 }
+
+// CTA-wide barrier that may be reached from different code locations (every role loop has its own)
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
 
 __device__ __forceinline__ double pow2d(int e) {  // 2^e, e clamped to the normal range
   e = max(-1022, min(1023, e));
@@ -152,7 +162,7 @@ template <int NL>
 struct Dir {
   double Ab[NL], Al[NL];
   int E;
-  uint32_t coloff[NL];  // byte offset of R_hi[class of slot k] inside a row record (dead slot: the zero entry)
+  uint32_t coloff[NL];  // byte offset of R[class of slot k] inside a row record (dead slot: the zero entry)
   uint32_t mask[NL];    // all-ones if slot k may take the skip transition
 };
 
@@ -179,7 +189,7 @@ __device__ __forceinline__ void dir_setup(Dir<NL>& s, int d, int lane, const int
         skip = m >= 1 && lab[L - 1 - m] != lab[L - m];
       }
     }
-    s.coloff[k] = (uint32_t)col * 4u;
+    s.coloff[k] = (uint32_t)col * 8u;
     s.mask[k] = skip ? 0xffffffffu : 0u;
     s.Ab[k] = (i == (d == 0 ? 1 : pad)) ? 1.0 : 0.0;
     s.Al[k] = 0.0;
@@ -236,26 +246,26 @@ __device__ __forceinline__ double inflow_factor(int E, int lane) {
 
 enum Mode { PLAIN = 0, STORE_O = 1, COMBINE = 2 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v));
-}
-
-// One frame of one direction.  erow: shared address of the frame's row record; orow: shared address of the
-// frame's row of high words ([k][lane]); grow: shared address of the frame's posterior row.
+// One frame of one direction.  erow: the frame's row record; orow: the frame's row of high words
+// ([k][lane]); grow: the frame's posterior row.  All loads of the frame are issued before any store so
+// that the NL slots form NL independent dependency chains.
 //   STORE_O : write the high words of the new label values to orow[k][lane]
 //   COMBINE : posterior = pre-emission sum * (other direction's high word at the mirrored slot, shifted by
 //             kshift in the exponent field) -> grow[gphys[k]]
+// (A hand software-pipelined variant -- next frame's emissions prefetched, the shuffle issued a frame early
+// -- was measured: 135 instead of 172 cycles per frame for a lone warp, but slower inside the full kernel,
+// where the schedulers are shared by four warps; tools/microbench_step.cu, tools/microbench_mix.cu.)
 template <int NL, int MODE>
-__device__ __forceinline__ void step(Dir<NL>& s, uint32_t erow, uint32_t orow, uint32_t grow, double fin,
-                                     int kshift, const uint32_t (&gphys)[NL], int lane) {
+__device__ __forceinline__ void step(Dir<NL>& s, const unsigned char* erow, uint32_t* orow, unsigned char* grow,
+                                     double fin, int kshift, const uint32_t (&gphys)[NL], int lane) {
+  double r[NL];
+  int oh[NL];
+#pragma unroll
+  for (int k = 0; k < NL; k++) r[k] = *reinterpret_cast<const double*>(erow + s.coloff[k]);
+  if (MODE == COMBINE) {
+#pragma unroll
+    for (int k = 0; k < NL; k++) oh[k] = (int)orow[(NL - 1 - k) * 32 + 31 - lane];
+  }
   double a_in = __shfl_up_sync(0xffffffffu, s.Al[NL - 1], 1);
   a_in = lane ? a_in * fin : 0.0;
 #pragma unroll
@@ -267,40 +277,117 @@ __device__ __forceinline__ void step(Dir<NL>& s, uint32_t erow, uint32_t orow, u
         (int)(((uint32_t)__double2hiint(nb) & m) | ((uint32_t)__double2hiint(s.Ab[k]) & ~m)),
         (int)(((uint32_t)__double2loint(nb) & m) | ((uint32_t)__double2loint(s.Ab[k]) & ~m)));
     const double q = s.Al[k] + w;
-    const double r = hi2d(lds32(erow + s.coloff[k]));
     if (MODE == COMBINE) {
-      const int oh = (int)lds32(orow + (uint32_t)(((NL - 1 - k) * 32 + 31) * 4) - (uint32_t)lane * 4u);
-      const double od = __hiloint2double(max(oh + kshift, 0), 0);
-      sts32(grow + gphys[k], __float_as_uint((float)(q * od)));
+      const double od = __hiloint2double(max(oh[k] + kshift, 0), 0);
+      *reinterpret_cast<float*>(grow + gphys[k]) = (float)(q * od);
     }
-    s.Al[k] = q * r;
-    if (MODE == STORE_O) sts32(orow + (uint32_t)(k * 32) * 4u + (uint32_t)lane * 4u, (uint32_t)__double2hiint(s.Al[k]));
+    s.Al[k] = q * r[k];
+    if (MODE == STORE_O) orow[k * 32 + lane] = (uint32_t)__double2hiint(s.Al[k]);
     s.Ab[k] = nb;
   }
 }
 
 // Advance one direction over a chunk of `len` frames whose row records start at erows (consumer order).
 // reverse: walk the records backwards (recompute warps run against the consumer's order).
-template <int NL, int MODE>
-__device__ __forceinline__ void run_chunk(Dir<NL>& s, uint32_t erows, int rowbytes, int len, bool reverse,
-                                          uint32_t obuf, uint32_t gbuf, int gstride, double fin, int kshift,
-                                          const uint32_t (&gphys)[NL], int lane) {
+template <int NL, int MODE, int ROWB>
+__device__ __forceinline__ void run_chunk(Dir<NL>& s, const unsigned char* erows, int len,
+                                          bool reverse, uint32_t* obuf, float* gbuf, double fin,
+                                          int kshift, const uint32_t (&gphys)[NL], int lane) {
+  constexpr int rowbytes = ROWB;
+  constexpr int gstride = NL * 32 + 4;
   if (len == KC) {
 #pragma unroll
     for (int g = 0; g < KC; g++) {
       const int f = reverse ? KC - 1 - g : g;
-      step<NL, MODE>(s, erows + f * rowbytes, obuf + f * (NL * 32 * 4), gbuf + f * gstride * 4, fin, kshift, gphys,
-                     lane);
+      step<NL, MODE>(s, erows + f * rowbytes, obuf + f * (NL * 32), reinterpret_cast<unsigned char*>(gbuf + f * gstride),
+                     fin, kshift, gphys, lane);
     }
   } else {
 #pragma unroll 1
     for (int g = 0; g < len; g++) {
       const int f = reverse ? len - 1 - g : g;
-      step<NL, MODE>(s, erows + f * rowbytes, obuf + f * (NL * 32 * 4), gbuf + f * gstride * 4, fin, kshift, gphys,
-                     lane);
+      step<NL, MODE>(s, erows + f * rowbytes, obuf + f * (NL * 32), reinterpret_cast<unsigned char*>(gbuf + f * gstride),
+                     fin, kshift, gphys, lane);
     }
   }
 }
+
+// Producer, one group of four rows (8 lanes per row, lane sub handles classes sub, sub+8, ...):
+// raw logits of row f (staged in shared memory by cp.async) -> row record f of the chunk: ratio emissions
+// as doubles, softmax as floats.  Returns log y_blank of the row in the lane that holds the blank class
+// (0 elsewhere and for rows past the end of a short chunk).  One copy of this code serves the producer and,
+// in phase 1, the gradient warps.
+template <int EPL, int ROWB, int YOFF>
+__device__ __noinline__ float rows_to_smem(const float* raw, int f, int len, unsigned char* rows, int C, int blank,
+                                           int* alarm_word) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & 7;
+  const bool valid = f < len;
+  const float* xrow = raw + f * (8 * EPL);
+  float x[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; e++) x[e] = xrow[sub + 8 * e];
+  float m = -INFINITY;
+#pragma unroll
+  for (int e = 0; e < EPL; e++)
+    if (sub + 8 * e < C) m = fmaxf(m, x[e]);
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+  float n[EPL];
+  float ssum = 0.f, nbl = 0.f, xbl = 0.f;
+#pragma unroll
+  for (int e = 0; e < EPL; e++) {
+    const int c = sub + 8 * e;
+    n[e] = c < C ? __expf(x[e] - m) : 0.f;
+    ssum += n[e];
+    if (c == blank) {
+      nbl = n[e];
+      xbl = x[e];
+    }
+  }
+  ssum += __shfl_xor_sync(0xffffffffu, ssum, 4);
+  ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
+  ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
+  const int src = (lane & ~7) | (blank & 7);
+  nbl = __shfl_sync(0xffffffffu, nbl, src);
+  const float inv_s = __fdividef(1.0f, ssum);
+  const float inv_nb = 1.0f / nbl;
+  unsigned char* row = rows + (size_t)f * ROWB;
+  uint2* Rrow = reinterpret_cast<uint2*>(row);
+  float* yrow = reinterpret_cast<float*>(row + YOFF);
+  float logyb = 0.f;
+  if (valid) {
+    bool bad = false;
+#pragma unroll
+    for (int e = 0; e < EPL; e++) {
+      const int c = sub + 8 * e;
+      if (c < C) {
+        const float r = n[e] * inv_nb;
+        // the recursion needs a normal float: anything else (blank or class probability underflowed,
+        // inf, nan) is the robust kernel's business
+        bad |= !(r >= 1.1754944e-38f && r <= 1.0e38f);
+        // (double)r assembled from the bits of the normal float r: no F2F on this path
+        const uint32_t rb = __float_as_uint(r);
+        Rrow[c] = make_uint2(rb << 29, (rb >> 3) + (896u << 20));
+        yrow[c] = n[e] * inv_s;
+      }
+    }
+    if (sub == 0) Rrow[C] = make_uint2(0u, 0u);
+    if (bad) atomicOr(alarm_word, (int)AL_EMISSION);
+    if (sub == (blank & 7)) logyb = (xbl - m) - __logf(ssum);
+  }
+  return logyb;
+}
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int NL>
 __device__ __forceinline__ uint32_t* ckpt_ptr(const Params& p, int b, int d, int c) {
@@ -317,8 +404,12 @@ __device__ __forceinline__ uint32_t gcell(int pos) {
 template <int NL, int EPL>
 __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const Smem sl = smem_layout(NL, p.C);
+  constexpr int CMAX = 8 * EPL;
+  constexpr int ROWB = row_bytes(CMAX);
+  constexpr int YOFF = row_yoff(CMAX);
+  const Smem sl = smem_layout(NL, CMAX);
   unsigned char* s_rows = smem + sl.rows;
+  float* s_raw = reinterpret_cast<float*>(smem + sl.raw);
   uint32_t* s_obuf = reinterpret_cast<uint32_t*>(smem + sl.obuf);
   float* s_gbuf = reinterpret_cast<float*>(smem + sl.gbuf);
   int* s_oexp = reinterpret_cast<int*>(smem + sl.oexp);
@@ -335,21 +426,21 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = p.T, B = p.B, C = p.C, blank = p.blank;
-  const int rowbytes = sl.rowbytes;
-  const int gstride = sl.gstride;
+  constexpr int rowbytes = ROWB;
+  constexpr int gstride = NL * 32 + 4;
   constexpr int N = NL * 32;
   constexpr int Lcap = N - 2;
   constexpr int OBUF = KC * NL * 32;  // words per buffer of high words
-  const int GBUF = KC * gstride;      // floats per posterior buffer
+  constexpr int GBUF = KC * gstride;  // floats per posterior buffer
 
   const int Tb = p.seq_len[b];
   const int l0 = p.lab_offs[b];
   const int L = p.lab_offs[b + 1] - l0;
 
   // ---- can this kernel take the utterance? everything unusual goes to the robust kernel -----------
-  int bad = (Tb < 2 * KC) | (Tb > T) | (L < 0) | (L > Lcap);
-  if (tid < 8) {
-    s_scal[tid] = 0;
+  int bad = (Tb < 2 * KC) | (Tb > T) | (L < 0) | (L > Lcap) | (C > CMAX);
+  if (tid < 16) {
+    if (tid < 8) s_scal[tid] = 0;
     s_psum[tid] = 0.0;
   }
   for (int c = tid; c < C + 2; c += NTHREADS) s_cls_off[c] = 0;
@@ -424,13 +515,13 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
   {
     int nf = KC * ((Tb + 2 * KC - 1) / (2 * KC));
     if (p.split > 0) nf = min(max(KC, (p.split / KC) * KC), ((Tb - 1) / KC) * KC);
-    S.n1[0] = nf;
-    S.n1[1] = Tb - nf;
-    S.nch1[0] = (S.n1[0] + KC - 1) / KC;
-    S.nch1[1] = (S.n1[1] + KC - 1) / KC;
-    S.P1 = max(S.nch1[0], S.nch1[1]);
-    S.offB = S.P1 - S.nch1[1];
-    S.last = gbase ? S.P1 + 1 + max(S.nch1[0], S.nch1[1]) : S.P1;
+    S.n1F = nf;
+    S.n1B = Tb - nf;
+    S.nch1F = (S.n1F + KC - 1) / KC;
+    S.nch1B = (S.n1B + KC - 1) / KC;
+    S.P1 = max(S.nch1F, S.nch1B);
+    S.offB = S.P1 - S.nch1B;
+    S.last = gbase ? S.P1 + 1 + S.P1 : S.P1;
   }
   const bool want_grad = gbase != nullptr;
   const float gs = p.grad_loss ? p.grad_loss[b] : 1.0f;
@@ -479,19 +570,24 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
   }
   int alarm = 0;
   bool scaled = false;     // recursion warps: state already divided by the mantissa of p
-  float xr[KC / 4][EPL];   // producer: raw logits of the chunk in flight
-#pragma unroll
-  for (int g = 0; g < KC / 4; g++)
-#pragma unroll
-    for (int e = 0; e < EPL; e++) xr[g][e] = 0.f;
-  double lsum = 0.0;        // producer: sum of log y_blank over the phase-1 rows this lane group owned
 
+  long long prof_w1 = 0, prof_w2 = 0;
+  const long long prof_t0 = clock64();
+  // Each role runs its own copy of the iteration loop (same trip count, one CTA barrier per iteration) so
+  // that a warp keeps only its own role's state in registers.
+#define NASR_PROF_BEGIN() const long long prof_a = p.prof ? clock64() : 0
+#define NASR_PROF_END()                                    \
+  if (p.prof) {                                            \
+    const long long dt = clock64() - prof_a;               \
+    if (I < S.P1) prof_w1 += dt; else prof_w2 += dt;       \
+  }
+  if (role == H_F || role == H_B) {
 #pragma unroll 1
-  for (int I = -3; I <= S.last; I++) {
-    if (role == H_F || role == H_B) {
+    for (int I = IFIRST; I <= S.last; I++) {
+      NASR_PROF_BEGIN();
       // ======================= recursion warps =======================
       const Chunk ci = chunk_at(S, d, I);
-      const uint32_t erows = smem_u32(s_rows + (size_t)(d * 4 + (I & 3)) * KC * rowbytes);
+      const unsigned char* erows = s_rows + (size_t)(d * 4 + (I & 3)) * KC * rowbytes;
       if (ci.phase == 1) {
         rescale<NL>(st, lane, alarm);
         uint32_t* ck = ckpt_ptr<NL>(p, b, d, ci.idx);
@@ -502,7 +598,7 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
         }
         ck[2 * NL * 32 + lane] = (uint32_t)st.E;
         const double fin = inflow_factor(st.E, lane);
-        run_chunk<NL, PLAIN>(st, erows, rowbytes, ci.len, false, 0u, 0u, gstride, fin, 0, gphys, lane);
+        run_chunk<NL, PLAIN, ROWB>(st, erows, ci.len, false, s_obuf, s_gbuf, fin, 0, gphys, lane);
         if (d == 1 && I == S.P1 - 1) {
           // pre-emission sums of the frame below the meeting point, for the forward warp
           rescale<NL>(st, lane, alarm);
@@ -556,7 +652,7 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
         const double mp = tot * pow2d(-et);
         double ls = 0.0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) ls += s_psum[i];
+        for (int i = 0; i < 16; i++) ls += s_psum[i];
         if (lane == 0) {
           s_scal[1] = Xm + et;
           *s_inv_mp = 1.0 / mp;
@@ -585,11 +681,16 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
           if (ks > ZALARM) alarm |= AL_RANGE;
           ks = max(-2047, min(ks, 600));
         }
-        run_chunk<NL, COMBINE>(st, erows, rowbytes, ci.len, false, smem_u32(s_obuf + (size_t)(d * 2 + buf) * OBUF),
-                               smem_u32(s_gbuf + (size_t)(d * 2 + buf) * GBUF), gstride, fin, ks * (1 << 20), gphys,
-                               lane);
+        run_chunk<NL, COMBINE, ROWB>(st, erows, ci.len, false, s_obuf + (size_t)(d * 2 + buf) * OBUF,
+                                     s_gbuf + (size_t)(d * 2 + buf) * GBUF, fin, ks * (1 << 20), gphys, lane);
       }
-    } else if (role == RC_F || role == RC_B) {
+      NASR_PROF_END();
+      cta_sync();
+    }
+  } else if (role == RC_F || role == RC_B) {
+#pragma unroll 1
+    for (int I = IFIRST; I <= S.last; I++) {
+      NASR_PROF_BEGIN();
       // ======================= recompute warps =======================
       // this warp computes direction d's rows; they are consumed by the other direction (side d^1)
       const int side = d ^ 1;
@@ -605,130 +706,143 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
         const double fin = inflow_factor(st.E, lane);
         const int buf = (I + 1) & 1;
         s_oexp[(side * 2 + buf) * 32 + lane] = st.E;
-        const uint32_t erows = smem_u32(s_rows + (size_t)(side * 4 + ((I + 1) & 3)) * KC * rowbytes);
-        run_chunk<NL, STORE_O>(st, erows, rowbytes, ci.len, true, smem_u32(s_obuf + (size_t)(side * 2 + buf) * OBUF),
-                               0u, gstride, fin, 0, gphys, lane);
+        const unsigned char* erows = s_rows + (size_t)(side * 4 + ((I + 1) & 3)) * KC * rowbytes;
+        run_chunk<NL, STORE_O, ROWB>(st, erows, ci.len, true, s_obuf + (size_t)(side * 2 + buf) * OBUF, s_gbuf, fin, 0,
+                                     gphys, lane);
       }
-    } else if (role == P_F || role == P_B) {
-      // ======================= producer warps =======================
-      const int sub = lane & 7, rl = lane >> 3;
-      {  // rows loaded in the previous iteration -> shared memory (chunk of iteration I+2)
+      NASR_PROF_END();
+      cta_sync();
+    }
+  } else if (role == P_F || role == P_B) {
+    // ======================= producer warps =======================
+    // Raw logits rows travel global -> shared memory by cp.async, issued five iterations before the recursion
+    // needs the chunk (an iteration is about as long as a DRAM round trip), and are turned into row records
+    // three iterations later.  In phase 1 the gradient warps have nothing to reduce and convert rows 4..7.
+    double lsum = 0.0;        // sum of log y_blank over the phase-1 rows this lane group owned
+    const int rl = lane >> 3, sub = lane & 7;
+#pragma unroll 1
+    for (int I = IFIRST; I <= S.last; I++) {
+      NASR_PROF_BEGIN();
+      {  // raw rows of the chunk of iteration I+2 (complete and visible since the last barrier) -> row records
         const Chunk ci = chunk_at(S, d, I + 2);
         if (ci.phase != 0 && (ci.phase == 1 || want_grad)) {
           unsigned char* rows = s_rows + (size_t)(d * 4 + ((I + 2) & 3)) * KC * rowbytes;
-#pragma unroll
-          for (int g = 0; g < KC / 4; g++) {
-            const int f = g * 4 + rl;
-            const bool valid = f < ci.len;
-            float m = -INFINITY;
-#pragma unroll
-            for (int e = 0; e < EPL; e++)
-              if (sub + 8 * e < C) m = fmaxf(m, xr[g][e]);
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-            float n[EPL];
-            float ssum = 0.f, nbl = 0.f, xbl = 0.f;
-#pragma unroll
-            for (int e = 0; e < EPL; e++) {
-              const int c = sub + 8 * e;
-              n[e] = c < C ? __expf(xr[g][e] - m) : 0.f;
-              ssum += n[e];
-              if (c == blank) {
-                nbl = n[e];
-                xbl = xr[g][e];
-              }
-            }
-            ssum += __shfl_xor_sync(0xffffffffu, ssum, 4);
-            ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
-            ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
-            const int src = (lane & ~7) | (blank & 7);
-            nbl = __shfl_sync(0xffffffffu, nbl, src);
-            const float inv_s = __fdividef(1.0f, ssum);
-            const float inv_nb = 1.0f / nbl;
-            unsigned char* row = rows + (size_t)f * rowbytes;
-            uint32_t* Rrow = reinterpret_cast<uint32_t*>(row);
-            float* yrow = reinterpret_cast<float*>(row + (size_t)(C + 1) * 4);
-            if (valid) {
-#pragma unroll
-              for (int e = 0; e < EPL; e++) {
-                const int c = sub + 8 * e;
-                if (c < C) {
-                  const float r = n[e] * inv_nb;
-                  // the recursion needs a normal float: anything else (blank or class probability
-                  // underflowed, inf, nan) is the robust kernel's business
-                  if (!(r >= 1.1754944e-38f && r <= 1.0e38f)) alarm |= AL_EMISSION;
-                  // high word of (double)r, rounded to nearest at the 20 mantissa bits it keeps
-                  Rrow[c] = ((__float_as_uint(r) + 4u) >> 3) + (896u << 20);
-                  yrow[c] = n[e] * inv_s;
-                }
-              }
-              if (sub == 0) Rrow[C] = 0u;
-              if (ci.phase == 1 && sub == (blank & 7)) lsum += (double)((xbl - m) - __logf(ssum));
-            }
+          const float* raw = s_raw + (size_t)(d * 4 + ((I + 2) & 3)) * KC * CMAX;
+          const float l0v = rows_to_smem<EPL, ROWB, YOFF>(raw, rl, ci.len, rows, C, blank, s_scal);
+          if (ci.phase == 1) {
+            lsum += (double)l0v;
+          } else {
+            rows_to_smem<EPL, ROWB, YOFF>(raw, 4 + rl, ci.len, rows, C, blank, s_scal);
           }
           if (sub == (blank & 7)) s_psum[d * 4 + rl] = lsum;
         }
       }
-      {  // issue the loads for the chunk of iteration I+3
-        const Chunk ci = chunk_at(S, d, I + 3);
+      {  // issue the copies for the chunk of iteration I+5 (one commit group per iteration, empty or not)
+        const Chunk ci = chunk_at(S, d, I + 5);
         if (ci.phase != 0 && (ci.phase == 1 || want_grad)) {
+          float* raw = s_raw + (size_t)(d * 4 + ((I + 5) & 3)) * KC * CMAX;
 #pragma unroll
           for (int g = 0; g < KC / 4; g++) {
             const int f = g * 4 + rl;
-            if (f < ci.len) {
-              const int t = d ? ci.base - f : ci.base + f;
-              const float* x = p.logits + ((size_t)t * B + b) * C;
+            const int ff = min(f, ci.len - 1);
+            const int t = d ? ci.base - ff : ci.base + ff;
+            const float* xrow = p.logits + ((size_t)t * B + b) * C;
 #pragma unroll
-              for (int e = 0; e < EPL; e++) {
-                const int c = sub + 8 * e;
-                xr[g][e] = c < C ? __ldg(x + c) : 0.f;
-              }
-            }
+            for (int e = 0; e < EPL; e++) cp_async4(raw + f * CMAX + sub + 8 * e, xrow + min(sub + 8 * e, C - 1));
           }
         }
+        cp_async_commit();
+        cp_async_wait<2>();  // everything up to the chunk of iteration I+3 has landed; the barrier publishes it
       }
-    } else {
+      NASR_PROF_END();
+      cta_sync();
+    }
+  } else {
+    double lsumg = 0.0;
+    const int rl = lane >> 3;
+#pragma unroll 1
+    for (int I = IFIRST; I <= S.last; I++) {
+      NASR_PROF_BEGIN();
+      {  // phase 1: second half of the producer's job
+        const Chunk c2 = chunk_at(S, d, I + 2);
+        if (c2.phase == 1) {
+          unsigned char* rows = s_rows + (size_t)(d * 4 + ((I + 2) & 3)) * KC * rowbytes;
+          const float* raw = s_raw + (size_t)(d * 4 + ((I + 2) & 3)) * KC * CMAX;
+          lsumg += (double)rows_to_smem<EPL, ROWB, YOFF>(raw, 4 + rl, c2.len, rows, C, blank, s_scal);
+          if ((lane & 7) == (blank & 7)) s_psum[8 + d * 4 + rl] = lsumg;
+        }
+      }
       // ======================= gradient warps =======================
       // posterior rows are in class-sorted order: an inclusive prefix sum turns "occupancy of class c" into
       // the difference of two prefixes
       const Chunk ci = chunk_at(S, d, I - 1);
       if (ci.phase == 2 && want_grad) {
         const int buf = (I - 1) & 1;
-        const uint32_t G = smem_u32(s_gbuf + (size_t)(d * 2 + buf) * GBUF);
+        float* G = s_gbuf + (size_t)(d * 2 + buf) * GBUF;
         const unsigned char* rows = s_rows + (size_t)(d * 4 + ((I - 1) & 3)) * KC * rowbytes;
         const int c0 = lane, c1 = lane + 32;
-#pragma unroll 2
-        for (int f = 0; f < ci.len; f++) {
-          const int t = d ? ci.base - f : ci.base + f;
-          const uint32_t Gr = G + (uint32_t)(f * gstride * 4);
-          const float* yrow = reinterpret_cast<const float*>(rows + (size_t)f * rowbytes + (size_t)(C + 1) * 4);
-          float v[NL];
+        constexpr int NF = 4;  // frames in flight: their dependency chains interleave
+#pragma unroll 1
+        for (int f0 = 0; f0 < ci.len; f0 += NF) {
+          float v[NF][NL];
 #pragma unroll
-          for (int i = 0; i < NL; i++) v[i] = __uint_as_float(lds32(Gr + (uint32_t)(i * 32 * 4) + (uint32_t)lane * 4u));
+          for (int j = 0; j < NF; j++)
 #pragma unroll
-          for (int i = 1; i < NL; i++) v[i] += v[i - 1];
-          float inc = v[NL - 1];
+            for (int i = 0; i < NL; i++) v[j][i] = G[(f0 + j) * gstride + i * 32 + lane];
+          float inc[NF], base[NF];
+#pragma unroll
+          for (int j = 0; j < NF; j++) {
+#pragma unroll
+            for (int i = 1; i < NL; i++) v[j][i] += v[j][i - 1];
+            inc[j] = v[j][NL - 1];
+          }
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
-            const float u = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += u;
-          }
-          const float base = inc - v[NL - 1];
 #pragma unroll
-          for (int i = 0; i < NL; i++) sts32(Gr + (uint32_t)(i * 32 * 4) + (uint32_t)lane * 4u, __float_as_uint(v[i] + base));
+            for (int j = 0; j < NF; j++) {
+              const float u = __shfl_up_sync(0xffffffffu, inc[j], o);
+              if (lane >= o) inc[j] += u;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < NF; j++) {
+            base[j] = inc[j] - v[j][NL - 1];
+#pragma unroll
+            for (int i = 0; i < NL; i++) G[(f0 + j) * gstride + i * 32 + lane] = v[j][i] + base[j];
+          }
           __syncwarp();
-          const float o0 = __uint_as_float(lds32(Gr + pc_hi0)) - __uint_as_float(lds32(Gr + pc_lo0));
-          const float o1 = __uint_as_float(lds32(Gr + pc_hi1)) - __uint_as_float(lds32(Gr + pc_lo1));
-          const float tot = __uint_as_float(lds32(Gr + pc_tot));
-          float* g = gbase + (size_t)t * rstride;
-          if (c0 < C) g[c0] = gs * (yrow[c0] - (c0 == blank ? 1.0f - tot : o0));
-          if (c1 < C) g[c1] = gs * (yrow[c1] - (c1 == blank ? 1.0f - tot : o1));
-          __syncwarp();
+          float o0[NF], o1[NF], tot[NF], y0[NF], y1[NF];
+#pragma unroll
+          for (int j = 0; j < NF; j++) {
+            const unsigned char* Grb = reinterpret_cast<const unsigned char*>(G + (f0 + j) * gstride);
+            const float* yrow = reinterpret_cast<const float*>(rows + (size_t)(f0 + j) * rowbytes + YOFF);
+            o0[j] = *reinterpret_cast<const float*>(Grb + pc_hi0) - *reinterpret_cast<const float*>(Grb + pc_lo0);
+            o1[j] = *reinterpret_cast<const float*>(Grb + pc_hi1) - *reinterpret_cast<const float*>(Grb + pc_lo1);
+            tot[j] = *reinterpret_cast<const float*>(Grb + pc_tot);
+            y0[j] = yrow[min(c0, C - 1)];
+            y1[j] = yrow[min(c1, C - 1)];
+          }
+#pragma unroll
+          for (int j = 0; j < NF; j++) {
+            const int f = f0 + j;
+            if (f < ci.len) {
+              const int t = d ? ci.base - f : ci.base + f;
+              float* g = gbase + (size_t)t * rstride;
+              if (c0 < C) g[c0] = gs * (y0[j] - (c0 == blank ? 1.0f - tot[j] : o0[j]));
+              if (c1 < C) g[c1] = gs * (y1[j] - (c1 == blank ? 1.0f - tot[j] : o1[j]));
+            }
+          }
         }
       }
+      NASR_PROF_END();
+      cta_sync();
     }
-    __syncthreads();
+  }
+#undef NASR_PROF_BEGIN
+#undef NASR_PROF_END
+  if (p.prof && lane == 0) {
+    long long* q = p.prof + ((size_t)b * 8 + warp) * 4;
+    q[0] = prof_w1; q[1] = prof_w2; q[2] = clock64() - prof_t0; q[3] = role;
   }
   if (alarm) atomicOr(&s_scal[0], alarm);
   __syncthreads();
@@ -741,6 +855,8 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
 
 namespace {
 
+constexpr int kMaxSmem = 226 * 1024;  // of the 227 KB a CTA may have on sm_100
+
 int pick_nl(int Lmax) {
   static const int kNL[] = {2, 4, 5, 7, 10, 20};
   for (int nl : kNL)
@@ -750,14 +866,14 @@ int pick_nl(int Lmax) {
 
 template <int NL, int EPL>
 int launch_fast(const fast::Params& p, cudaStream_t stream) {
-  const fast::Smem sl = fast::smem_layout(NL, p.C);
+  const fast::Smem sl = fast::smem_layout(NL, 8 * EPL);
   static bool attr_set = false;
   if (!attr_set) {
     NASR_CUDA(cudaFuncSetAttribute(fast::ctc_fast_kernel<NL, EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   200 * 1024));
+                                   kMaxSmem));
     attr_set = true;
   }
-  if (sl.total > 200 * 1024) {
+  if (sl.total > (size_t)kMaxSmem) {
     set_error("nasr_ctc: fast kernel shared memory %zu too large", sl.total);
     return NASR_ERR_UNSUPPORTED;
   }
@@ -776,6 +892,7 @@ int launch_fast_c(const fast::Params& p, cudaStream_t stream) {
 }  // namespace
 
 int g_debug_split = 0;  // test hook (nasr_debug_config): frames of the forward half, 0 = automatic
+long long* g_debug_prof = nullptr;  // test hook (nasr_debug_profile): device buffer for per-warp cycle counts
 
 static int max_chunks(int T) {
   // chunks one direction can own in phase 1: half the frames normally, all of them under a split override
@@ -784,7 +901,9 @@ static int max_chunks(int T) {
 }
 
 bool ctc_fast_supported(int T, int C, int Lmax) {
-  return T >= 2 * fast::KC && C <= 64 && pick_nl(Lmax) != 0;
+  const int NL = pick_nl(Lmax);
+  if (T < 2 * fast::KC || C > 64 || NL == 0) return false;
+  return fast::smem_layout(NL, C <= 40 ? 40 : 64).total <= (size_t)kMaxSmem;
 }
 
 size_t ctc_fast_workspace_bytes(int T, int B, int C, int Lmax) {
@@ -805,6 +924,7 @@ int ctc_fast_launch(const float* logits, int T, int B, int C, const int32_t* lab
   p.ckpt = static_cast<uint32_t*>(ckpt);
   p.maxch = max_chunks(T);
   p.split = g_debug_split;
+  p.prof = g_debug_prof;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;

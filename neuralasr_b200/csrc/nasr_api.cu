@@ -41,6 +41,7 @@ int batch_sums(const float* loss, const float* ler, const int32_t* dist, int B, 
                cudaStream_t stream);
 extern int g_debug_path;   // ctc_loss.cu
 extern int g_debug_split;  // ctc_fast.cu
+extern long long* g_debug_prof;
 
 namespace {
 
@@ -126,6 +127,11 @@ int nasr_debug_config(int path, int split_frames) {
   NASR_CHECK_ARG(path >= 0 && path <= 2 && split_frames >= 0, "nasr_debug_config: bad arguments");
   g_debug_path = path;
   g_debug_split = split_frames;
+  return NASR_OK;
+}
+
+int nasr_debug_profile(void* device_buffer) {
+  g_debug_prof = static_cast<long long*>(device_buffer);
   return NASR_OK;
 }
 

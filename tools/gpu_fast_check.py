@@ -79,3 +79,30 @@ if which in ("all", "time"):
         print("cfg3 path %d: %.3f ms per step  -> %.2f%% of HBM peak (116.7 MB / 6543 GB/s = 17.8 us)" % (path, ms, 100 * 0.01784 / ms))
     common.debug_config(0, 0)
     run("cfg3", 2, 0, T=1000, B=256, C=38, Lmax=200, mode="full", Lmin=100, empty_row=False)
+if which in ("all", "time", "roles"):
+    import ctypes
+    from neuralasr_b200 import _lib
+    lib = _lib.load()
+    g = make_batch(1234, T=1000, B=256, C=38, Lmax=200, mode="full", Lmin=100, empty_row=False)
+    x = torch.from_numpy(g["logits"]).to(dev)
+    lab = common.prepare_labels(_triple(g), dev)
+    seq = torch.from_numpy(g["seq_len"]).to(dev)
+    prof = torch.zeros(256 * 8 * 4, dtype=torch.int64, device=dev)
+    common.debug_config(2, 0)
+    gr = torch.empty_like(x)
+    common.ctc_loss_and_grad(x, lab, seq, out_grad=gr)
+    lib.nasr_debug_profile(ctypes.c_void_p(prof.data_ptr()))
+    common.ctc_loss_and_grad(x, lab, seq, out_grad=gr)
+    torch.cuda.synchronize()
+    lib.nasr_debug_profile(None)
+    common.debug_config(0, 0)
+    pr = prof.cpu().numpy().reshape(256, 8, 4)
+    names = ["H_F", "H_B", "RC_F", "RC_B", "P_F", "P_B", "G_F", "G_B"]
+    print("per-role cycles (mean over CTAs | max): work before meeting, work after meeting, total")
+    for r in range(8):
+        sel = pr[:, :, 3] == r
+        w1, w2, tot = pr[:, :, 0][sel], pr[:, :, 1][sel], pr[:, :, 2][sel]
+        print("  %-5s phase1 %8.0f | %8d   phase2 %8.0f | %8d   total %8.0f | %8d" % (names[r], w1.mean(), w1.max(), w2.mean(), w2.max(), tot.mean(), tot.max()))
+    L = np.diff(g["label_offsets"])
+    tot = pr[:, 0, 2]
+    print("  total cycles by CTA index: first wave(0..147) mean %.0f, second wave(148..255) mean %.0f" % (tot[:148].mean(), tot[148:].mean()))
