@@ -221,3 +221,98 @@ def test_full_size_properties(common):
                                        g["seq_len"][pick])
     np.testing.assert_allclose(loss[pick], wl, rtol=LOSS_RTOL)
     assert np.abs(grad[:, pick] - wg).max() <= GRAD_ATOL
+
+
+# ------------------------------------------------------------------------------------------------
+# the two kernels behind nasr_ctc_loss_grad: throughput kernel (ctc_fast.cu) + robust retry (ctc_loss.cu)
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture
+def debug_paths(common):
+    yield common.debug_config
+    common.debug_config(0, 0)            # always restore the default dispatch
+
+
+def _flags(common, B):
+    return common.retry_flags(torch.device("cuda", 0), B).cpu().numpy()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(T=500, B=16, C=38, Lmax=100, mode="ragged"),                 # BASELINE cfg1
+    dict(T=400, B=12, C=38, Lmax=60, mode="ragged", peaky=True),
+    dict(T=100, B=5, C=64, Lmax=20, mode="ragged"),                   # widest vocabulary the fast kernel takes
+    dict(T=40, B=3, C=5, Lmax=6, mode="ragged"),
+    dict(T=3000, B=2, C=38, Lmax=600, mode="full", empty_row=False),  # BASELINE cfg4: 20 slots per lane
+])
+def test_each_kernel_alone_matches_oracle(common, debug_paths, kw):
+    g = make_batch(4242, **kw)
+    want_loss, want_grad, want_status = c_oracle.ctc_loss_grad(
+        g["logits"], g["label_values"], g["label_offsets"], g["seq_len"], precision="f64")
+    debug_paths(1, 0)                    # robust kernel only
+    loss, grad, status = _run_loss(common, g)
+    _assert_loss_grad(loss, grad, status, want_loss, want_grad, want_status)
+    debug_paths(2, 0)                    # throughput kernel only: it must take every regular utterance itself
+    loss, grad, status = _run_loss(common, g)
+    flags = _flags(common, kw["B"])
+    regular = g["seq_len"] >= 16
+    assert not flags[regular].any(), "throughput kernel handed over %s" % flags
+    ok = flags == 0
+    np.testing.assert_allclose(loss[ok], want_loss[ok], rtol=LOSS_RTOL, atol=1e-5)
+    assert np.abs(grad[:, ok] - want_grad[:, ok]).max() <= GRAD_ATOL
+
+
+@pytest.mark.parametrize("split", [8, 16, 64, 104])
+def test_uneven_meeting_points(common, debug_paths, split):
+    """The forward/backward halves may meet anywhere: same results for lopsided splits."""
+    g = make_batch(99, T=120, B=6, C=38, Lmax=30, mode="ragged")
+    want_loss, want_grad, _ = c_oracle.ctc_loss_grad(g["logits"], g["label_values"], g["label_offsets"],
+                                                     g["seq_len"], precision="f64")
+    debug_paths(2, split)
+    loss, grad, status = _run_loss(common, g)
+    assert not _flags(common, 6).any()
+    _assert_loss_grad(loss, grad, status, want_loss, want_grad)
+
+
+def test_out_of_range_inputs_go_to_the_robust_kernel(common, debug_paths):
+    """Logit gaps beyond what a float ratio can hold, short utterances, infeasible and invalid rows: the
+    throughput kernel must flag them (never answer wrongly) and the default path must still be right."""
+    g = make_batch(7, T=64, B=8, C=12, Lmax=10, mode="full", empty_row=False)
+    x = g["logits"]
+    x[10:20, 0, 11] -= 60.0              # blank nearly impossible for ten frames: ratio emissions ~e^60 each
+    x[30, 1, 3] += 60.0                  # one class dominates a frame by e^60
+    x[:, 2, :] *= 5.0                    # large dynamic range everywhere (gaps up to ~e^80)
+    g["seq_len"][3] = 9                  # shorter than two chunks
+    debug_paths(2, 0)
+    _run_loss(common, g)
+    flags = _flags(common, 8)
+    assert flags[0] and flags[3]
+    debug_paths(0, 0)
+    want_loss, want_grad, want_status = c_oracle.ctc_loss_grad(
+        x, g["label_values"], g["label_offsets"], g["seq_len"], precision="f64")
+    loss, grad, status = _run_loss(common, g)
+    _assert_loss_grad(loss, grad, status, want_loss, want_grad, want_status)
+
+
+def test_loss_only_call(common):
+    g = make_batch(3, T=200, B=5, C=38, Lmax=40, mode="ragged")
+    x = torch.from_numpy(g["logits"]).cuda()
+    loss, grad, status = common.ctc_loss_and_grad(x, _triple(g), g["seq_len"], want_grad=False)
+    want_loss, _, _ = c_oracle.ctc_loss_grad(g["logits"], g["label_values"], g["label_offsets"], g["seq_len"],
+                                             precision="f64", want_grad=False)
+    assert grad is None
+    np.testing.assert_allclose(loss.cpu().numpy(), want_loss, rtol=LOSS_RTOL)
+
+
+def test_random_shapes_sweep(common):
+    """Seeded sweep over odd shapes (hypothesis-style, fixed seeds so the GPU box needs no database)."""
+    rng = np.random.default_rng(2024)
+    for i in range(12):
+        C = int(rng.integers(2, 60))
+        Lmax = int(rng.integers(1, 70))
+        T = int(rng.integers(max(2 * Lmax + 2, 17), 2 * Lmax + 160))
+        B = int(rng.integers(1, 7))
+        g = make_batch(1000 + i, T=T, B=B, C=C, Lmax=Lmax, mode=["ragged", "full", "tight"][i % 3],
+                       repeat_p=0.0 if C == 2 else 0.15, empty_row=bool(i % 2))
+        want_loss, want_grad, want_status = c_oracle.ctc_loss_grad(
+            g["logits"], g["label_values"], g["label_offsets"], g["seq_len"], precision="f64")
+        loss, grad, status = _run_loss(common, g)
+        _assert_loss_grad(loss, grad, status, want_loss, want_grad, want_status)
