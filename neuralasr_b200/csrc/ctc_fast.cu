@@ -66,6 +66,7 @@ struct Params {
   int maxch;
   int num_sms;
   int split;           // debug: frames of the forward half (multiple of KC), 0 = automatic
+  int ablate;          // debug: bit0 gradient warps idle, bit1 producers idle in phase 2, bit2 recompute warps idle, bit3 no posterior store
   long long* prof;     // debug: [B][8 warps][4] cycles of work in phase 1 / phase 2, total, role (or NULL)
 };
 
@@ -77,10 +78,14 @@ struct Smem {
 __host__ __device__ constexpr size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // Row record of one frame, sized for the largest class count the instantiation takes (CMAX = 8*EPL):
-// double R[CMAX+1] (ratio emissions; entry C is 0.0, the "emission" of dead slots), then float y[CMAX]
-// (softmax, for the gradient).  Compile-time so that frame offsets are immediates.
-__host__ __device__ constexpr int row_bytes(int cmax) { return (int)al16((size_t)(cmax + 1) * 8 + (size_t)cmax * 4); }
-__host__ __device__ constexpr int row_yoff(int cmax) { return (cmax + 1) * 8; }
+// uint32 R_hi[CMAX+1] -- the HIGH WORDS of the double ratio emissions, rounded to nearest at the 20 mantissa
+// bits they keep (entry CMAX is 0, the "emission" of dead slots) -- then float y[CMAX] (softmax, for the
+// gradient).  4-byte entries because a C=38 row of doubles puts three classes on every bank pair and the
+// recursion's gathers then cost 3.75 wavefronts each (profiles/r1_v1_summary.md); a row of words is almost
+// conflict free.  The rounding error (2.4e-7 relative, unbiased) is far inside the gradient tolerance.
+// Compile-time sizes so that frame offsets are immediates.
+__host__ __device__ constexpr int row_bytes(int cmax) { return (int)al16((size_t)(2 * cmax + 1) * 4); }
+__host__ __device__ constexpr int row_yoff(int cmax) { return (cmax + 1) * 4; }
 
 __host__ __device__ inline Smem smem_layout(int NL, int cmax) {
   Smem s;
@@ -163,18 +168,18 @@ struct Dir {
   double Ab[NL], Al[NL];
   int E;
   uint32_t coloff[NL];  // byte offset of R[class of slot k] inside a row record (dead slot: the zero entry)
-  uint32_t mask[NL];    // all-ones if slot k may take the skip transition
+  double skip[NL];      // 1.0 if slot k may take the skip transition (label differs from the previous one), else 0.0
 };
 
 // Slot tables and the virtual row before the first frame, for direction d (0 forward, 1 mirrored).
 template <int NL>
-__device__ __forceinline__ void dir_setup(Dir<NL>& s, int d, int lane, const int* lab, int L, int C) {
+__device__ __forceinline__ void dir_setup(Dir<NL>& s, int d, int lane, const int* lab, int L, int CZ) {
   const int N = NL * 32;
   const int pad = N - L - 1;
 #pragma unroll
   for (int k = 0; k < NL; k++) {
     const int i = lane * NL + k;
-    int col = C;  // zero entry
+    int col = CZ;  // zero entry of the row record
     bool skip = false;
     if (d == 0) {
       const int j = i - 1;
@@ -189,8 +194,8 @@ __device__ __forceinline__ void dir_setup(Dir<NL>& s, int d, int lane, const int
         skip = m >= 1 && lab[L - 1 - m] != lab[L - m];
       }
     }
-    s.coloff[k] = (uint32_t)col * 8u;
-    s.mask[k] = skip ? 0xffffffffu : 0u;
+    s.coloff[k] = (uint32_t)col * 4u;
+    s.skip[k] = skip ? 1.0 : 0.0;
     s.Ab[k] = (i == (d == 0 ? 1 : pad)) ? 1.0 : 0.0;
     s.Al[k] = 0.0;
   }
@@ -258,10 +263,10 @@ enum Mode { PLAIN = 0, STORE_O = 1, COMBINE = 2 };
 template <int NL, int MODE>
 __device__ __forceinline__ void step(Dir<NL>& s, const unsigned char* erow, uint32_t* orow, unsigned char* grow,
                                      double fin, int kshift, const uint32_t (&gphys)[NL], int lane) {
-  double r[NL];
+  uint32_t rh[NL];
   int oh[NL];
 #pragma unroll
-  for (int k = 0; k < NL; k++) r[k] = *reinterpret_cast<const double*>(erow + s.coloff[k]);
+  for (int k = 0; k < NL; k++) rh[k] = *reinterpret_cast<const uint32_t*>(erow + s.coloff[k]);
   if (MODE == COMBINE) {
 #pragma unroll
     for (int k = 0; k < NL; k++) oh[k] = (int)orow[(NL - 1 - k) * 32 + 31 - lane];
@@ -272,16 +277,14 @@ __device__ __forceinline__ void step(Dir<NL>& s, const unsigned char* erow, uint
   for (int k = NL - 1; k >= 0; k--) {
     const double alp = k > 0 ? s.Al[k - 1] : a_in;
     const double nb = s.Ab[k] + alp;
-    const uint32_t m = s.mask[k];
-    const double w = __hiloint2double(
-        (int)(((uint32_t)__double2hiint(nb) & m) | ((uint32_t)__double2hiint(s.Ab[k]) & ~m)),
-        (int)(((uint32_t)__double2loint(nb) & m) | ((uint32_t)__double2loint(s.Ab[k]) & ~m)));
-    const double q = s.Al[k] + w;
+    // q = Al + Ab + [skip allowed] * alp: one DFMA with a {0,1} constant instead of a bitwise select of
+    // nb / Ab (2 LOP3 on the half-rate ALU pipe cost more dispatch than the extra FP64 operation)
+    const double q = fma(s.skip[k], alp, s.Al[k] + s.Ab[k]);
     if (MODE == COMBINE) {
       const double od = __hiloint2double(max(oh[k] + kshift, 0), 0);
       *reinterpret_cast<float*>(grow + gphys[k]) = (float)(q * od);
     }
-    s.Al[k] = q * r[k];
+    s.Al[k] = q * hi2d(rh[k]);
     if (MODE == STORE_O) orow[k * 32 + lane] = (uint32_t)__double2hiint(s.Al[k]);
     s.Ab[k] = nb;
   }
@@ -313,68 +316,70 @@ __device__ __forceinline__ void run_chunk(Dir<NL>& s, const unsigned char* erows
 }
 
 // Producer, one group of four rows (8 lanes per row, lane sub handles classes sub, sub+8, ...):
-// raw logits of row f (staged in shared memory by cp.async) -> row record f of the chunk: ratio emissions
-// as doubles, softmax as floats.  Returns log y_blank of the row in the lane that holds the blank class
-// (0 elsewhere and for rows past the end of a short chunk).  One copy of this code serves the producer and,
-// in phase 1, the gradient warps.
+// raw logits of row f (staged in shared memory by cp.async; columns C..CMAX-1 hold -inf, written once at
+// kernel start, so no class-count predicates are needed here) -> row record f of the chunk: high words of
+// the ratio emissions, softmax as floats.  Returns log y_blank of the row in the lane that holds the blank
+// class (0 elsewhere and for rows past the end of a short chunk).  One copy of this code serves the
+// producer and, in phase 1, the gradient warps.
 template <int EPL, int ROWB, int YOFF>
 __device__ __noinline__ float rows_to_smem(const float* raw, int f, int len, unsigned char* rows, int C, int blank,
                                            int* alarm_word) {
   const int lane = threadIdx.x & 31;
   const int sub = lane & 7;
-  const bool valid = f < len;
   const float* xrow = raw + f * (8 * EPL);
   float x[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; e++) x[e] = xrow[sub + 8 * e];
-  float m = -INFINITY;
+  float m = x[0];
 #pragma unroll
-  for (int e = 0; e < EPL; e++)
-    if (sub + 8 * e < C) m = fmaxf(m, x[e]);
+  for (int e = 1; e < EPL; e++) m = fmaxf(m, x[e]);
   m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
   m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
   m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
   float n[EPL];
-  float ssum = 0.f, nbl = 0.f, xbl = 0.f;
+  float ssum = 0.f, nmin = 1.f;
+  const float ml2 = m * 1.4426950408889634f;
 #pragma unroll
   for (int e = 0; e < EPL; e++) {
-    const int c = sub + 8 * e;
-    n[e] = c < C ? __expf(x[e] - m) : 0.f;
+    n[e] = exp2f(fmaf(x[e], 1.4426950408889634f, -ml2));   // e^(x-m); 0 for the -inf padding columns
     ssum += n[e];
-    if (c == blank) {
-      nbl = n[e];
-      xbl = x[e];
-    }
+    nmin = fminf(nmin, sub + 8 * e < C ? n[e] : 1.f);
   }
   ssum += __shfl_xor_sync(0xffffffffu, ssum, 4);
   ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
   ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
+  nmin = fminf(nmin, __shfl_xor_sync(0xffffffffu, nmin, 4));
+  nmin = fminf(nmin, __shfl_xor_sync(0xffffffffu, nmin, 2));
+  nmin = fminf(nmin, __shfl_xor_sync(0xffffffffu, nmin, 1));
+  // the blank's numerator and logit, from the lane and register that hold class `blank`
+  float nbl = 0.f, xbl = 0.f;
+#pragma unroll
+  for (int e = 0; e < EPL; e++)
+    if (e == (blank >> 3)) {
+      nbl = n[e];
+      xbl = x[e];
+    }
   const int src = (lane & ~7) | (blank & 7);
   nbl = __shfl_sync(0xffffffffu, nbl, src);
   const float inv_s = __fdividef(1.0f, ssum);
-  const float inv_nb = 1.0f / nbl;
-  unsigned char* row = rows + (size_t)f * ROWB;
-  uint2* Rrow = reinterpret_cast<uint2*>(row);
-  float* yrow = reinterpret_cast<float*>(row + YOFF);
+  const float inv_nb = __fdividef(1.0f, nbl);
   float logyb = 0.f;
-  if (valid) {
-    bool bad = false;
+  if (f < len) {
+    unsigned char* row = rows + (size_t)f * ROWB;
+    uint32_t* Rrow = reinterpret_cast<uint32_t*>(row);
+    float* yrow = reinterpret_cast<float*>(row + YOFF);
 #pragma unroll
     for (int e = 0; e < EPL; e++) {
       const int c = sub + 8 * e;
-      if (c < C) {
-        const float r = n[e] * inv_nb;
-        // the recursion needs a normal float: anything else (blank or class probability underflowed,
-        // inf, nan) is the robust kernel's business
-        bad |= !(r >= 1.1754944e-38f && r <= 1.0e38f);
-        // (double)r assembled from the bits of the normal float r: no F2F on this path
-        const uint32_t rb = __float_as_uint(r);
-        Rrow[c] = make_uint2(rb << 29, (rb >> 3) + (896u << 20));
-        yrow[c] = n[e] * inv_s;
-      }
+      // high word of (double)(n/n_blank) from the bits of the float, rounded to nearest (no F2F here);
+      // the padding columns get garbage that nothing reads
+      Rrow[c] = ((__float_as_uint(n[e] * inv_nb) + 4u) >> 3) + (896u << 20);
+      yrow[c] = n[e] * inv_s;
     }
-    if (sub == 0) Rrow[C] = make_uint2(0u, 0u);
-    if (bad) atomicOr(alarm_word, (int)AL_EMISSION);
+    // every ratio n/n_blank must be a normal float: n >= FLT_MIN (then n/n_blank >= FLT_MIN because
+    // n_blank <= 1) and n_blank >= 1e-38 (then n/n_blank <= 1e38).  Anything else -- a class or blank
+    // probability that underflowed, inf, nan -- is the robust kernel's business.
+    if (!(nmin >= 1.1754944e-38f && nbl >= 1.0e-38f && ssum <= 3.0e38f)) atomicOr(alarm_word, (int)AL_EMISSION);
     if (sub == (blank & 7)) logyb = (xbl - m) - __logf(ssum);
   }
   return logyb;
@@ -400,6 +405,13 @@ template <int NL>
 __device__ __forceinline__ uint32_t gcell(int pos) {
   return (uint32_t)((pos % NL) * 32 + pos / NL);
 }
+
+// How many CTAs of this kernel currently sit on each SM (incremented on arrival, decremented on exit, so it
+// is zero between launches).  A CTA uses its arrival rank to pick its warp->role permutation: the block
+// scheduler's pairing of CTAs on an SM is not a function of blockIdx (measured: only 30 of 108 pairs are
+// (b, b+148)), and two CTAs with the same permutation put all four recursion warps of phase 1 on two of the
+// four schedulers.
+__device__ int g_sm_arrivals[1024];
 
 template <int NL, int EPL>
 __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(const Params p) {
@@ -492,6 +504,11 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
     for (int i = 0; i < j; i++) r += (s_lab[i] == v);
     s_pos[j] = (uint16_t)(s_cls_off[v] + r);
   }
+  // raw rows: the columns past C stay -inf for the whole kernel; row records: the zero entry of dead slots
+  for (int i = tid; i < 2 * 4 * KC * CMAX; i += NTHREADS)
+    if (i % CMAX >= C) s_raw[i] = -INFINITY;
+  for (int i = tid; i < 2 * 4 * KC; i += NTHREADS)
+    *reinterpret_cast<uint32_t*>(s_rows + (size_t)i * rowbytes + CMAX * 4) = 0u;
   // the zero cell of every posterior row (prefix "before position 0")
   for (int i = tid; i < 2 * 2 * KC; i += NTHREADS) {
     float* row = s_gbuf + (size_t)i * gstride;
@@ -528,7 +545,11 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
 
   // roles: the second CTA that lands on an SM swaps recursion and recompute warps (and producer and
   // gradient warps) so that the four heavy warps of phase 1 sit on four different schedulers
-  const int perm = (blockIdx.x / max(1, p.num_sms)) & 1;
+  unsigned smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  if (tid == 0) s_scal[3] = atomicAdd(&g_sm_arrivals[smid & 1023], 1);
+  __syncthreads();
+  const int perm = s_scal[3] & 1;
   const int role = warp ^ (perm << 1);
   const int d = role & 1;  // direction / side this warp works for
   __syncthreads();
@@ -536,7 +557,7 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
   Dir<NL> st;
   uint32_t gphys[NL];  // recursion warps: byte offset of slot k's posterior inside a posterior row
   if (role <= RC_B) {
-    dir_setup<NL>(st, d, lane, s_lab, L, C);
+    dir_setup<NL>(st, d, lane, s_lab, L, CMAX);
     const int pad = N - L - 1;
 #pragma unroll
     for (int k = 0; k < NL; k++) {
@@ -578,8 +599,14 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
 #define NASR_PROF_BEGIN() const long long prof_a = p.prof ? clock64() : 0
 #define NASR_PROF_END()                                    \
   if (p.prof) {                                            \
-    const long long dt = clock64() - prof_a;               \
+    const long long pe = clock64();                        \
+    const long long dt = pe - prof_a;                      \
     if (I < S.P1) prof_w1 += dt; else prof_w2 += dt;       \
+    if (b < 4 && lane == 0 && I - IFIRST < 200) {          \
+      long long* tr = p.prof + (size_t)p.B * 32 + (((size_t)b * 200 + (I - IFIRST)) * 8 + warp) * 2; \
+      tr[0] = prof_a - prof_t0;                            \
+      tr[1] = pe - prof_t0;                                \
+    }                                                      \
   }
   if (role == H_F || role == H_B) {
 #pragma unroll 1
@@ -609,7 +636,7 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
           for (int k = NL - 1; k >= 0; k--) {
             const double alp = k > 0 ? st.Al[k - 1] : a_in;
             const double nb = st.Ab[k] + alp;
-            const double pre = st.Al[k] + (st.mask[k] ? nb : st.Ab[k]);
+            const double pre = fma(st.skip[k], alp, st.Al[k] + st.Ab[k]);
             s_meet_nb[k * 32 + lane] = nb;
             s_meet_pre[k * 32 + lane] = pre;
           }
@@ -695,7 +722,7 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
       // this warp computes direction d's rows; they are consumed by the other direction (side d^1)
       const int side = d ^ 1;
       const Chunk ci = chunk_at(S, side, I + 1);
-      if (ci.phase == 2 && want_grad) {
+      if (ci.phase == 2 && want_grad && !(p.ablate & 4)) {
         const uint32_t* ck = ckpt_ptr<NL>(p, b, d, ci.idx);
 #pragma unroll
         for (int k = 0; k < NL; k++) {
@@ -725,7 +752,7 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
       NASR_PROF_BEGIN();
       {  // raw rows of the chunk of iteration I+2 (complete and visible since the last barrier) -> row records
         const Chunk ci = chunk_at(S, d, I + 2);
-        if (ci.phase != 0 && (ci.phase == 1 || want_grad)) {
+        if (ci.phase != 0 && (ci.phase == 1 || (want_grad && !(p.ablate & 2)))) {
           unsigned char* rows = s_rows + (size_t)(d * 4 + ((I + 2) & 3)) * KC * rowbytes;
           const float* raw = s_raw + (size_t)(d * 4 + ((I + 2) & 3)) * KC * CMAX;
           const float l0v = rows_to_smem<EPL, ROWB, YOFF>(raw, rl, ci.len, rows, C, blank, s_scal);
@@ -739,7 +766,7 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
       }
       {  // issue the copies for the chunk of iteration I+5 (one commit group per iteration, empty or not)
         const Chunk ci = chunk_at(S, d, I + 5);
-        if (ci.phase != 0 && (ci.phase == 1 || want_grad)) {
+        if (ci.phase != 0 && (ci.phase == 1 || (want_grad && !(p.ablate & 2)))) {
           float* raw = s_raw + (size_t)(d * 4 + ((I + 5) & 3)) * KC * CMAX;
 #pragma unroll
           for (int g = 0; g < KC / 4; g++) {
@@ -748,7 +775,8 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
             const int t = d ? ci.base - ff : ci.base + ff;
             const float* xrow = p.logits + ((size_t)t * B + b) * C;
 #pragma unroll
-            for (int e = 0; e < EPL; e++) cp_async4(raw + f * CMAX + sub + 8 * e, xrow + min(sub + 8 * e, C - 1));
+            for (int e = 0; e < EPL; e++)
+              if (sub + 8 * e < C) cp_async4(raw + f * CMAX + sub + 8 * e, xrow + sub + 8 * e);
           }
         }
         cp_async_commit();
@@ -776,7 +804,7 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
       // posterior rows are in class-sorted order: an inclusive prefix sum turns "occupancy of class c" into
       // the difference of two prefixes
       const Chunk ci = chunk_at(S, d, I - 1);
-      if (ci.phase == 2 && want_grad) {
+      if (ci.phase == 2 && want_grad && !(p.ablate & 1)) {
         const int buf = (I - 1) & 1;
         float* G = s_gbuf + (size_t)(d * 2 + buf) * GBUF;
         const unsigned char* rows = s_rows + (size_t)(d * 4 + ((I - 1) & 3)) * KC * rowbytes;
@@ -842,11 +870,16 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
 #undef NASR_PROF_END
   if (p.prof && lane == 0) {
     long long* q = p.prof + ((size_t)b * 8 + warp) * 4;
-    q[0] = prof_w1; q[1] = prof_w2; q[2] = clock64() - prof_t0; q[3] = role;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    q[0] = prof_w1; q[1] = prof_w2; q[2] = clock64() - prof_t0; q[3] = role | ((long long)smid << 8);
   }
   if (alarm) atomicOr(&s_scal[0], alarm);
   __syncthreads();
-  if (tid == 0) p.retry[b] = s_scal[0];
+  if (tid == 0) {
+    p.retry[b] = s_scal[0];
+    atomicSub(&g_sm_arrivals[smid & 1023], 1);
+  }
 }
 
 }  // namespace fast
@@ -892,6 +925,7 @@ int launch_fast_c(const fast::Params& p, cudaStream_t stream) {
 }  // namespace
 
 int g_debug_split = 0;  // test hook (nasr_debug_config): frames of the forward half, 0 = automatic
+int g_debug_ablate = 0;
 long long* g_debug_prof = nullptr;  // test hook (nasr_debug_profile): device buffer for per-warp cycle counts
 
 static int max_chunks(int T) {
@@ -925,6 +959,7 @@ int ctc_fast_launch(const float* logits, int T, int B, int C, const int32_t* lab
   p.maxch = max_chunks(T);
   p.split = g_debug_split;
   p.prof = g_debug_prof;
+  p.ablate = g_debug_ablate;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;

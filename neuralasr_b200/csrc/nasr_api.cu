@@ -42,6 +42,7 @@ int batch_sums(const float* loss, const float* ler, const int32_t* dist, int B, 
 extern int g_debug_path;   // ctc_loss.cu
 extern int g_debug_split;  // ctc_fast.cu
 extern long long* g_debug_prof;
+extern int g_debug_ablate;
 
 namespace {
 
@@ -124,7 +125,9 @@ const char* nasr_last_error(void) { return t_err; }
 uint64_t nasr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int nasr_debug_config(int path, int split_frames) {
-  NASR_CHECK_ARG(path >= 0 && path <= 2 && split_frames >= 0, "nasr_debug_config: bad arguments");
+  NASR_CHECK_ARG(path >= 0 && (path & 0xff) <= 2 && split_frames >= 0, "nasr_debug_config: bad arguments");
+  g_debug_ablate = path >> 8;  // tuning only: switch warp roles off to see what they cost (results are then wrong)
+  path &= 0xff;
   g_debug_path = path;
   g_debug_split = split_frames;
   return NASR_OK;

@@ -87,7 +87,7 @@ if which in ("all", "time", "roles"):
     x = torch.from_numpy(g["logits"]).to(dev)
     lab = common.prepare_labels(_triple(g), dev)
     seq = torch.from_numpy(g["seq_len"]).to(dev)
-    prof = torch.zeros(256 * 8 * 4, dtype=torch.int64, device=dev)
+    prof = torch.zeros(256 * 8 * 4 + 4 * 200 * 8 * 2, dtype=torch.int64, device=dev)
     common.debug_config(2, 0)
     gr = torch.empty_like(x)
     common.ctc_loss_and_grad(x, lab, seq, out_grad=gr)
@@ -96,13 +96,54 @@ if which in ("all", "time", "roles"):
     torch.cuda.synchronize()
     lib.nasr_debug_profile(None)
     common.debug_config(0, 0)
-    pr = prof.cpu().numpy().reshape(256, 8, 4)
+    trace = prof.cpu().numpy()[256 * 32:].reshape(4, 200, 8, 2)
+    np.save(os.path.join(ROOT, 'gpurun_out', 'r1_trace.npy'), trace)
+    np.save(os.path.join(ROOT, 'gpurun_out', 'r1_trace_roles.npy'), prof.cpu().numpy()[:256 * 32].reshape(256, 8, 4)[:4, :, 3])
+    pr = prof.cpu().numpy()[:256 * 32].reshape(256, 8, 4)
     names = ["H_F", "H_B", "RC_F", "RC_B", "P_F", "P_B", "G_F", "G_B"]
     print("per-role cycles (mean over CTAs | max): work before meeting, work after meeting, total")
     for r in range(8):
-        sel = pr[:, :, 3] == r
+        sel = (pr[:, :, 3] & 255) == r
         w1, w2, tot = pr[:, :, 0][sel], pr[:, :, 1][sel], pr[:, :, 2][sel]
         print("  %-5s phase1 %8.0f | %8d   phase2 %8.0f | %8d   total %8.0f | %8d" % (names[r], w1.mean(), w1.max(), w2.mean(), w2.max(), tot.mean(), tot.max()))
+    smid = pr[:, 0, 3] >> 8
+    print("  smid of CTA 0..15:", smid[:16].tolist(), " CTA 148..163:", smid[148:164].tolist())
+    import collections
+    by = collections.defaultdict(list)
+    for bb in range(256):
+        by[int(smid[bb])].append(bb)
+    pairs = [v for v in by.values() if len(v) == 2]
+    print("  SMs with two CTAs: %d; examples of co-resident CTA ids: %s; pairs whose ids differ by 148: %d" % (
+        len(pairs), pairs[:8], sum(1 for v in pairs if abs(v[0] - v[1]) == 148)))
     L = np.diff(g["label_offsets"])
     tot = pr[:, 0, 2]
     print("  total cycles by CTA index: first wave(0..147) mean %.0f, second wave(148..255) mean %.0f" % (tot[:148].mean(), tot[148:].mean()))
+if which == "ablate":
+    g = make_batch(1234, T=1000, B=256, C=38, Lmax=200, mode="full", Lmin=100, empty_row=False)
+    x = torch.from_numpy(g["logits"]).to(dev)
+    lab = common.prepare_labels(_triple(g), dev)
+    seq = torch.from_numpy(g["seq_len"]).to(dev)
+    xs = [x.clone() for _ in range(4)]
+    gs = [torch.empty_like(x) for _ in range(4)]
+    for mask, name in [(0, "full"), (1, "no gradient warps"), (2, "no producers in phase 2"), (4, "no recompute"), (7, "recursion only"), (1 | 4, "no grad, no recompute")]:
+        common.debug_config(2 | (mask << 8), 0)
+        for i in range(3):
+            common.ctc_loss_and_grad(xs[i % 4], lab, seq, out_grad=gs[i % 4])
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(20):
+            common.ctc_loss_and_grad(xs[i % 4], lab, seq, out_grad=gs[i % 4])
+        b.record(); torch.cuda.synchronize()
+        print("ablate %-28s %.3f ms" % (name, a.elapsed_time(b) / 20))
+    # loss only = phase 1 only
+    common.debug_config(2, 0)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(3):
+        common.ctc_loss_and_grad(xs[i % 4], lab, seq, want_grad=False)
+    torch.cuda.synchronize(); a.record()
+    for i in range(20):
+        common.ctc_loss_and_grad(xs[i % 4], lab, seq, want_grad=False)
+    b.record(); torch.cuda.synchronize()
+    print("loss only (phase 1 + meeting)        %.3f ms" % (a.elapsed_time(b) / 20))
+    common.debug_config(0, 0)

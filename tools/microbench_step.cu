@@ -22,7 +22,7 @@ __global__ void bench(double* out, long long* cycles, int chunks) {
   Dir<NL> st;
   uint32_t gphys[NL];
   for (int k = 0; k < NL; k++) {
-    st.Ab[k] = 1.0 + lane; st.Al[k] = 0.5 + k; st.coloff[k] = ((lane * NL + k) % 38) * 8; st.mask[k] = (k & 1) ? 0xffffffffu : 0u;
+    st.Ab[k] = 1.0 + lane; st.Al[k] = 0.5 + k; st.coloff[k] = ((lane * NL + k) % 38) * 8; st.skip[k] = (maskin[lane * NL + k]) ? 1.0 : 0.0;
     gphys[k] = ((k * 32 + (lane * 5 + k) % 32)) * 4;
   }
   st.E = 0;
