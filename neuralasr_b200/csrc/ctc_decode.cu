@@ -32,29 +32,70 @@ greedy_decode_kernel(const float* __restrict__ logits, int T, int B, int C,
   float acc = 0.f;     // warp 1 lane 0
   for (int base = 0; base < Tb; base += kDecodeChunk) {
     const int n = min(kDecodeChunk, Tb - base);
-    for (int i = warp; i < n; i += nw) {
-      const float* x = logits + ((size_t)(base + i) * B + b) * C;
-      float m = -INFINITY;
-      int am = 0x7fffffff;
-      for (int c = lane; c < C; c += 32) {
-        const float v = __ldg(x + c);
-        if (am == 0x7fffffff || v > m) {  // strict '>' keeps the earliest index within a lane
-          m = v;
-          am = c;
-        }
-      }
+    if (C <= 64) {
+      // narrow rows (a row is 152 B at C=38): 8 lanes per frame, 4 frames per warp instruction and 4 such
+      // groups in flight, so that 32 independent loads per lane cover the DRAM latency
+      const int sub = lane & 7, rl = lane >> 3;
+      for (int g0 = warp; g0 * 4 < n; g0 += nw * 4) {
+        float v[4][8];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float om = __shfl_xor_sync(0xffffffffu, m, o);
-        const int oa = __shfl_xor_sync(0xffffffffu, am, o);
-        if (om > m || (om == m && oa < am)) {
-          m = om;
-          am = oa;
+        for (int u = 0; u < 4; u++) {
+          const int i = min((g0 + u * nw) * 4 + rl, n - 1);
+          const float* x = logits + ((size_t)(base + i) * B + b) * C;
+#pragma unroll
+          for (int e = 0; e < 8; e++) v[u][e] = __ldg(x + min(sub + 8 * e, C - 1));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = (g0 + u * nw) * 4 + rl;
+          float m = v[u][0];
+          int am = sub;
+#pragma unroll
+          for (int e = 1; e < 8; e++)
+            if (sub + 8 * e < C && v[u][e] > m) {  // strict '>' keeps the earliest index within a lane
+              m = v[u][e];
+              am = sub + 8 * e;
+            }
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, m, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+            if (om > m || (om == m && oa < am)) {
+              m = om;
+              am = oa;
+            }
+          }
+          if (sub == 0 && i < n) {
+            s_id[i] = am;
+            s_mx[i] = m;
+          }
         }
       }
-      if (lane == 0) {
-        s_id[i] = am;
-        s_mx[i] = m;
+    } else {
+      for (int i = warp; i < n; i += nw) {
+        const float* x = logits + ((size_t)(base + i) * B + b) * C;
+        float m = -INFINITY;
+        int am = 0x7fffffff;
+        for (int c = lane; c < C; c += 32) {
+          const float v = __ldg(x + c);
+          if (am == 0x7fffffff || v > m) {  // strict '>' keeps the earliest index within a lane
+            m = v;
+            am = c;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float om = __shfl_xor_sync(0xffffffffu, m, o);
+          const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+          if (om > m || (om == m && oa < am)) {
+            m = om;
+            am = oa;
+          }
+        }
+        if (lane == 0) {
+          s_id[i] = am;
+          s_mx[i] = m;
+        }
       }
     }
     __syncthreads();
@@ -81,15 +122,22 @@ greedy_decode_kernel(const float* __restrict__ logits, int T, int B, int C,
   if (warp == 1 && lane == 0 && neg_sum_logits) neg_sum_logits[b] = acc;
 }
 
-// One warp per utterance, anti-diagonal wavefront over the (truth x hyp) lattice; three diagonals and
-// both symbol strings live in shared memory.  dist = D[n][m], exact integers.
+// One warp per utterance.  Fast path: Myers' bit-vector algorithm in its block form -- lane w owns bits
+// [32w, 32w+32) of the truth (pattern) axis: vertical deltas Pv/Mv of one column of the DP lattice as two
+// words; per hypothesis symbol each lane does ~20 integer operations and hands the horizontal delta at the
+// top of its block (-1, 0, +1) to the next lane.  The lanes run skewed by one symbol (lane w works on symbol
+// s-w at step s), so the hand-off is one shuffle per step and the whole utterance takes |hyp| + W - 1 steps
+// instead of the |hyp| + |truth| barrier-separated anti-diagonals of the plain DP.  Match masks Peq[sym][w]
+// live in shared memory, indexed by symbol value.  Exact integers (tests compare with the oracle bit for bit).
+// Slow path (truth longer than 1024 symbols, or symbol values too large for the table): anti-diagonal
+// wavefront, three diagonals and both strings in shared memory.
 template <typename HypT>
 __global__ void __launch_bounds__(32)
 edit_distance_kernel(const HypT* __restrict__ hyp, long hyp_stride, const int32_t* __restrict__ hyp_len,
                      const int32_t* __restrict__ hyp_offsets,
                      const int32_t* __restrict__ truth_values, const int32_t* __restrict__ truth_offsets,
-                     int max_truth_len, int max_hyp_len, int normalize, int32_t* __restrict__ dist,
-                     float* __restrict__ ler) {
+                     int max_truth_len, int max_hyp_len, int table_words, int normalize,
+                     int32_t* __restrict__ dist, float* __restrict__ ler) {
   extern __shared__ int sm[];
   const int b = blockIdx.x, lane = threadIdx.x;
   const int t0 = truth_offsets[b];
@@ -109,39 +157,93 @@ edit_distance_kernel(const HypT* __restrict__ hyp, long hyp_stride, const int32_
   } else if (n == 0 || m == 0) {
     d = n + m;
   } else {
-    int* tr = sm;                       // [max_truth_len]
-    int* hy = tr + max_truth_len;       // [max_hyp_len]
-    int* d0 = hy + max_hyp_len;         // three diagonals, indexed by truth position j in [0, m]
-    int* d1 = d0 + max_truth_len + 1;
-    int* d2 = d1 + max_truth_len + 1;
-    for (int j = lane; j < m; j += 32) tr[j] = truth_values[t0 + j];
-    for (int i = lane; i < n; i += 32) hy[i] = (int)h[i];  // the reference casts int64 -> int32 first
-    __syncwarp();
-    // diagonal k holds cells (i, j) with i + j = k, i over hyp [0,n], j over truth [0,m]
-    int* pp = d0;  // diagonal k-2
-    int* pv = d1;  // diagonal k-1
-    int* cu = d2;  // diagonal k
-    for (int k = 0; k <= n + m; k++) {
-      const int jlo = max(0, k - n), jhi = min(m, k);
-      for (int j = jlo + lane; j <= jhi; j += 32) {
-        const int i = k - j;
-        int v;
-        if (i == 0) {
-          v = j;
-        } else if (j == 0) {
-          v = i;
-        } else {
-          v = min(min(pv[j] + 1, pv[j - 1] + 1), pp[j - 1] + (hy[i - 1] != tr[j - 1]));
-        }
-        cu[j] = v;
-      }
-      __syncwarp();
-      int* tmp = pp;
-      pp = pv;
-      pv = cu;
-      cu = tmp;
+    // does the bit-vector path apply?  W words of 32 truth positions, one per lane; table of (max symbol+1) x W
+    const int W = (m + 31) >> 5;
+    int mx = -1, mn = 0;
+    for (int j = lane; j < m; j += 32) {
+      const int v = truth_values[t0 + j];
+      mx = max(mx, v);
+      mn = min(mn, v);
     }
-    d = pv[m];
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    const long long need = (long long)(mx + 1) * W;
+    if (W <= 32 && mn >= 0 && need <= table_words) {
+      unsigned* peq = reinterpret_cast<unsigned*>(sm);  // [sym][W]
+      const int nsym = mx + 1;
+      for (int i = lane; i < nsym * W; i += 32) peq[i] = 0u;
+      __syncwarp();
+      for (int j = lane; j < m; j += 32) atomicOr(&peq[truth_values[t0 + j] * W + (j >> 5)], 1u << (j & 31));
+      __syncwarp();
+      unsigned Pv = 0xffffffffu, Mv = 0u;
+      int score = m;
+      const int lastw = W - 1;
+      const int topbit = lane == lastw ? ((m - 1) & 31) : 31;
+      int hout = 0;
+      long long cnext = (lane == 0) ? (long long)h[0] : 0;
+      const int steps = n + W - 1;
+      for (int s = 0; s < steps; s++) {
+        const int hin_up = __shfl_up_sync(0xffffffffu, hout, 1);
+        const int i = s - lane;
+        const bool active = lane < W && i >= 0 && i < n;
+        const long long c = cnext;
+        // prefetch the symbol of the next step (lane w reads hyp[s+1-w])
+        const int inext = i + 1;
+        if (lane < W && inext >= 0 && inext < n) cnext = (long long)h[inext];
+        if (active) {
+          const int hin = lane == 0 ? 1 : hin_up;
+          unsigned Eq = (c >= 0 && c < nsym) ? peq[(int)c * W + lane] : 0u;
+          const unsigned Xv = Eq | Mv;
+          if (hin < 0) Eq |= 1u;
+          const unsigned Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+          unsigned Ph = Mv | ~(Xh | Pv);
+          unsigned Mh = Pv & Xh;
+          hout = (int)((Ph >> topbit) & 1u) - (int)((Mh >> topbit) & 1u);
+          if (lane == lastw) score += hout;
+          Ph <<= 1;
+          Mh <<= 1;
+          if (hin < 0) Mh |= 1u;
+          else if (hin > 0) Ph |= 1u;
+          Pv = Mh | ~(Xv | Ph);
+          Mv = Ph & Xv;
+        }
+      }
+      d = __shfl_sync(0xffffffffu, score, lastw);
+    } else {
+      int* tr = sm;                       // [max_truth_len]
+      int* hy = tr + max_truth_len;       // [max_hyp_len]
+      int* d0 = hy + max_hyp_len;         // three diagonals, indexed by truth position j in [0, m]
+      int* d1 = d0 + max_truth_len + 1;
+      int* d2 = d1 + max_truth_len + 1;
+      for (int j = lane; j < m; j += 32) tr[j] = truth_values[t0 + j];
+      for (int i = lane; i < n; i += 32) hy[i] = (int)h[i];  // the reference casts int64 -> int32 first
+      __syncwarp();
+      // diagonal k holds cells (i, j) with i + j = k, i over hyp [0,n], j over truth [0,m]
+      int* pp = d0;  // diagonal k-2
+      int* pv = d1;  // diagonal k-1
+      int* cu = d2;  // diagonal k
+      for (int k = 0; k <= n + m; k++) {
+        const int jlo = max(0, k - n), jhi = min(m, k);
+        for (int j = jlo + lane; j <= jhi; j += 32) {
+          const int i = k - j;
+          int v;
+          if (i == 0) {
+            v = j;
+          } else if (j == 0) {
+            v = i;
+          } else {
+            v = min(min(pv[j] + 1, pv[j - 1] + 1), pp[j - 1] + (hy[i - 1] != tr[j - 1]));
+          }
+          cu[j] = v;
+        }
+        __syncwarp();
+        int* tmp = pp;
+        pp = pv;
+        pv = cu;
+        cu = tmp;
+      }
+      d = pv[m];
+    }
   }
   if (lane == 0) {
     dist[b] = d;
@@ -222,7 +324,9 @@ int launch_edit_distance(const HypT* hyp, long hyp_stride, const int32_t* hyp_le
                          const int32_t* hyp_offsets, const int32_t* truth_values,
                          const int32_t* truth_offsets, int max_truth_len, int max_hyp_len, int B,
                          int normalize, int32_t* dist, float* ler, cudaStream_t stream) {
-  const size_t smem = sizeof(int) * ((size_t)max_truth_len + max_hyp_len + 3 * ((size_t)max_truth_len + 1));
+  const size_t dp = sizeof(int) * ((size_t)max_truth_len + max_hyp_len + 3 * ((size_t)max_truth_len + 1));
+  const size_t table = 64 * 1024;  // match masks of the bit-vector path: (max symbol + 1) * ceil(|truth|/32) words
+  const size_t smem = dp > table ? dp : table;
   if (smem > 200 * 1024) {
     set_error("nasr_edit_distance: max_truth_len=%d max_hyp_len=%d exceed shared memory", max_truth_len,
               max_hyp_len);
@@ -236,7 +340,7 @@ int launch_edit_distance(const HypT* hyp, long hyp_stride, const int32_t* hyp_le
   }
   edit_distance_kernel<HypT><<<B, 32, smem, stream>>>(hyp, hyp_stride, hyp_len, hyp_offsets,
                                                      truth_values, truth_offsets, max_truth_len,
-                                                     max_hyp_len, normalize, dist, ler);
+                                                     max_hyp_len, (int)(table / 4), normalize, dist, ler);
   count_launch();
   NASR_CUDA(cudaGetLastError());
   return NASR_OK;

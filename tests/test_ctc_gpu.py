@@ -316,3 +316,25 @@ def test_random_shapes_sweep(common):
             g["logits"], g["label_values"], g["label_offsets"], g["seq_len"], precision="f64")
         loss, grad, status = _run_loss(common, g)
         _assert_loss_grad(loss, grad, status, want_loss, want_grad, want_status)
+
+
+def _sparse_from_rows(rows, dtype):
+    idx = np.asarray([(b, j) for b, r in enumerate(rows) for j in range(len(r))], np.int64).reshape(-1, 2)
+    vals = np.asarray([v for r in rows for v in r], dtype)
+    return idx, vals, np.asarray([len(rows), max(1, max(len(r) for r in rows))], np.int64)
+
+
+def test_edit_distance_paths_match_oracle(common):
+    """Bit-vector path (small symbol values, truth <= 1024), and the wavefront path it falls back to for
+    long truths and for symbol values that do not fit the match-mask table."""
+    from neuralasr_b200.networks.common import edit_distance
+    rng = np.random.default_rng(5)
+    cases = []
+    for m, n, hi in [(1, 1, 3), (31, 40, 4), (32, 7, 4), (33, 90, 3), (64, 64, 2), (65, 300, 30), (200, 900, 37),
+                     (1024, 700, 20), (1025, 300, 20), (1500, 1400, 5), (50, 60, 10 ** 6), (0, 5, 3), (7, 0, 3)]:
+        cases.append((rng.integers(0, hi, m).tolist(), rng.integers(0, hi + 1, n).tolist()))
+    truth_rows = [c[0] for c in cases]
+    hyp_rows = [c[1] for c in cases]
+    d, ler = edit_distance(_sparse_from_rows(hyp_rows, np.int64), _sparse_from_rows(truth_rows, np.int32))
+    want = [o.levenshtein(h, t) for t, h in cases]
+    assert d.cpu().numpy().tolist() == want
