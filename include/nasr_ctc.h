@@ -104,9 +104,22 @@ int nasr_ctc_loss_grad_f32(const float* logits, int T, int B, int C,
                            float* loss, float* grad, const float* grad_loss, int32_t* status,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same call for logits / grad whose frames and utterances are strided: element (t, b, c) lives at
+ * logits[t*stride_t + b*stride_b + c] (grad uses the same strides).  stride_t = B*C, stride_b = C is the call
+ * above; stride_t = C, stride_b = T*C reads a batch-major [B, T, C] tensor in place, which removes the
+ * transpose every model tail of the reference performs before create_loss (networks/bilstm_ctc_net.py:48,
+ * lstm_ctc_net.py:43, wavenet.py:171); a block of utterances b0.. of a [T, B, C] tensor is the pointer
+ * logits + b0*C with the parent's strides. */
+int nasr_ctc_loss_grad_strided_f32(const float* logits, int T, int B, int C, long long stride_t,
+                                   long long stride_b, const int32_t* label_values,
+                                   const int32_t* label_offsets, int max_label_len, const int32_t* seq_len,
+                                   int blank, float* loss, float* grad, const float* grad_loss,
+                                   int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Same call with the tensors passed as DLPack tensors (the north-star "ctypes + DLPack buffers" form):
- * device, dtype, rank and contiguity of every argument are validated here instead of in the caller.
- * grad and grad_loss may be NULL. */
+ * device, dtype, rank and layout of every argument are validated here instead of in the caller.
+ * logits (and grad, with identical strides) may be any [T, B, C] view whose innermost stride is 1, e.g. the
+ * transposed view of a batch-major tensor; everything else must be compact.  grad and grad_loss may be NULL. */
 int nasr_ctc_loss_grad_dl(const DLTensor* logits, const DLTensor* label_values,
                           const DLTensor* label_offsets, int max_label_len, const DLTensor* seq_len,
                           int blank, const DLTensor* loss, const DLTensor* grad,
@@ -125,6 +138,12 @@ int nasr_ctc_loss_grad_dl(const DLTensor* logits, const DLTensor* label_values,
 int nasr_ctc_greedy_decode_i64(const float* logits, int T, int B, int C, const int32_t* seq_len,
                                int blank, int merge_repeated, int64_t* hyp, int32_t* hyp_len,
                                float* neg_sum_logits, void* stream);
+
+/* Same for strided logits (see nasr_ctc_loss_grad_strided_f32). */
+int nasr_ctc_greedy_decode_strided_i64(const float* logits, int T, int B, int C, long long stride_t,
+                                       long long stride_b, const int32_t* seq_len, int blank,
+                                       int merge_repeated, int64_t* hyp, int32_t* hyp_len,
+                                       float* neg_sum_logits, void* stream);
 
 /* Dense hypotheses -> the SparseTensor triple TF returns as decoded[0] (tfnetwork.py:64):
  * hyp_offsets int32[B+1] must hold the exclusive prefix sum of hyp_len (M = hyp_offsets[B]);
@@ -164,7 +183,9 @@ int nasr_batch_sums_f64(const float* loss, const float* ler, const int32_t* dist
  * HOST-buffer path: what a caller that holds numpy arrays (the reference's feed_dict world,
  * tfnetwork.py:183-190) uses.  The context owns device buffers, pinned staging and one stream, sized
  * for the maxima given at creation.  One call = H2D of logits/labels/seq_len, loss+grad, greedy decode,
- * edit distance, D2H of the results, and a stream synchronise.
+ * edit distance, D2H of the results, and a stream synchronise.  Large batches are processed in four blocks
+ * of utterances so that the H2D copy of one block, the kernels of the previous one and the D2H copy of the one
+ * before overlap.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct nasr_host_ctx nasr_host_ctx;
 

@@ -24,8 +24,12 @@ SIGNATURES = {
     "nasr_ctc_workspace_bytes": (_i, [_i, _i, _i, _i, ctypes.POINTER(_sz)]),
     "nasr_ctc_loss_grad_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp,
                                     _sz, _vp]),
+    "nasr_ctc_loss_grad_strided_f32": (_i, [_vp, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _vp, _vp, _i, _vp,
+                                            _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nasr_ctc_loss_grad_dl": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nasr_ctc_greedy_decode_i64": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "nasr_ctc_greedy_decode_strided_i64": (_i, [_vp, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _vp, _i, _i,
+                                                _vp, _vp, _vp, _vp]),
     "nasr_hyp_to_sparse_i64": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "nasr_edit_distance_i64": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "nasr_edit_distance_csr_i64": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),

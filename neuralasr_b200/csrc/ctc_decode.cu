@@ -17,7 +17,7 @@ constexpr int kDecodeChunk = 2048;  // frames staged per pass (argmax ids + max 
 // (coalesced row read).  Phase 2: warp 0 collapses (drop blank, merge repeats) with ballot compaction
 // while lane 0 of warp 1 accumulates -max in frame order.
 __global__ void __launch_bounds__(kDecodeThreads)
-greedy_decode_kernel(const float* __restrict__ logits, int T, int B, int C,
+greedy_decode_kernel(const float* __restrict__ logits, int T, int B, int C, long long st_t, long long st_b,
                      const int32_t* __restrict__ seq_len, int blank, int merge_repeated,
                      int64_t* __restrict__ hyp, int32_t* __restrict__ hyp_len,
                      float* __restrict__ neg_sum_logits) {
@@ -41,7 +41,7 @@ greedy_decode_kernel(const float* __restrict__ logits, int T, int B, int C,
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const int i = min((g0 + u * nw) * 4 + rl, n - 1);
-          const float* x = logits + ((size_t)(base + i) * B + b) * C;
+          const float* x = logits + (size_t)(base + i) * st_t + (size_t)b * st_b;
 #pragma unroll
           for (int e = 0; e < 8; e++) v[u][e] = __ldg(x + min(sub + 8 * e, C - 1));
         }
@@ -73,7 +73,7 @@ greedy_decode_kernel(const float* __restrict__ logits, int T, int B, int C,
       }
     } else {
       for (int i = warp; i < n; i += nw) {
-        const float* x = logits + ((size_t)(base + i) * B + b) * C;
+        const float* x = logits + (size_t)(base + i) * st_t + (size_t)b * st_b;
         float m = -INFINITY;
         int am = 0x7fffffff;
         for (int c = lane; c < C; c += 32) {
@@ -348,14 +348,15 @@ int launch_edit_distance(const HypT* hyp, long hyp_stride, const int32_t* hyp_le
 
 }  // namespace
 
-int greedy_decode(const float* logits, int T, int B, int C, const int32_t* seq_len, int blank,
-                  int merge_repeated, int64_t* hyp, int32_t* hyp_len, float* neg_sum_logits,
-                  cudaStream_t stream) {
+int greedy_decode(const float* logits, int T, int B, int C, long long st_t, long long st_b,
+                  const int32_t* seq_len, int blank, int merge_repeated, int64_t* hyp, int32_t* hyp_len,
+                  float* neg_sum_logits, cudaStream_t stream) {
+  NASR_CHECK_ARG(st_t >= 0 && st_b >= 0, "nasr_ctc_greedy_decode: negative stride");
   NASR_CHECK_ARG(T >= 0 && B >= 0 && C >= 1, "nasr_ctc_greedy_decode: bad shape T=%d B=%d C=%d", T, B, C);
   if (B == 0) return NASR_OK;
   NASR_CHECK_ARG((logits || T == 0) && seq_len && hyp_len && (hyp || T == 0),
                  "nasr_ctc_greedy_decode: NULL argument");
-  greedy_decode_kernel<<<B, kDecodeThreads, 0, stream>>>(logits, T, B, C, seq_len, blank,
+  greedy_decode_kernel<<<B, kDecodeThreads, 0, stream>>>(logits, T, B, C, st_t, st_b, seq_len, blank,
                                                         merge_repeated, hyp, hyp_len, neg_sum_logits);
   count_launch();
   NASR_CUDA(cudaGetLastError());

@@ -53,6 +53,7 @@ enum Role { H_F = 0, H_B = 1, RC_F = 2, RC_B = 3, P_F = 4, P_B = 5, G_F = 6, G_B
 struct Params {
   const float* logits;
   int T, B, C;
+  long long st_t, st_b;  // element strides of logits and grad between frames / between utterances
   const int32_t* lab_vals;
   const int32_t* lab_offs;
   const int32_t* seq_len;
@@ -516,8 +517,8 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
   }
 
   // ---- gradient rows of padded frames are exactly zero -----------------------------------------
-  const size_t rstride = (size_t)B * C;
-  float* gbase = p.grad ? p.grad + (size_t)b * C : nullptr;
+  const size_t rstride = (size_t)p.st_t;
+  float* gbase = p.grad ? p.grad + (size_t)b * p.st_b : nullptr;
   if (gbase) {
     const size_t n = (size_t)(T - Tb) * C;
     for (size_t i = tid; i < n; i += NTHREADS) {
@@ -773,7 +774,7 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
             const int f = g * 4 + rl;
             const int ff = min(f, ci.len - 1);
             const int t = d ? ci.base - ff : ci.base + ff;
-            const float* xrow = p.logits + ((size_t)t * B + b) * C;
+            const float* xrow = p.logits + (size_t)t * p.st_t + (size_t)b * p.st_b;
 #pragma unroll
             for (int e = 0; e < EPL; e++)
               if (sub + 8 * e < C) cp_async4(raw + f * CMAX + sub + 8 * e, xrow + sub + 8 * e);
@@ -946,12 +947,13 @@ size_t ctc_fast_workspace_bytes(int T, int B, int C, int Lmax) {
   return (size_t)B * 2 * max_chunks(T) * (2 * NL + 1) * 32 * sizeof(uint32_t);
 }
 
-int ctc_fast_launch(const float* logits, int T, int B, int C, const int32_t* label_values,
+int ctc_fast_launch(const float* logits, int T, int B, int C, long long st_t, long long st_b,
+                    const int32_t* label_values,
                     const int32_t* label_offsets, int Lmax, const int32_t* seq_len, int blank, float* loss,
                     float* grad, const float* grad_loss, int32_t* status, int32_t* retry, void* ckpt,
                     cudaStream_t stream) {
   fast::Params p;
-  p.logits = logits; p.T = T; p.B = B; p.C = C;
+  p.logits = logits; p.T = T; p.B = B; p.C = C; p.st_t = st_t; p.st_b = st_b;
   p.lab_vals = label_values; p.lab_offs = label_offsets; p.seq_len = seq_len;
   p.blank = blank; p.loss = loss; p.grad = grad; p.grad_loss = grad_loss; p.status = status;
   p.retry = retry;

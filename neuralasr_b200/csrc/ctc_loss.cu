@@ -93,6 +93,7 @@ bool make_plan(int T, int B, int C, int Lmax, Plan* p) {
 struct Params {
   const float* logits;
   int T, B, C;
+  long long st_t, st_b;  // element strides of logits and grad between frames / between utterances
   const int32_t* lab_vals;
   const int32_t* lab_offs;
   const int32_t* seq_len;
@@ -117,7 +118,7 @@ __device__ void softmax_rows(const Params& p, int b, int t0, int t1, float* yseg
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int C = p.C;
   for (int t = t0 + warp; t < t1; t += nw) {
-    const float* x = p.logits + ((size_t)t * p.B + b) * C;
+    const float* x = p.logits + (size_t)t * p.st_t + (size_t)b * p.st_b;
     float* y = yseg + (size_t)(t - t0) * p.Cpad;
     float m = -INFINITY;
     for (int c = lane; c < C; c += 32) {
@@ -209,8 +210,8 @@ __global__ void __launch_bounds__(512) ctc_robust_kernel(const Params p) {
   const int L = p.lab_offs[b + 1] - l0;
   const int U = 2 * L + 1;
   const float gs = p.grad_loss ? p.grad_loss[b] : 1.0f;
-  const size_t rstride = (size_t)B * C;          // elements between consecutive frames of one utterance
-  float* gbase = p.grad ? p.grad + (size_t)b * C : nullptr;
+  const size_t rstride = (size_t)p.st_t;         // elements between consecutive frames of one utterance
+  float* gbase = p.grad ? p.grad + (size_t)b * p.st_b : nullptr;
 
   // ---- validation (TF: InvalidArgument) -------------------------------------------------------
   int st = 0;
@@ -480,8 +481,8 @@ __global__ void __launch_bounds__(512) ctc_robust_kernel(const Params p) {
 // implemented in ctc_fast.cu
 bool ctc_fast_supported(int T, int C, int Lmax);
 size_t ctc_fast_workspace_bytes(int T, int B, int C, int Lmax);
-int ctc_fast_launch(const float* logits, int T, int B, int C, const int32_t* label_values,
-                    const int32_t* label_offsets, int Lmax, const int32_t* seq_len, int blank, float* loss,
+int ctc_fast_launch(const float* logits, int T, int B, int C, long long st_t, long long st_b,
+                    const int32_t* label_values, const int32_t* label_offsets, int Lmax, const int32_t* seq_len, int blank, float* loss,
                     float* grad, const float* grad_loss, int32_t* status, int32_t* retry, void* ckpt,
                     cudaStream_t stream);
 
@@ -502,10 +503,11 @@ int ctc_workspace_bytes(int T, int B, int C, int Lmax, size_t* out) {
   return NASR_OK;
 }
 
-int ctc_loss_grad(const float* logits, int T, int B, int C, const int32_t* label_values,
-                  const int32_t* label_offsets, int Lmax, const int32_t* seq_len, int blank,
-                  float* loss, float* grad, const float* grad_loss, int32_t* status, void* workspace,
+int ctc_loss_grad(const float* logits, int T, int B, int C, long long st_t, long long st_b,
+                  const int32_t* label_values, const int32_t* label_offsets, int Lmax, const int32_t* seq_len,
+                  int blank, float* loss, float* grad, const float* grad_loss, int32_t* status, void* workspace,
                   size_t workspace_bytes, cudaStream_t stream) {
+  NASR_CHECK_ARG(st_t >= 0 && st_b >= 0, "nasr_ctc_loss_grad: negative stride");
   NASR_CHECK_ARG(T >= 0 && B >= 0 && C >= 1 && Lmax >= 0, "nasr_ctc_loss_grad: bad shape T=%d B=%d C=%d L=%d", T, B, C, Lmax);
   NASR_CHECK_ARG(blank >= 0 && blank < C, "nasr_ctc_loss_grad: blank=%d outside [0,%d)", blank, C);
   NASR_CHECK_ARG(C < kSkipBit, "nasr_ctc_loss_grad: C too large");
@@ -532,13 +534,13 @@ int ctc_loss_grad(const float* logits, int T, int B, int C, const int32_t* label
 
   const bool use_fast = g_debug_path != 1 && ctc_fast_supported(T, C, Lmax);
   if (use_fast) {
-    int rc = ctc_fast_launch(logits, T, B, C, label_values, label_offsets, Lmax, seq_len, blank, loss, grad,
+    int rc = ctc_fast_launch(logits, T, B, C, st_t, st_b, label_values, label_offsets, Lmax, seq_len, blank, loss, grad,
                              grad_loss, status, retry, fast_ckpt, stream);
     if (rc != NASR_OK) return rc;
     if (g_debug_path == 2) return NASR_OK;  // test hook: leave flagged utterances alone (retry[] tells which)
   }
   Params p;
-  p.logits = logits; p.T = T; p.B = B; p.C = C;
+  p.logits = logits; p.T = T; p.B = B; p.C = C; p.st_t = st_t; p.st_b = st_b;
   p.lab_vals = label_values; p.lab_offs = label_offsets; p.seq_len = seq_len;
   p.blank = blank; p.Lmax = Lmax;
   p.loss = loss; p.grad = grad; p.grad_loss = grad_loss; p.status = status;

@@ -22,13 +22,13 @@ void set_error(const char* fmt, ...) {
 
 // implemented in ctc_loss.cu / ctc_decode.cu
 int ctc_workspace_bytes(int T, int B, int C, int Lmax, size_t* out);
-int ctc_loss_grad(const float* logits, int T, int B, int C, const int32_t* label_values,
-                  const int32_t* label_offsets, int Lmax, const int32_t* seq_len, int blank,
-                  float* loss, float* grad, const float* grad_loss, int32_t* status, void* workspace,
+int ctc_loss_grad(const float* logits, int T, int B, int C, long long st_t, long long st_b,
+                  const int32_t* label_values, const int32_t* label_offsets, int Lmax, const int32_t* seq_len,
+                  int blank, float* loss, float* grad, const float* grad_loss, int32_t* status, void* workspace,
                   size_t workspace_bytes, cudaStream_t stream);
-int greedy_decode(const float* logits, int T, int B, int C, const int32_t* seq_len, int blank,
-                  int merge_repeated, int64_t* hyp, int32_t* hyp_len, float* neg_sum_logits,
-                  cudaStream_t stream);
+int greedy_decode(const float* logits, int T, int B, int C, long long st_t, long long st_b,
+                  const int32_t* seq_len, int blank, int merge_repeated, int64_t* hyp, int32_t* hyp_len,
+                  float* neg_sum_logits, cudaStream_t stream);
 int edit_distance_dense(const int64_t* hyp, int hyp_stride, const int32_t* hyp_len,
                         const int32_t* truth_values, const int32_t* truth_offsets, int max_truth_len,
                         int B, int normalize, int32_t* dist, float* ler, cudaStream_t stream);
@@ -47,7 +47,8 @@ extern int g_debug_ablate;
 namespace {
 
 // DLPack validation: CUDA device, expected dtype, expected rank, compact row-major.
-bool dl_ok(const DLTensor* t, const char* name, int code, int bits, int ndim, int device_id) {
+bool dl_ok(const DLTensor* t, const char* name, int code, int bits, int ndim, int device_id,
+           bool check_contiguous = true) {
   if (!t) {
     set_error("%s: NULL DLTensor", name);
     return false;
@@ -69,7 +70,7 @@ bool dl_ok(const DLTensor* t, const char* name, int code, int bits, int ndim, in
     set_error("%s: rank %d, expected %d", name, t->ndim, ndim);
     return false;
   }
-  if (t->strides) {
+  if (t->strides && check_contiguous) {
     int64_t expect = 1;
     for (int i = t->ndim - 1; i >= 0; i--) {
       if (t->shape[i] != 1 && t->strides[i] != expect) {
@@ -80,6 +81,27 @@ bool dl_ok(const DLTensor* t, const char* name, int code, int bits, int ndim, in
       expect *= t->shape[i];
     }
   }
+  return true;
+}
+
+// [T,B,C] float32 CUDA tensor whose innermost dimension is dense; frames and utterances may be strided
+// (e.g. the transposed view of a batch-major [B,T,C] tensor).  Returns the element strides.
+bool dl_logits_ok(const DLTensor* t, const char* name, int device_id, long long* st_t, long long* st_b) {
+  if (!dl_ok(t, name, 2, 32, 3, device_id, /*check_contiguous=*/false)) return false;
+  const int64_t B = t->shape[1], C = t->shape[2];
+  long long s0 = (long long)B * C, s1 = C, s2 = 1;
+  if (t->strides) {
+    s0 = t->strides[0];
+    s1 = t->strides[1];
+    s2 = t->strides[2];
+  }
+  if ((C != 1 && s2 != 1) || s0 < 0 || s1 < 0) {
+    set_error("%s: innermost stride must be 1 and outer strides non-negative (got %lld, %lld, %lld)", name, s0, s1,
+              s2);
+    return false;
+  }
+  *st_t = s0;
+  *st_b = s1;
   return true;
 }
 
@@ -102,7 +124,9 @@ using namespace nasr;
 struct nasr_host_ctx {
   int device;
   int max_T, max_B, max_C, max_L;
-  cudaStream_t stream;
+  cudaStream_t stream;             // compute
+  cudaStream_t s_in, s_out;        // H2D / D2H copies of the utterance blocks
+  cudaEvent_t ev_in[8], ev_done[8];
   // device
   float *d_logits, *d_grad, *d_loss, *d_grad_loss, *d_nsl, *d_ler;
   int32_t *d_lab_vals, *d_lab_offs, *d_seq, *d_status, *d_hyp_len, *d_dist;
@@ -149,8 +173,18 @@ int nasr_ctc_loss_grad_f32(const float* logits, int T, int B, int C, const int32
                            const int32_t* label_offsets, int max_label_len, const int32_t* seq_len,
                            int blank, float* loss, float* grad, const float* grad_loss,
                            int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
-  return ctc_loss_grad(logits, T, B, C, label_values, label_offsets, max_label_len, seq_len, blank,
-                       loss, grad, grad_loss, status, workspace, workspace_bytes,
+  return ctc_loss_grad(logits, T, B, C, (long long)B * C, C, label_values, label_offsets, max_label_len, seq_len,
+                       blank, loss, grad, grad_loss, status, workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int nasr_ctc_loss_grad_strided_f32(const float* logits, int T, int B, int C, long long stride_t,
+                                   long long stride_b, const int32_t* label_values,
+                                   const int32_t* label_offsets, int max_label_len, const int32_t* seq_len,
+                                   int blank, float* loss, float* grad, const float* grad_loss,
+                                   int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+  return ctc_loss_grad(logits, T, B, C, stride_t, stride_b, label_values, label_offsets, max_label_len, seq_len,
+                       blank, loss, grad, grad_loss, status, workspace, workspace_bytes,
                        static_cast<cudaStream_t>(stream));
 }
 
@@ -159,7 +193,8 @@ int nasr_ctc_loss_grad_dl(const DLTensor* logits, const DLTensor* label_values,
                           int blank, const DLTensor* loss, const DLTensor* grad,
                           const DLTensor* grad_loss, const DLTensor* status,
                           const DLTensor* workspace, void* stream) {
-  if (!dl_ok(logits, "logits", 2, 32, 3, -1)) return NASR_ERR_INVALID_ARGUMENT;
+  long long st_t = 0, st_b = 0;
+  if (!dl_logits_ok(logits, "logits", -1, &st_t, &st_b)) return NASR_ERR_INVALID_ARGUMENT;
   const int dev = logits->device.device_id;
   const int64_t T = logits->shape[0], B = logits->shape[1], C = logits->shape[2];
   NASR_CHECK_ARG(T < (1 << 30) && B < (1 << 30) && C < (1 << 30), "logits: dimension too large");
@@ -177,9 +212,12 @@ int nasr_ctc_loss_grad_dl(const DLTensor* logits, const DLTensor* label_values,
                  (long long)B);
   float* g = nullptr;
   if (grad) {
-    if (!dl_ok(grad, "grad", 2, 32, 3, dev)) return NASR_ERR_INVALID_ARGUMENT;
+    long long gt = 0, gb = 0;
+    if (!dl_logits_ok(grad, "grad", dev, &gt, &gb)) return NASR_ERR_INVALID_ARGUMENT;
     NASR_CHECK_ARG(grad->shape[0] == T && grad->shape[1] == B && grad->shape[2] == C,
                    "grad: shape differs from logits");
+    NASR_CHECK_ARG(gt == st_t && gb == st_b, "grad: strides differ from the logits' (%lld,%lld vs %lld,%lld)", gt,
+                   gb, st_t, st_b);
     g = dl_ptr<float>(grad);
   }
   const float* gl = nullptr;
@@ -188,7 +226,7 @@ int nasr_ctc_loss_grad_dl(const DLTensor* logits, const DLTensor* label_values,
     NASR_CHECK_ARG(grad_loss->shape[0] == B, "grad_loss: length must be B");
     gl = dl_ptr<const float>(grad_loss);
   }
-  return ctc_loss_grad(dl_ptr<const float>(logits), (int)T, (int)B, (int)C,
+  return ctc_loss_grad(dl_ptr<const float>(logits), (int)T, (int)B, (int)C, st_t, st_b,
                        dl_ptr<const int32_t>(label_values), dl_ptr<const int32_t>(label_offsets),
                        max_label_len, dl_ptr<const int32_t>(seq_len), blank, dl_ptr<float>(loss), g, gl,
                        dl_ptr<int32_t>(status), dl_ptr<void>(workspace), (size_t)dl_numel(workspace),
@@ -198,8 +236,16 @@ int nasr_ctc_loss_grad_dl(const DLTensor* logits, const DLTensor* label_values,
 int nasr_ctc_greedy_decode_i64(const float* logits, int T, int B, int C, const int32_t* seq_len,
                                int blank, int merge_repeated, int64_t* hyp, int32_t* hyp_len,
                                float* neg_sum_logits, void* stream) {
-  return greedy_decode(logits, T, B, C, seq_len, blank, merge_repeated, hyp, hyp_len, neg_sum_logits,
-                       static_cast<cudaStream_t>(stream));
+  return greedy_decode(logits, T, B, C, (long long)B * C, C, seq_len, blank, merge_repeated, hyp, hyp_len,
+                       neg_sum_logits, static_cast<cudaStream_t>(stream));
+}
+
+int nasr_ctc_greedy_decode_strided_i64(const float* logits, int T, int B, int C, long long stride_t,
+                                       long long stride_b, const int32_t* seq_len, int blank,
+                                       int merge_repeated, int64_t* hyp, int32_t* hyp_len,
+                                       float* neg_sum_logits, void* stream) {
+  return greedy_decode(logits, T, B, C, stride_t, stride_b, seq_len, blank, merge_repeated, hyp, hyp_len,
+                       neg_sum_logits, static_cast<cudaStream_t>(stream));
 }
 
 int nasr_hyp_to_sparse_i64(const int64_t* hyp, int hyp_stride, const int32_t* hyp_offsets, int B,
@@ -258,6 +304,14 @@ void nasr_host_ctx_destroy(nasr_host_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->s_in) cudaStreamSynchronize(c->s_in);
+  if (c->s_out) cudaStreamSynchronize(c->s_out);
+  for (int i = 0; i < 8; i++) {
+    if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+    if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+  }
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
   cudaFree(c->d_logits); cudaFree(c->d_grad); cudaFree(c->d_loss); cudaFree(c->d_grad_loss);
   cudaFree(c->d_nsl); cudaFree(c->d_ler); cudaFree(c->d_lab_vals); cudaFree(c->d_lab_offs);
   cudaFree(c->d_seq); cudaFree(c->d_status); cudaFree(c->d_hyp_len); cudaFree(c->d_dist);
@@ -295,6 +349,12 @@ int nasr_host_ctx_create(int device, int max_T, int max_B, int max_C, int max_la
     }                                                                                   \
   } while (0)
   NASR_CTX_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  NASR_CTX_TRY(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+  NASR_CTX_TRY(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 8; i++) {
+    NASR_CTX_TRY(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+    NASR_CTX_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+  }
   NASR_CTX_TRY(cudaMalloc(&c->d_logits, sizeof(float) * nlog));
   NASR_CTX_TRY(cudaMalloc(&c->d_grad, sizeof(float) * nlog));
   NASR_CTX_TRY(cudaMalloc(&c->d_loss, sizeof(float) * max_B));
@@ -354,26 +414,49 @@ int nasr_host_ctc_step(nasr_host_ctx* c, const float* logits, int T, int B, int 
   memcpy(c->h_small + o_offs, label_offsets, sizeof(int32_t) * (B + 1));
   memcpy(c->h_small + o_seq, seq_len, sizeof(int32_t) * B);
   if (grad_loss) memcpy(c->h_small + o_gl, grad_loss, sizeof(float) * B);
-  NASR_CUDA(cudaMemcpyAsync(c->d_logits, c->h_logits, sizeof(float) * nlog, cudaMemcpyHostToDevice, s));
-  if (N) NASR_CUDA(cudaMemcpyAsync(c->d_lab_vals, c->h_small + o_vals, sizeof(int32_t) * N, cudaMemcpyHostToDevice, s));
-  NASR_CUDA(cudaMemcpyAsync(c->d_lab_offs, c->h_small + o_offs, sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, s));
-  NASR_CUDA(cudaMemcpyAsync(c->d_seq, c->h_small + o_seq, sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
-  if (grad_loss) NASR_CUDA(cudaMemcpyAsync(c->d_grad_loss, c->h_small + o_gl, sizeof(float) * B, cudaMemcpyHostToDevice, s));
-  int rc = ctc_loss_grad(c->d_logits, T, B, C, c->d_lab_vals, c->d_lab_offs, Lmax, c->d_seq, blank,
-                         c->d_loss, grad ? c->d_grad : nullptr, grad_loss ? c->d_grad_loss : nullptr,
-                         c->d_status, c->d_ws, c->ws_bytes, s);
-  if (rc != NASR_OK) return rc;
+  // Small inputs first, then the batch in blocks of utterances: the H2D copy of block k+1, the kernels of
+  // block k and the D2H copy of block k-1 run concurrently (PCIe is full duplex; logits and grad are the two
+  // 4*T*B*C-byte transfers that dominate this call).  A block is a [T, Bk, C] column slab of the [T, B, C]
+  // tensors: a pitched copy on the bus, a strided launch on the device.  (Alternating the blocks' kernels
+  // between two compute streams was measured and gave nothing.)
+  cudaStream_t sin = c->s_in, sout = c->s_out;
+  if (N) NASR_CUDA(cudaMemcpyAsync(c->d_lab_vals, c->h_small + o_vals, sizeof(int32_t) * N, cudaMemcpyHostToDevice, sin));
+  NASR_CUDA(cudaMemcpyAsync(c->d_lab_offs, c->h_small + o_offs, sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, sin));
+  NASR_CUDA(cudaMemcpyAsync(c->d_seq, c->h_small + o_seq, sizeof(int32_t) * B, cudaMemcpyHostToDevice, sin));
+  if (grad_loss) NASR_CUDA(cudaMemcpyAsync(c->d_grad_loss, c->h_small + o_gl, sizeof(float) * B, cudaMemcpyHostToDevice, sin));
   const bool want_decode = hyp || hyp_len || neg_sum_logits || dist || ler;
-  if (want_decode) {
-    rc = greedy_decode(c->d_logits, T, B, C, c->d_seq, blank, 1, c->d_hyp, c->d_hyp_len, c->d_nsl, s);
+  const int nblk = (nlog * sizeof(float) >= ((size_t)8 << 20) && B >= 8) ? 4 : 1;
+  const size_t pitch = sizeof(float) * (size_t)B * C;
+  for (int k = 0; k < nblk; k++) {
+    const int b0 = (int)((long long)B * k / nblk), b1 = (int)((long long)B * (k + 1) / nblk);
+    const int Bk = b1 - b0;
+    if (Bk == 0) continue;
+    const size_t off = (size_t)b0 * C;
+    NASR_CUDA(cudaMemcpy2DAsync(c->d_logits + off, pitch, c->h_logits + off, pitch, sizeof(float) * (size_t)Bk * C,
+                                (size_t)T, cudaMemcpyHostToDevice, sin));
+    NASR_CUDA(cudaEventRecord(c->ev_in[k], sin));
+    NASR_CUDA(cudaStreamWaitEvent(s, c->ev_in[k], 0));
+    int rc = ctc_loss_grad(c->d_logits + off, T, Bk, C, (long long)B * C, C, c->d_lab_vals, c->d_lab_offs + b0, Lmax,
+                           c->d_seq + b0, blank, c->d_loss + b0, grad ? c->d_grad + off : nullptr,
+                           grad_loss ? c->d_grad_loss + b0 : nullptr, c->d_status + b0, c->d_ws, c->ws_bytes, s);
     if (rc != NASR_OK) return rc;
-    if (dist || ler) {
-      rc = edit_distance_dense(c->d_hyp, T, c->d_hyp_len, c->d_lab_vals, c->d_lab_offs, Lmax, B, 1,
-                               c->d_dist, c->d_ler, s);
+    if (want_decode) {
+      rc = greedy_decode(c->d_logits + off, T, Bk, C, (long long)B * C, C, c->d_seq + b0, blank, 1,
+                         c->d_hyp + (size_t)b0 * T, c->d_hyp_len + b0, c->d_nsl + b0, s);
       if (rc != NASR_OK) return rc;
+      if (dist || ler) {
+        rc = edit_distance_dense(c->d_hyp + (size_t)b0 * T, T, c->d_hyp_len + b0, c->d_lab_vals, c->d_lab_offs + b0,
+                                 Lmax, Bk, 1, c->d_dist + b0, c->d_ler + b0, s);
+        if (rc != NASR_OK) return rc;
+      }
     }
+    NASR_CUDA(cudaEventRecord(c->ev_done[k], s));
+    NASR_CUDA(cudaStreamWaitEvent(sout, c->ev_done[k], 0));
+    if (grad)
+      NASR_CUDA(cudaMemcpy2DAsync(c->h_grad + off, pitch, c->d_grad + off, pitch, sizeof(float) * (size_t)Bk * C,
+                                  (size_t)T, cudaMemcpyDeviceToHost, sout));
   }
-  if (grad) NASR_CUDA(cudaMemcpyAsync(c->h_grad, c->d_grad, sizeof(float) * nlog, cudaMemcpyDeviceToHost, s));
+  s = sout;  // everything below is ordered after the last block's kernels
   NASR_CUDA(cudaMemcpyAsync(c->h_small + o_loss, c->d_loss, sizeof(float) * B, cudaMemcpyDeviceToHost, s));
   NASR_CUDA(cudaMemcpyAsync(c->h_small + o_status, c->d_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, s));
   if (want_decode) {

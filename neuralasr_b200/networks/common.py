@@ -67,10 +67,17 @@ def _check_logits(logits):
     if logits.dtype != torch.float32 or logits.dim() != 3:
         raise ValueError("logits must be float32 [T, B, C] (time-major), got %s %s"
                          % (logits.dtype, tuple(logits.shape)))
-    if not logits.is_contiguous():
-        raise ValueError("logits must be contiguous [T, B, C]; transpose the model output with "
-                         ".contiguous() (the reference transposes too: bilstm_ctc_net.py:48)")
+    if logits.shape[2] > 1 and logits.stride(2) != 1:
+        raise ValueError("logits: the class axis must be dense (stride 1); frames and utterances may be "
+                         "strided, e.g. model_output_btc.transpose(0, 1) needs no .contiguous()")
     return logits
+
+
+def batch_major(logits_btc):
+    """View a batch-major ``[B, T, C]`` model output as the ``[T, B, C]`` the helpers take — no copy: the
+    kernels read and write through the strides, so the transpose every reference model tail does before
+    ``create_loss`` (``bilstm_ctc_net.py:48``, ``lstm_ctc_net.py:43``, ``wavenet.py:171``) disappears."""
+    return logits_btc.transpose(0, 1)
 
 
 def _seq_len_tensor(seq_len, device, B):
@@ -161,9 +168,10 @@ def ctc_loss_and_grad(logits, labels, seq_len, grad_loss=None, want_grad=True, o
     status = torch.empty(B, dtype=torch.int32, device=dev)
     grad = None
     if want_grad:
-        grad = out_grad if out_grad is not None else torch.empty_like(logits)
-        if grad.shape != logits.shape or grad.dtype != torch.float32 or not grad.is_contiguous():
-            raise ValueError("out_grad must be a contiguous float32 tensor shaped like logits")
+        grad = out_grad if out_grad is not None else torch.empty_strided(logits.shape, logits.stride(),
+                                                                         dtype=torch.float32, device=dev)
+        if grad.shape != logits.shape or grad.dtype != torch.float32 or grad.stride() != logits.stride():
+            raise ValueError("out_grad must be a float32 tensor with the shape and strides of logits")
     gl = None
     if grad_loss is not None:
         gl = grad_loss.to(device=dev, dtype=torch.float32).contiguous()
@@ -191,10 +199,10 @@ def ctc_loss_and_grad(logits, labels, seq_len, grad_loss=None, want_grad=True, o
             for cap in keep:   # we never took ownership: run the producer's deleter ourselves
                 _release_capsule(cap)
         else:
-            rc = lib.nasr_ctc_loss_grad_f32(_ptr(logits), T, B, C, _ptr(lab.values), _ptr(lab.offsets),
-                                            lab.max_len, _ptr(sl), blank, _ptr(loss_b), _ptr(grad),
-                                            _ptr(gl), _ptr(status), _ptr(ws), ws.numel(),
-                                            _stream_ptr(dev))
+            rc = lib.nasr_ctc_loss_grad_strided_f32(_ptr(logits), T, B, C, logits.stride(0), logits.stride(1),
+                                                    _ptr(lab.values), _ptr(lab.offsets), lab.max_len, _ptr(sl),
+                                                    blank, _ptr(loss_b), _ptr(grad), _ptr(gl), _ptr(status),
+                                                    _ptr(ws), ws.numel(), _stream_ptr(dev))
     _lib.check(rc, "nasr_ctc_loss_grad")
     return loss_b, grad, status
 
@@ -323,9 +331,10 @@ def decoding(logits, seq_len, merge_repeated=True, blank=None):
     hyp_len = torch.empty(B, dtype=torch.int32, device=dev)
     nsl = torch.empty((B, 1), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.nasr_ctc_greedy_decode_i64(_ptr(logits), T, B, C, _ptr(sl), blank,
-                                                  int(bool(merge_repeated)), _ptr(hyp), _ptr(hyp_len),
-                                                  _ptr(nsl), _stream_ptr(dev)), "nasr_ctc_greedy_decode")
+        _lib.check(lib.nasr_ctc_greedy_decode_strided_i64(_ptr(logits), T, B, C, logits.stride(0),
+                                                          logits.stride(1), _ptr(sl), blank,
+                                                          int(bool(merge_repeated)), _ptr(hyp), _ptr(hyp_len),
+                                                          _ptr(nsl), _stream_ptr(dev)), "nasr_ctc_greedy_decode")
     return DecodedSparse(hyp, hyp_len), nsl
 
 

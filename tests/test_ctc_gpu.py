@@ -338,3 +338,48 @@ def test_edit_distance_paths_match_oracle(common):
     d, ler = edit_distance(_sparse_from_rows(hyp_rows, np.int64), _sparse_from_rows(truth_rows, np.int32))
     want = [o.levenshtein(h, t) for t, h in cases]
     assert d.cpu().numpy().tolist() == want
+
+
+def test_batch_major_logits_without_transpose(common):
+    """A [B,T,C] model output goes in as a strided [T,B,C] view (plain and DLPack entries): same loss, the
+    gradient comes back in the batch-major layout, decode agrees."""
+    g = make_batch(17, T=150, B=6, C=38, Lmax=30, mode="ragged")
+    want_loss, want_grad, _ = c_oracle.ctc_loss_grad(g["logits"], g["label_values"], g["label_offsets"],
+                                                     g["seq_len"], precision="f64")
+    x_btc = torch.from_numpy(np.ascontiguousarray(g["logits"].transpose(1, 0, 2))).cuda()     # [B,T,C]
+    view = common.batch_major(x_btc)
+    assert not view.is_contiguous()
+    for use_dlpack in (False, True):
+        loss, grad, status = common.ctc_loss_and_grad(view, _triple(g), g["seq_len"], use_dlpack=use_dlpack)
+        assert grad.stride() == view.stride()
+        np.testing.assert_allclose(loss.cpu().numpy(), want_loss, rtol=LOSS_RTOL, atol=1e-5)
+        assert np.abs(grad.cpu().numpy() - want_grad).max() <= GRAD_ATOL
+        assert np.abs(grad.transpose(0, 1).contiguous().cpu().numpy() - want_grad.transpose(1, 0, 2)).max() <= GRAD_ATOL
+    xr = x_btc.clone().requires_grad_(True)
+    common.loss(common.batch_major(xr), _triple(g), g["seq_len"]).backward()
+    assert np.abs(xr.grad.cpu().numpy() - want_grad.transpose(1, 0, 2) / 6).max() <= GRAD_ATOL
+    dec, _ = common.decoding(view, g["seq_len"])
+    hv, _, _ = c_oracle.greedy_decode(g["logits"], g["seq_len"])
+    assert np.array_equal(dec.values.cpu().numpy(), hv)
+
+
+def test_host_context_blocks_match_single_launch(common):
+    """The HOST-buffer call splits a large batch into four utterance blocks (pitched copies, strided launches):
+    results must equal the device path bit for bit."""
+    from neuralasr_b200 import host
+    g = make_batch(78, T=700, B=26, C=38, Lmax=60, mode="ragged")     # 2.8 MB... below the split threshold
+    g2 = make_batch(79, T=900, B=70, C=38, Lmax=80, mode="ragged")    # 9.6 MB: split into 4 blocks of 17/18
+    for gg in (g, g2):
+        T, B, C = gg["logits"].shape
+        ctx = host.HostContext(0, T, B, C, 80)
+        out = ctx.step(gg["logits"], gg["label_values"], gg["label_offsets"], gg["seq_len"], want_hyp=True)
+        loss, grad, status = _run_loss(common, gg)
+        assert np.array_equal(out["loss"], loss) and np.array_equal(out["grad"], grad)
+        assert np.array_equal(out["status"], status)
+        hv, ho, _ = c_oracle.greedy_decode(gg["logits"], gg["seq_len"])
+        want_d, want_ler = c_oracle.edit_distance(hv, ho, gg["label_values"], gg["label_offsets"])
+        assert np.array_equal(out["hyp_len"], np.diff(ho)) and np.array_equal(out["dist"], want_d)
+        assert np.array_equal(out["ler"], want_ler)
+        for b in range(B):
+            assert np.array_equal(out["hyp"][b, : out["hyp_len"][b]], hv[ho[b]:ho[b + 1]])
+        ctx.close()
