@@ -383,3 +383,42 @@ def test_host_context_blocks_match_single_launch(common):
         for b in range(B):
             assert np.array_equal(out["hyp"][b, : out["hyp_len"][b]], hv[ho[b]:ho[b + 1]])
         ctx.close()
+
+
+def test_step_functions_follow_the_reference_conventions(common):
+    """train / validate / evaluate / decode (tfnetwork.py:166-190) on logits, dense padded labels in."""
+    from neuralasr_b200.steps import CtcHead, dense_to_sparse
+    g = make_batch(55, T=120, B=5, C=20, Lmax=12, mode="ragged", empty_row=False)
+    lens = np.diff(g["label_offsets"])
+    dense = np.zeros((5, lens.max()), np.int32)
+    for b, lab in enumerate(g["labels_dense"]):
+        dense[b, : len(lab)] = lab
+    want_loss, want_grad, _ = c_oracle.ctc_loss_grad(g["logits"], g["label_values"], g["label_offsets"],
+                                                     g["seq_len"], precision="f64")
+    hv, ho, _ = c_oracle.greedy_decode(g["logits"], g["seq_len"])
+    _, want_ler = c_oracle.edit_distance(hv, ho, g["label_values"], g["label_offsets"])
+    head = CtcHead()
+    x = torch.from_numpy(g["logits"]).cuda().requires_grad_(True)
+    loss_val, ler_val = head.train(x, dense, g["seq_len"], lens)
+    assert abs(loss_val - want_loss.mean()) <= LOSS_RTOL * want_loss.mean()
+    assert abs(ler_val - want_ler.astype(np.float64).mean()) < 1e-6
+    assert np.abs(x.grad.cpu().numpy() - want_grad / 5).max() <= GRAD_ATOL and head.global_step == 1
+    v = head.validate(x.detach(), dense, g["seq_len"], lens)
+    assert isinstance(v, list) and abs(v[0] - loss_val) < 1e-6 and abs(v[1] - ler_val) < 1e-7
+    values, l2, e2 = head.evaluate(x.detach(), dense, g["seq_len"], lens)
+    assert np.array_equal(values, hv) and values.dtype == np.int64
+    assert np.array_equal(head.decode(x.detach(), g["seq_len"]), hv)
+    # batch-major head: same numbers from a [B,T,C] tensor
+    bm = CtcHead(time_major=False)
+    xb = torch.from_numpy(np.ascontiguousarray(g["logits"].transpose(1, 0, 2))).cuda()
+    assert np.array_equal(bm.decode(xb, g["seq_len"]), hv)
+    assert abs(bm.validate(xb, dense, g["seq_len"], lens)[0] - loss_val) < 1e-5
+    # LAS-style metric caller: dense predictions and dense labels through dense_to_sparse (las.py:116-117)
+    pred = np.zeros((5, 40), np.int64)
+    for b in range(5):
+        h = hv[ho[b]:ho[b + 1]][:40] + 1            # shift ids by one so that 0 can be the eos filler
+        pred[b, : len(h)] = h
+    lab1 = np.where(np.arange(dense.shape[1])[None, :] < lens[:, None], dense + 1, 0)
+    m = common.label_error_rate(dense_to_sparse(pred), dense_to_sparse(lab1))
+    want = [o.levenshtein((hv[ho[b]:ho[b + 1]][:40]).tolist(), g["labels_dense"][b].tolist()) for b in range(5)]
+    assert m.distances.cpu().numpy().tolist() == want

@@ -96,3 +96,31 @@ def test_no_cpu_fallback():
         common.decoding(x, [4, 4])
     src = open(os.path.join(ROOT, "neuralasr_b200", "networks", "common.py")).read()
     assert "oracle" not in src
+
+
+def test_symbols_table_and_convert_to_str(tmp_path):
+    from neuralasr_b200.symbols import Symbols
+    s = Symbols(label_context=0)
+    s.insert_padding()                              # preprocess_mfcc.py:81: padding first ...
+    for ch in "abc_":
+        s.insert_sym(ch)
+    s.insert_blank()                                # ... blank last (preprocess_mfcc.py:92)
+    assert s.get_padding_id() == 0 and s.get_blank_id() == s.num_classes - 1 == 5
+    assert s.insert_sym("b") == 2                   # idempotent
+    assert s.convert_to_str([1, 2, 4, 3, 5, 1]) == "ab ca"
+    path = str(tmp_path / "symbols.txt")
+    s.write(path)
+    r = Symbols(0, path)
+    assert r.sym_to_id == s.sym_to_id and r.counter == s.counter and r.get_sym(4) == "_"
+    # label context 1: symbols are trigrams, the middle character is the label (preprocess_mfcc.py:18-29)
+    t = Symbols(label_context=1)
+    ids = [t.insert_sym(x) for x in ("^he", "hel", "el_", "l_o")]
+    assert t.convert_to_str(ids) == "hel "
+
+
+def test_dense_to_sparse_drops_eos():
+    pytest.importorskip("torch")
+    from neuralasr_b200.steps import dense_to_sparse
+    idx, vals, shape = dense_to_sparse(np.array([[3, 0, 4], [0, 0, 0], [7, 8, 0]]))
+    assert idx.tolist() == [[0, 0], [0, 2], [2, 0], [2, 1]] and vals.tolist() == [3, 4, 7, 8]
+    assert shape.tolist() == [3, 3]
