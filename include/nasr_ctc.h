@@ -222,7 +222,8 @@ int nasr_debug_config(int path, int split_frames);
 
 /* Test/tuning hook: when device_buffer is non-NULL the throughput kernel writes, per utterance and warp,
  * int64[4] = {cycles of work before the meeting, cycles of work after it, total cycles, warp role} to
- * device_buffer[(b*8 + warp)*4 ...] (B*8*4 int64).  NULL switches it off (the default). */
+ * device_buffer[(b*16 + warp)*4 ...] (B*16*4 int64, then a per-iteration trace of the first four utterances:
+ * 4*200*8*2 int64).  NULL switches it off (the default). */
 int nasr_debug_profile(void* device_buffer);
 
 #ifdef __cplusplus

@@ -40,6 +40,7 @@ namespace fast {
 constexpr int KC = 8;            // frames per chunk (= rescale and checkpoint interval)
 constexpr int IFIRST = -5;       // first iteration: the producers' copies run five iterations ahead of the recursion
 constexpr int NTHREADS = 256;    // 8 warps
+constexpr int NTHREADS_WIDE = 448;  // wide-vocabulary variant: 2 recursion + 2 recompute + 2 gradient + 8 producer warps
 constexpr int GCAP = 200;        // a lane with mass sits at most this far below the nearest lane with mass beneath it
 constexpr int GROWTH = 550;      // bits a lane maximum may grow inside one chunk (GCAP of inflow + 350 of emissions)
 // Certificate: a value flushed in a lane of exponent Ea is < 2^(Ea-1022); its partner in the other direction is
@@ -68,11 +69,11 @@ struct Params {
   int num_sms;
   int split;           // debug: frames of the forward half (multiple of KC), 0 = automatic
   int ablate;          // debug: bit0 gradient warps idle, bit1 producers idle in phase 2, bit2 recompute warps idle, bit3 no posterior store
-  long long* prof;     // debug: [B][8 warps][4] cycles of work in phase 1 / phase 2, total, role (or NULL)
+  long long* prof;     // debug: [B][16 warps][4] cycles of work in phase 1 / phase 2, total, role (or NULL)
 };
 
 struct Smem {
-  size_t rows, raw, obuf, gbuf, oexp, meet_nb, meet_pre, meet_e, lab, pos, cls_off, psum, scal, total;
+  size_t rows, raw, rowbuf, stage, dtab, obuf, gbuf, oexp, meet_nb, meet_pre, meet_e, lab, pos, cls_off, psum, scal, total;
   int gstride;  // floats per posterior row: NL*32 cells + one zero cell (+ padding)
 };
 
@@ -88,14 +89,23 @@ __host__ __device__ constexpr size_t al16(size_t x) { return (x + 15) & ~(size_t
 __host__ __device__ constexpr int row_bytes(int cmax) { return (int)al16((size_t)(2 * cmax + 1) * 4); }
 __host__ __device__ constexpr int row_yoff(int cmax) { return (cmax + 1) * 4; }
 
-__host__ __device__ inline Smem smem_layout(int NL, int cmax) {
+// wideC > 0 selects the wide-vocabulary layout (C > 64): a row record is then uint32 R_hi[NL*32] in the SLOT
+// order of the side it belongs to (the producer gathers the emissions of the transcript's classes, so the
+// record does not grow with C), there is no raw-logits ring, every producer warp owns one row of C floats
+// (rowbuf), and the gradient warps get a table of the distinct classes of the transcript (dtab).
+constexpr int kWideProducers = 8;
+__host__ __device__ inline Smem smem_layout(int NL, int cmax, int wideC = 0) {
   Smem s;
-  const int rowbytes = row_bytes(cmax);
-  s.gstride = NL * 32 + 4;
   const int Lcap = NL * 32;
+  const int rowbytes = wideC ? NL * 32 * 4 : row_bytes(cmax);
+  if (wideC) cmax = wideC;
+  s.gstride = NL * 32 + 4;
   size_t o = 0;
   s.rows = o;      o = al16(o + (size_t)2 * 4 * KC * rowbytes);              // [side][4 slots][KC] records
-  s.raw = o;       o = al16(o + (size_t)2 * 4 * KC * cmax * 4);              // [side][4 slots][KC][cmax] raw logits
+  s.raw = o;       o = al16(o + (wideC ? 0 : (size_t)2 * 4 * KC * cmax * 4)); // [side][4 slots][KC][cmax] raw logits
+  s.rowbuf = o;    o = al16(o + (wideC ? (size_t)kWideProducers * wideC * 4 : 0));
+  s.stage = o;     o = al16(o + (wideC ? (size_t)kWideProducers * 2 * wideC * 4 : 0));  // raw rows in flight
+  s.dtab = o;      o = al16(o + (wideC ? (size_t)3 * Lcap * 4 : 0));
   s.obuf = o;      o = al16(o + (size_t)2 * 2 * KC * NL * 32 * 4);           // [side][2][KC][NL][32] high words
   s.gbuf = o;      o = al16(o + (size_t)2 * 2 * KC * s.gstride * 4);         // [side][2][KC][gstride] posteriors
   s.oexp = o;      o = al16(o + (size_t)2 * 2 * 32 * 4);
@@ -173,8 +183,10 @@ struct Dir {
 };
 
 // Slot tables and the virtual row before the first frame, for direction d (0 forward, 1 mirrored).
+// wide: 0 = narrow records indexed by class; 1 = slot-ordered records read in this direction's own order
+// (recursion warps); 2 = slot-ordered records of the OTHER side, read mirrored (recompute warps).
 template <int NL>
-__device__ __forceinline__ void dir_setup(Dir<NL>& s, int d, int lane, const int* lab, int L, int CZ) {
+__device__ __forceinline__ void dir_setup(Dir<NL>& s, int d, int lane, const int* lab, int L, int CZ, int wide = 0) {
   const int N = NL * 32;
   const int pad = N - L - 1;
 #pragma unroll
@@ -196,6 +208,8 @@ __device__ __forceinline__ void dir_setup(Dir<NL>& s, int d, int lane, const int
       }
     }
     s.coloff[k] = (uint32_t)col * 4u;
+    if (wide == 1) s.coloff[k] = (uint32_t)(k * 32 + lane) * 4u;
+    if (wide == 2) s.coloff[k] = (uint32_t)((NL - 1 - k) * 32 + 31 - lane) * 4u;
     s.skip[k] = skip ? 1.0 : 0.0;
     s.Ab[k] = (i == (d == 0 ? 1 : pad)) ? 1.0 : 0.0;
     s.Al[k] = 0.0;
@@ -395,6 +409,94 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ---- wide-vocabulary producer (64 < C <= 1024, C % 4 == 0): one warp per row, the row in registers -------
+// lane l holds classes 4l + 128i + {0,1,2,3}, i = 0..7 (eight 16-byte loads, coalesced)
+struct WideRow {
+  float4 v[8];
+};
+
+// global -> this warp's staging row, asynchronously (16-byte LDGSTS; the row is consumed an iteration later)
+__device__ __forceinline__ void wide_issue(float* stage, const float* xrow, int C, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int c = 4 * lane + 128 * i;
+    if (c < C)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(stage + c)),
+                   "l"(xrow + c)
+                   : "memory");
+  }
+}
+__device__ __forceinline__ void wide_fetch(WideRow& r, const float* stage, int C, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int c = 4 * lane + 128 * i;
+    r.v[i] = c < C ? *reinterpret_cast<const float4*>(stage + c)
+                   : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  }
+}
+
+// One row: softmax pieces, the slot-ordered record of ratio emissions (high words) for the recursion, and --
+// in phase 2 -- the provisional gradient row grad_loss * softmax, from which the gradient warps later subtract
+// the occupancies of the transcript's classes.  pcls[k] = class of slot (lane, k) of this side, -1 if dead.
+// Returns log y_blank (all lanes).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int NL>
+__device__ __forceinline__ float wide_row(const WideRow& r, float* rowbuf, uint32_t* rec, const int (&pcls)[NL],
+                                          float* grow, float gs, int C, int blank, int lane, int& alarm) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 8; i++) m = fmaxf(m, fmaxf(fmaxf(r.v[i].x, r.v[i].y), fmaxf(r.v[i].z, r.v[i].w)));
+  m = warp_max(m);
+  const float ml2 = m * 1.4426950408889634f;
+  float ssum = 0.f;
+  // e^(x - m) straight into the warp's row buffer (kept out of registers: two rows of logits are in flight)
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    float4 n;
+    n.x = ex2_approx(fmaf(r.v[i].x, 1.4426950408889634f, -ml2));
+    n.y = ex2_approx(fmaf(r.v[i].y, 1.4426950408889634f, -ml2));
+    n.z = ex2_approx(fmaf(r.v[i].z, 1.4426950408889634f, -ml2));
+    n.w = ex2_approx(fmaf(r.v[i].w, 1.4426950408889634f, -ml2));
+    ssum += (n.x + n.y) + (n.z + n.w);
+    const int c = 4 * lane + 128 * i;
+    if (c < C) *reinterpret_cast<float4*>(rowbuf + c) = n;
+  }
+  ssum = warp_sum(ssum);
+  __syncwarp();
+  const float nbl = rowbuf[blank];
+  const float inv_nb = __fdividef(1.0f, nbl);
+  bool bad = !(nbl >= 1.0e-38f && ssum <= 3.0e38f);
+#pragma unroll
+  for (int k = 0; k < NL; k++) {
+    uint32_t w = 0u;
+    if (pcls[k] >= 0) {
+      const float rr = rowbuf[pcls[k]] * inv_nb;
+      bad |= !(rr >= 1.1754944e-38f && rr <= 1.0e38f);   // only the transcript's classes have to stay normal
+      w = ((__float_as_uint(rr) + 4u) >> 3) + (896u << 20);
+    }
+    rec[k * 32 + lane] = w;
+  }
+  if (bad) alarm |= AL_EMISSION;
+  if (grow) {
+    const float sc = gs * __fdividef(1.0f, ssum);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int c = 4 * lane + 128 * i;
+      if (c < C) {
+        const float4 n = *reinterpret_cast<const float4*>(rowbuf + c);
+        __stcg(reinterpret_cast<float4*>(grow + c), make_float4(n.x * sc, n.y * sc, n.z * sc, n.w * sc));
+      }
+    }
+  }
+  __syncwarp();
+  return __logf(nbl) - __logf(ssum);
+}
+
 template <int NL>
 __device__ __forceinline__ uint32_t* ckpt_ptr(const Params& p, int b, int d, int c) {
   return p.ckpt + (((size_t)b * 2 + d) * p.maxch + c) * (size_t)((2 * NL + 1) * 32);
@@ -414,15 +516,22 @@ __device__ __forceinline__ uint32_t gcell(int pos) {
 // four schedulers.
 __device__ int g_sm_arrivals[1024];
 
+// EPL = 0 instantiates the wide-vocabulary variant (64 < C <= 1024, C % 4 == 0): 14 warps, one CTA per SM.
 template <int NL, int EPL>
-__global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(const Params p) {
+__global__ void __launch_bounds__((EPL ? NTHREADS : NTHREADS_WIDE), ((EPL && NL <= 8) ? 2 : 1))
+ctc_fast_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  constexpr int CMAX = 8 * EPL;
-  constexpr int ROWB = row_bytes(CMAX);
+  constexpr bool WIDE = EPL == 0;
+  constexpr int NT = WIDE ? NTHREADS_WIDE : NTHREADS;
+  constexpr int CMAX = WIDE ? 1024 : 8 * EPL;
+  constexpr int ROWB = WIDE ? NL * 32 * 4 : row_bytes(CMAX);
   constexpr int YOFF = row_yoff(CMAX);
-  const Smem sl = smem_layout(NL, CMAX);
+  const Smem sl = smem_layout(NL, CMAX, WIDE ? p.C : 0);
   unsigned char* s_rows = smem + sl.rows;
   float* s_raw = reinterpret_cast<float*>(smem + sl.raw);
+  float* s_rowbuf = reinterpret_cast<float*>(smem + sl.rowbuf);
+  float* s_stage = reinterpret_cast<float*>(smem + sl.stage);
+  int* s_dtab = reinterpret_cast<int*>(smem + sl.dtab);
   uint32_t* s_obuf = reinterpret_cast<uint32_t*>(smem + sl.obuf);
   float* s_gbuf = reinterpret_cast<float*>(smem + sl.gbuf);
   int* s_oexp = reinterpret_cast<int*>(smem + sl.oexp);
@@ -451,16 +560,16 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
   const int L = p.lab_offs[b + 1] - l0;
 
   // ---- can this kernel take the utterance? everything unusual goes to the robust kernel -----------
-  int bad = (Tb < 2 * KC) | (Tb > T) | (L < 0) | (L > Lcap) | (C > CMAX);
+  int bad = (Tb < 2 * KC) | (Tb > T) | (L < 0) | (L > Lcap) | (C > CMAX) | (WIDE && (C & 3));
   if (tid < 16) {
     if (tid < 8) s_scal[tid] = 0;
     s_psum[tid] = 0.0;
   }
-  for (int c = tid; c < C + 2; c += NTHREADS) s_cls_off[c] = 0;
+  for (int c = tid; c < C + 2; c += NT) s_cls_off[c] = 0;
   __syncthreads();
   int rep = 0;
   if (!bad) {
-    for (int i = tid; i < L; i += NTHREADS) {
+    for (int i = tid; i < L; i += NT) {
       const int v = p.lab_vals[l0 + i];
       s_lab[i] = v;
       if (v < 0 || v >= C || v == blank) {
@@ -499,19 +608,33 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
   }
   __syncthreads();
   // s_cls_off[c] = number of labels with class < c
-  for (int j = tid; j < L; j += NTHREADS) {
+  for (int j = tid; j < L; j += NT) {
     const int v = s_lab[j];
     int r = 0;
     for (int i = 0; i < j; i++) r += (s_lab[i] == v);
     s_pos[j] = (uint16_t)(s_cls_off[v] + r);
   }
-  // raw rows: the columns past C stay -inf for the whole kernel; row records: the zero entry of dead slots
-  for (int i = tid; i < 2 * 4 * KC * CMAX; i += NTHREADS)
-    if (i % CMAX >= C) s_raw[i] = -INFINITY;
-  for (int i = tid; i < 2 * 4 * KC; i += NTHREADS)
-    *reinterpret_cast<uint32_t*>(s_rows + (size_t)i * rowbytes + CMAX * 4) = 0u;
+  if (!WIDE) {
+    // raw rows: the columns past C stay -inf for the whole kernel; row records: the zero entry of dead slots
+    for (int i = tid; i < 2 * 4 * KC * CMAX; i += NT)
+      if (i % CMAX >= C) s_raw[i] = -INFINITY;
+    for (int i = tid; i < 2 * 4 * KC; i += NT)
+      *reinterpret_cast<uint32_t*>(s_rows + (size_t)i * rowbytes + CMAX * 4) = 0u;
+  } else {
+    // distinct classes of the transcript, with the posterior-row cells that hold the inclusive prefix just
+    // before and at the end of each class: [0,Lcap) class, [Lcap,2Lcap) cell "lo", [2Lcap,3Lcap) cell "hi"
+    for (int c = tid; c < C; c += NT) {
+      const int lo = s_cls_off[c], hi = s_cls_off[c + 1];
+      if (hi > lo && c != blank) {
+        const int u = atomicAdd(&s_scal[6], 1);
+        s_dtab[u] = c;
+        s_dtab[(Lcap + 2) + u] = lo > 0 ? (int)gcell<NL>(lo - 1) : N;
+        s_dtab[2 * (Lcap + 2) + u] = (int)gcell<NL>(hi - 1);
+      }
+    }
+  }
   // the zero cell of every posterior row (prefix "before position 0")
-  for (int i = tid; i < 2 * 2 * KC; i += NTHREADS) {
+  for (int i = tid; i < 2 * 2 * KC; i += NT) {
     float* row = s_gbuf + (size_t)i * gstride;
     row[N] = 0.f;
   }
@@ -521,7 +644,7 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
   float* gbase = p.grad ? p.grad + (size_t)b * p.st_b : nullptr;
   if (gbase) {
     const size_t n = (size_t)(T - Tb) * C;
-    for (size_t i = tid; i < n; i += NTHREADS) {
+    for (size_t i = tid; i < n; i += NT) {
       const size_t t = Tb + i / C;
       gbase[t * rstride + (i % C)] = 0.f;
     }
@@ -550,15 +673,16 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
   asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
   if (tid == 0) s_scal[3] = atomicAdd(&g_sm_arrivals[smid & 1023], 1);
   __syncthreads();
-  const int perm = s_scal[3] & 1;
-  const int role = warp ^ (perm << 1);
+  const int perm = WIDE ? 0 : (s_scal[3] & 1);
+  // wide: warps 0-3 recursion / recompute, 4-5 gradient, 6-13 producers (side = parity)
+  const int role = WIDE ? (warp < 4 ? warp : (warp < 6 ? G_F + (warp & 1) : P_F + (warp & 1))) : (warp ^ (perm << 1));
   const int d = role & 1;  // direction / side this warp works for
   __syncthreads();
 
   Dir<NL> st;
   uint32_t gphys[NL];  // recursion warps: byte offset of slot k's posterior inside a posterior row
   if (role <= RC_B) {
-    dir_setup<NL>(st, d, lane, s_lab, L, CMAX);
+    dir_setup<NL>(st, d, lane, s_lab, L, CMAX, WIDE ? (role <= H_B ? 1 : 2) : 0);
     const int pad = N - L - 1;
 #pragma unroll
     for (int k = 0; k < NL; k++) {
@@ -590,6 +714,18 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
     }
     if (L > 0) pc_tot = gcell<NL>(L - 1) * 4u;
   }
+  // wide gradient warps: this lane's share of the distinct classes of the transcript (at most NL of them)
+  int wd_cls[NL], wd_lo[NL], wd_hi[NL];
+  if (WIDE && role >= G_F) {
+    const int U = s_scal[6];
+#pragma unroll
+    for (int i = 0; i < NL; i++) {
+      const int u = lane + 32 * i;
+      wd_cls[i] = u < U ? s_dtab[u] : -1;
+      wd_lo[i] = u < U ? s_dtab[N + u] : N;
+      wd_hi[i] = u < U ? s_dtab[2 * N + u] : N;
+    }
+  }
   int alarm = 0;
   bool scaled = false;     // recursion warps: state already divided by the mantissa of p
 
@@ -603,8 +739,8 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
     const long long pe = clock64();                        \
     const long long dt = pe - prof_a;                      \
     if (I < S.P1) prof_w1 += dt; else prof_w2 += dt;       \
-    if (b < 4 && lane == 0 && I - IFIRST < 200) {          \
-      long long* tr = p.prof + (size_t)p.B * 32 + (((size_t)b * 200 + (I - IFIRST)) * 8 + warp) * 2; \
+    if (b < 4 && lane == 0 && warp < 8 && I - IFIRST < 200) {  \
+      long long* tr = p.prof + (size_t)p.B * 64 + (((size_t)b * 200 + (I - IFIRST)) * 8 + warp) * 2; \
       tr[0] = prof_a - prof_t0;                            \
       tr[1] = pe - prof_t0;                                \
     }                                                      \
@@ -742,6 +878,78 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
       cta_sync();
     }
   } else if (role == P_F || role == P_B) {
+    if constexpr (WIDE) {
+      // ======================= producer warps, wide vocabulary =======================
+      // Warp j of a side converts rows j and j+4 of every chunk of that side, two iterations before the
+      // recursion needs it; the row that follows is requested while the current one is processed, and the
+      // rows of two chunks later are prefetched into L2.
+      const int pj = (warp - 6) >> 1;
+      float* rowbuf = s_rowbuf + (size_t)(warp - 6) * C;
+      int pcls[NL];
+      {
+        const int pad = N - L - 1;
+#pragma unroll
+        for (int k = 0; k < NL; k++) {
+          const int i = lane * NL + k;
+          if (d == 0) {
+            pcls[k] = (i >= 1 && i <= L) ? s_lab[i - 1] : -1;
+          } else {
+            const int m = i - pad;
+            pcls[k] = (m >= 0 && m < L) ? s_lab[L - 1 - m] : -1;
+          }
+        }
+      }
+      double lsum = 0.0;
+      float* stA = s_stage + (size_t)(warp - 6) * 2 * C;   // staging rows of this warp: row pj and row pj+4
+      float* stB = stA + C;
+      auto row_ptr = [&](const Chunk& ci, int f) {
+        const int ff = min(f, ci.len - 1);
+        const int t = d ? ci.base - ff : ci.base + ff;
+        return p.logits + (size_t)t * p.st_t + (size_t)b * p.st_b;
+      };
+      auto wanted = [&](const Chunk& ci) { return ci.phase != 0 && (ci.phase == 1 || want_grad); };
+      {
+        const Chunk c0 = chunk_at(S, d, IFIRST + 2);
+        if (wanted(c0)) {
+          wide_issue(stA, row_ptr(c0, pj), C, lane);
+          wide_issue(stB, row_ptr(c0, pj + 4), C, lane);
+        }
+        cp_async_commit();
+      }
+#pragma unroll 1
+      for (int I = IFIRST; I <= S.last; I++) {
+        NASR_PROF_BEGIN();
+        const Chunk ci = chunk_at(S, d, I + 2);
+        const Chunk cn = chunk_at(S, d, I + 3);
+        const bool on = wanted(ci), onn = wanted(cn);
+        uint32_t* recs = reinterpret_cast<uint32_t*>(s_rows + (size_t)(d * 4 + ((I + 2) & 3)) * KC * rowbytes);
+        cp_async_wait<0>();   // the rows of this iteration were requested one iteration ago
+        __syncwarp();
+        WideRow r;
+        if (on) wide_fetch(r, stA, C, lane);
+        __syncwarp();
+        if (onn) wide_issue(stA, row_ptr(cn, pj), C, lane);
+        if (on && pj < ci.len) {
+          const int t = d ? ci.base - pj : ci.base + pj;
+          float* grow = (ci.phase == 2) ? gbase + (size_t)t * rstride : nullptr;
+          const float ly = wide_row<NL>(r, rowbuf, recs + pj * N, pcls, grow, gs, C, blank, lane, alarm);
+          if (ci.phase == 1) lsum += (double)ly;
+        }
+        if (on) wide_fetch(r, stB, C, lane);
+        __syncwarp();
+        if (onn) wide_issue(stB, row_ptr(cn, pj + 4), C, lane);
+        cp_async_commit();
+        if (on && pj + 4 < ci.len) {
+          const int t = d ? ci.base - (pj + 4) : ci.base + (pj + 4);
+          float* grow = (ci.phase == 2) ? gbase + (size_t)t * rstride : nullptr;
+          const float ly = wide_row<NL>(r, rowbuf, recs + (pj + 4) * N, pcls, grow, gs, C, blank, lane, alarm);
+          if (ci.phase == 1) lsum += (double)ly;
+        }
+        if (lane == 0) s_psum[warp - 6] = lsum;
+        NASR_PROF_END();
+        cta_sync();
+      }
+    } else {
     // ======================= producer warps =======================
     // Raw logits rows travel global -> shared memory by cp.async, issued five iterations before the recursion
     // needs the chunk (an iteration is about as long as a DRAM round trip), and are turned into row records
@@ -786,13 +994,14 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
       NASR_PROF_END();
       cta_sync();
     }
+    }
   } else {
     double lsumg = 0.0;
     const int rl = lane >> 3;
 #pragma unroll 1
     for (int I = IFIRST; I <= S.last; I++) {
       NASR_PROF_BEGIN();
-      {  // phase 1: second half of the producer's job
+      if constexpr (!WIDE) {  // phase 1: second half of the producer's job
         const Chunk c2 = chunk_at(S, d, I + 2);
         if (c2.phase == 1) {
           unsigned char* rows = s_rows + (size_t)(d * 4 + ((I + 2) & 3)) * KC * rowbytes;
@@ -840,6 +1049,26 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
             for (int i = 0; i < NL; i++) G[(f0 + j) * gstride + i * 32 + lane] = v[j][i] + base[j];
           }
           __syncwarp();
+          if constexpr (WIDE) {
+            // the producers already wrote grad_loss * softmax for these frames; subtract the occupancy of
+            // every distinct class of the transcript (and of the blank) in place
+#pragma unroll
+            for (int j = 0; j < NF; j++) {
+              const int f = f0 + j;
+              if (f < ci.len) {
+                const int t = d ? ci.base - f : ci.base + f;
+                float* g = gbase + (size_t)t * rstride;
+                const float* Gr = G + (f0 + j) * gstride;
+                // one contribution per cell, so the order-free reduction in L2 is deterministic; red
+                // does not wait for a round trip the way a load-modify-store would
+#pragma unroll
+                for (int i = 0; i < NL; i++)
+                  if (wd_cls[i] >= 0) atomicAdd(g + wd_cls[i], -(gs * (Gr[wd_hi[i]] - Gr[wd_lo[i]])));
+                if (lane == 0) atomicAdd(g + blank, -(gs * (1.0f - Gr[pc_tot >> 2])));
+              }
+            }
+            continue;
+          }
           float o0[NF], o1[NF], tot[NF], y0[NF], y1[NF];
 #pragma unroll
           for (int j = 0; j < NF; j++) {
@@ -870,7 +1099,7 @@ __global__ void __launch_bounds__(NTHREADS, (NL <= 8 ? 2 : 1)) ctc_fast_kernel(c
 #undef NASR_PROF_BEGIN
 #undef NASR_PROF_END
   if (p.prof && lane == 0) {
-    long long* q = p.prof + ((size_t)b * 8 + warp) * 4;
+    long long* q = p.prof + ((size_t)b * 16 + warp) * 4;
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     q[0] = prof_w1; q[1] = prof_w2; q[2] = clock64() - prof_t0; q[3] = role | ((long long)smid << 8);
@@ -898,9 +1127,19 @@ int pick_nl(int Lmax) {
   return 0;
 }
 
+bool is_wide(int C) { return C > 64 && C <= 1024 && (C & 3) == 0; }
+
+// the wide-vocabulary variant is instantiated for these slot counts only (L <= 126, 158, 222)
+int pick_nl_wide(int Lmax) {
+  static const int kNL[] = {4, 5, 7};
+  for (int nl : kNL)
+    if (Lmax <= nl * 32 - 2) return nl;
+  return 0;
+}
+
 template <int NL, int EPL>
 int launch_fast(const fast::Params& p, cudaStream_t stream) {
-  const fast::Smem sl = fast::smem_layout(NL, 8 * EPL);
+  const fast::Smem sl = fast::smem_layout(NL, 8 * EPL, EPL ? 0 : p.C);
   static bool attr_set = false;
   if (!attr_set) {
     NASR_CUDA(cudaFuncSetAttribute(fast::ctc_fast_kernel<NL, EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -911,7 +1150,7 @@ int launch_fast(const fast::Params& p, cudaStream_t stream) {
     set_error("nasr_ctc: fast kernel shared memory %zu too large", sl.total);
     return NASR_ERR_UNSUPPORTED;
   }
-  fast::ctc_fast_kernel<NL, EPL><<<p.B, fast::NTHREADS, sl.total, stream>>>(p);
+  fast::ctc_fast_kernel<NL, EPL><<<p.B, EPL ? fast::NTHREADS : fast::NTHREADS_WIDE, sl.total, stream>>>(p);
   count_launch();
   NASR_CUDA(cudaGetLastError());
   return NASR_OK;
@@ -936,14 +1175,19 @@ static int max_chunks(int T) {
 }
 
 bool ctc_fast_supported(int T, int C, int Lmax) {
+  if (T < 2 * fast::KC) return false;
+  if (is_wide(C)) {
+    const int NL = pick_nl_wide(Lmax);
+    return NL != 0 && fast::smem_layout(NL, 0, C).total <= (size_t)kMaxSmem;
+  }
   const int NL = pick_nl(Lmax);
-  if (T < 2 * fast::KC || C > 64 || NL == 0) return false;
+  if (C > 64 || NL == 0) return false;
   return fast::smem_layout(NL, C <= 40 ? 40 : 64).total <= (size_t)kMaxSmem;
 }
 
 size_t ctc_fast_workspace_bytes(int T, int B, int C, int Lmax) {
   if (!ctc_fast_supported(T, C, Lmax)) return 0;
-  const int NL = pick_nl(Lmax);
+  const int NL = is_wide(C) ? pick_nl_wide(Lmax) : pick_nl(Lmax);
   return (size_t)B * 2 * max_chunks(T) * (2 * NL + 1) * 32 * sizeof(uint32_t);
 }
 
@@ -969,6 +1213,13 @@ int ctc_fast_launch(const float* logits, int T, int B, int C, long long st_t, lo
     NASR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   p.num_sms = num_sms;
+  if (is_wide(C)) {
+    switch (pick_nl_wide(Lmax)) {
+      case 4: return launch_fast<4, 0>(p, stream);
+      case 5: return launch_fast<5, 0>(p, stream);
+      case 7: return launch_fast<7, 0>(p, stream);
+    }
+  }
   switch (pick_nl(Lmax)) {
     case 2: return launch_fast_c<2>(p, stream);
     case 4: return launch_fast_c<4>(p, stream);

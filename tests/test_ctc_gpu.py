@@ -242,6 +242,9 @@ def _flags(common, B):
     dict(T=100, B=5, C=64, Lmax=20, mode="ragged"),                   # widest vocabulary the fast kernel takes
     dict(T=40, B=3, C=5, Lmax=6, mode="ragged"),
     dict(T=3000, B=2, C=38, Lmax=600, mode="full", empty_row=False),  # BASELINE cfg4: 20 slots per lane
+    dict(T=200, B=6, C=1024, Lmax=40, mode="ragged"),                 # wide-vocabulary variant (BASELINE cfg5 classes)
+    dict(T=400, B=4, C=132, Lmax=150, mode="ragged"),                 # wide variant, C not a multiple of 128
+    dict(T=300, B=3, C=512, Lmax=200, mode="full", empty_row=False),
 ])
 def test_each_kernel_alone_matches_oracle(common, debug_paths, kw):
     g = make_batch(4242, **kw)

@@ -79,15 +79,20 @@ if which in ("all", "time"):
         print("cfg3 path %d: %.3f ms per step  -> %.2f%% of HBM peak (116.7 MB / 6543 GB/s = 17.8 us)" % (path, ms, 100 * 0.01784 / ms))
     common.debug_config(0, 0)
     run("cfg3", 2, 0, T=1000, B=256, C=38, Lmax=200, mode="full", Lmin=100, empty_row=False)
-if which in ("all", "time", "roles"):
+if which in ("all", "time", "roles", "roles5"):
     import ctypes
     from neuralasr_b200 import _lib
     lib = _lib.load()
-    g = make_batch(1234, T=1000, B=256, C=38, Lmax=200, mode="full", Lmin=100, empty_row=False)
+    if which == "roles5":
+        shape = dict(T=800, B=128, C=1024, Lmax=150, mode="full", Lmin=75, empty_row=False)
+    else:
+        shape = dict(T=1000, B=256, C=38, Lmax=200, mode="full", Lmin=100, empty_row=False)
+    NB = shape["B"]
+    g = make_batch(1234, **shape)
     x = torch.from_numpy(g["logits"]).to(dev)
     lab = common.prepare_labels(_triple(g), dev)
     seq = torch.from_numpy(g["seq_len"]).to(dev)
-    prof = torch.zeros(256 * 8 * 4 + 4 * 200 * 8 * 2, dtype=torch.int64, device=dev)
+    prof = torch.zeros(NB * 16 * 4 + 4 * 200 * 8 * 2, dtype=torch.int64, device=dev)
     common.debug_config(2, 0)
     gr = torch.empty_like(x)
     common.ctc_loss_and_grad(x, lab, seq, out_grad=gr)
@@ -96,28 +101,27 @@ if which in ("all", "time", "roles"):
     torch.cuda.synchronize()
     lib.nasr_debug_profile(None)
     common.debug_config(0, 0)
-    trace = prof.cpu().numpy()[256 * 32:].reshape(4, 200, 8, 2)
+    trace = prof.cpu().numpy()[NB * 64:].reshape(4, 200, 8, 2)
     np.save(os.path.join(ROOT, 'gpurun_out', 'r1_trace.npy'), trace)
-    np.save(os.path.join(ROOT, 'gpurun_out', 'r1_trace_roles.npy'), prof.cpu().numpy()[:256 * 32].reshape(256, 8, 4)[:4, :, 3])
-    pr = prof.cpu().numpy()[:256 * 32].reshape(256, 8, 4)
+    pr = prof.cpu().numpy()[:NB * 64].reshape(NB, 16, 4)
+    np.save(os.path.join(ROOT, 'gpurun_out', 'r1_trace_roles.npy'), pr[:4, :8, 3])
     names = ["H_F", "H_B", "RC_F", "RC_B", "P_F", "P_B", "G_F", "G_B"]
     print("per-role cycles (mean over CTAs | max): work before meeting, work after meeting, total")
+    live = pr[:, :, 2] > 0
     for r in range(8):
-        sel = (pr[:, :, 3] & 255) == r
+        sel = ((pr[:, :, 3] & 255) == r) & live
         w1, w2, tot = pr[:, :, 0][sel], pr[:, :, 1][sel], pr[:, :, 2][sel]
-        print("  %-5s phase1 %8.0f | %8d   phase2 %8.0f | %8d   total %8.0f | %8d" % (names[r], w1.mean(), w1.max(), w2.mean(), w2.max(), tot.mean(), tot.max()))
+        print("  %-5s (%2d warps per CTA) phase1 %8.0f | %8d   phase2 %8.0f | %8d   total %8.0f | %8d" % (
+            names[r], sel.sum() // NB, w1.mean(), w1.max(), w2.mean(), w2.max(), tot.mean(), tot.max()))
     smid = pr[:, 0, 3] >> 8
-    print("  smid of CTA 0..15:", smid[:16].tolist(), " CTA 148..163:", smid[148:164].tolist())
     import collections
     by = collections.defaultdict(list)
-    for bb in range(256):
+    for bb in range(NB):
         by[int(smid[bb])].append(bb)
     pairs = [v for v in by.values() if len(v) == 2]
-    print("  SMs with two CTAs: %d; examples of co-resident CTA ids: %s; pairs whose ids differ by 148: %d" % (
-        len(pairs), pairs[:8], sum(1 for v in pairs if abs(v[0] - v[1]) == 148)))
-    L = np.diff(g["label_offsets"])
+    print("  SMs with two CTAs: %d" % len(pairs))
     tot = pr[:, 0, 2]
-    print("  total cycles by CTA index: first wave(0..147) mean %.0f, second wave(148..255) mean %.0f" % (tot[:148].mean(), tot[148:].mean()))
+    print("  total cycles per CTA: mean %.0f max %d" % (tot.mean(), tot.max()))
 if which == "ablate":
     g = make_batch(1234, T=1000, B=256, C=38, Lmax=200, mode="full", Lmin=100, empty_row=False)
     x = torch.from_numpy(g["logits"]).to(dev)
