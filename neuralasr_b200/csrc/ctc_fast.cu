@@ -40,7 +40,7 @@ namespace fast {
 constexpr int KC = 8;            // frames per chunk (= rescale and checkpoint interval)
 constexpr int IFIRST = -5;       // first iteration: the producers' copies run five iterations ahead of the recursion
 constexpr int NTHREADS = 256;    // 8 warps
-constexpr int NTHREADS_WIDE = 448;  // wide-vocabulary variant: 2 recursion + 2 recompute + 2 gradient + 8 producer warps
+constexpr int NTHREADS_WIDE = 512;  // wide-vocabulary variant: 2 recursion + 2 recompute + 4 gradient + 8 producer warps
 constexpr int GCAP = 200;        // a lane with mass sits at most this far below the nearest lane with mass beneath it
 constexpr int GROWTH = 550;      // bits a lane maximum may grow inside one chunk (GCAP of inflow + 350 of emissions)
 // Certificate: a value flushed in a lane of exponent Ea is < 2^(Ea-1022); its partner in the other direction is
@@ -516,7 +516,7 @@ __device__ __forceinline__ uint32_t gcell(int pos) {
 // four schedulers.
 __device__ int g_sm_arrivals[1024];
 
-// EPL = 0 instantiates the wide-vocabulary variant (64 < C <= 1024, C % 4 == 0): 14 warps, one CTA per SM.
+// EPL = 0 instantiates the wide-vocabulary variant (64 < C <= 1024, C % 4 == 0): 16 warps, one CTA per SM.
 template <int NL, int EPL>
 __global__ void __launch_bounds__((EPL ? NTHREADS : NTHREADS_WIDE), ((EPL && NL <= 8) ? 2 : 1))
 ctc_fast_kernel(const Params p) {
@@ -674,8 +674,9 @@ ctc_fast_kernel(const Params p) {
   if (tid == 0) s_scal[3] = atomicAdd(&g_sm_arrivals[smid & 1023], 1);
   __syncthreads();
   const int perm = WIDE ? 0 : (s_scal[3] & 1);
-  // wide: warps 0-3 recursion / recompute, 4-5 gradient, 6-13 producers (side = parity)
-  const int role = WIDE ? (warp < 4 ? warp : (warp < 6 ? G_F + (warp & 1) : P_F + (warp & 1))) : (warp ^ (perm << 1));
+  // wide: warps 0-3 recursion / recompute, 4-7 gradient (4,5 frames 0-3 of a chunk, 6,7 frames 4-7),
+  // 8-15 producers; side = parity of the warp index
+  const int role = WIDE ? (warp < 4 ? warp : (warp < 8 ? G_F + (warp & 1) : P_F + (warp & 1))) : (warp ^ (perm << 1));
   const int d = role & 1;  // direction / side this warp works for
   __syncthreads();
 
@@ -715,11 +716,12 @@ ctc_fast_kernel(const Params p) {
     if (L > 0) pc_tot = gcell<NL>(L - 1) * 4u;
   }
   // wide gradient warps: this lane's share of the distinct classes of the transcript (at most NL of them)
-  int wd_cls[NL], wd_lo[NL], wd_hi[NL];
+  constexpr int WD = WIDE ? NL : 1;
+  int wd_cls[WD], wd_lo[WD], wd_hi[WD];
   if (WIDE && role >= G_F) {
     const int U = s_scal[6];
 #pragma unroll
-    for (int i = 0; i < NL; i++) {
+    for (int i = 0; i < WD; i++) {
       const int u = lane + 32 * i;
       wd_cls[i] = u < U ? s_dtab[u] : -1;
       wd_lo[i] = u < U ? s_dtab[N + u] : N;
@@ -883,8 +885,8 @@ ctc_fast_kernel(const Params p) {
       // Warp j of a side converts rows j and j+4 of every chunk of that side, two iterations before the
       // recursion needs it; the row that follows is requested while the current one is processed, and the
       // rows of two chunks later are prefetched into L2.
-      const int pj = (warp - 6) >> 1;
-      float* rowbuf = s_rowbuf + (size_t)(warp - 6) * C;
+      const int pj = (warp - 8) >> 1;
+      float* rowbuf = s_rowbuf + (size_t)(warp - 8) * C;
       int pcls[NL];
       {
         const int pad = N - L - 1;
@@ -900,7 +902,7 @@ ctc_fast_kernel(const Params p) {
         }
       }
       double lsum = 0.0;
-      float* stA = s_stage + (size_t)(warp - 6) * 2 * C;   // staging rows of this warp: row pj and row pj+4
+      float* stA = s_stage + (size_t)(warp - 8) * 2 * C;   // staging rows of this warp: row pj and row pj+4
       float* stB = stA + C;
       auto row_ptr = [&](const Chunk& ci, int f) {
         const int ff = min(f, ci.len - 1);
@@ -945,7 +947,7 @@ ctc_fast_kernel(const Params p) {
           const float ly = wide_row<NL>(r, rowbuf, recs + (pj + 4) * N, pcls, grow, gs, C, blank, lane, alarm);
           if (ci.phase == 1) lsum += (double)ly;
         }
-        if (lane == 0) s_psum[warp - 6] = lsum;
+        if (lane == 0) s_psum[warp - 8] = lsum;
         NASR_PROF_END();
         cta_sync();
       }
@@ -1020,8 +1022,11 @@ ctc_fast_kernel(const Params p) {
         const unsigned char* rows = s_rows + (size_t)(d * 4 + ((I - 1) & 3)) * KC * rowbytes;
         const int c0 = lane, c1 = lane + 32;
         constexpr int NF = 4;  // frames in flight: their dependency chains interleave
+        // wide: two gradient warps per side, each takes one half of the chunk's frames
+        const int f_first = WIDE ? ((warp >> 1) & 1) * NF : 0;
+        const int f_step = WIDE ? 2 * NF : NF;
 #pragma unroll 1
-        for (int f0 = 0; f0 < ci.len; f0 += NF) {
+        for (int f0 = f_first; f0 < ci.len; f0 += f_step) {
           float v[NF][NL];
 #pragma unroll
           for (int j = 0; j < NF; j++)
@@ -1062,7 +1067,7 @@ ctc_fast_kernel(const Params p) {
                 // one contribution per cell, so the order-free reduction in L2 is deterministic; red
                 // does not wait for a round trip the way a load-modify-store would
 #pragma unroll
-                for (int i = 0; i < NL; i++)
+                for (int i = 0; i < WD; i++)
                   if (wd_cls[i] >= 0) atomicAdd(g + wd_cls[i], -(gs * (Gr[wd_hi[i]] - Gr[wd_lo[i]])));
                 if (lane == 0) atomicAdd(g + blank, -(gs * (1.0f - Gr[pc_tot >> 2])));
               }
