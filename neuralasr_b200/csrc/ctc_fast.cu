@@ -1021,7 +1021,7 @@ ctc_fast_kernel(const Params p) {
         float* G = s_gbuf + (size_t)(d * 2 + buf) * GBUF;
         const unsigned char* rows = s_rows + (size_t)(d * 4 + ((I - 1) & 3)) * KC * rowbytes;
         const int c0 = lane, c1 = lane + 32;
-        constexpr int NF = 4;  // frames in flight: their dependency chains interleave
+        constexpr int NF = 4;  // frames in flight (8 was measured: the extra shared-memory traffic in flight slows the recursion warps): their dependency chains interleave
         // wide: two gradient warps per side, each takes one half of the chunk's frames
         const int f_first = WIDE ? ((warp >> 1) & 1) * NF : 0;
         const int f_step = WIDE ? 2 * NF : NF;

@@ -151,3 +151,21 @@ if which == "ablate":
     b.record(); torch.cuda.synchronize()
     print("loss only (phase 1 + meeting)        %.3f ms" % (a.elapsed_time(b) / 20))
     common.debug_config(0, 0)
+if which == "bsweep":
+    for NB in (64, 128, 148, 192, 256, 296):
+        g = make_batch(1234, T=1000, B=NB, C=38, Lmax=200, mode="full", Lmin=100, empty_row=False)
+        x = torch.from_numpy(g["logits"]).to(dev)
+        lab = common.prepare_labels(_triple(g), dev)
+        seq = torch.from_numpy(g["seq_len"]).to(dev)
+        xs = [x.clone() for _ in range(6)]
+        gs = [torch.empty_like(x) for _ in range(6)]
+        for i in range(3):
+            common.ctc_loss_and_grad(xs[i % 6], lab, seq, out_grad=gs[i % 6])
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(20):
+            common.ctc_loss_and_grad(xs[i % 6], lab, seq, out_grad=gs[i % 6])
+        b.record(); torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 20
+        print("B=%3d: %.3f ms per call, %.2f us per utterance" % (NB, ms, 1e3 * ms / NB))
