@@ -86,7 +86,7 @@ if which in ("all", "time", "roles", "roles5"):
     if which == "roles5":
         shape = dict(T=800, B=128, C=1024, Lmax=150, mode="full", Lmin=75, empty_row=False)
     else:
-        shape = dict(T=1000, B=256, C=38, Lmax=200, mode="full", Lmin=100, empty_row=False)
+        shape = dict(T=1000, B=int(os.environ.get("NB", "256")), C=38, Lmax=200, mode="full", Lmin=100, empty_row=False)
     NB = shape["B"]
     g = make_batch(1234, **shape)
     x = torch.from_numpy(g["logits"]).to(dev)
