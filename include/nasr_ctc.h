@@ -145,6 +145,32 @@ int nasr_ctc_greedy_decode_strided_i64(const float* logits, int T, int B, int C,
                                        int merge_repeated, int64_t* hyp, int32_t* hyp_len,
                                        float* neg_sum_logits, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Beam search decode.  Replaces tf.nn.ctc_beam_search_decoder(logits, seq_len) with its defaults
+ * (beam_width=100, top_paths=1, merge_repeated=True) — what create_model runs today,
+ * networks/tfnetwork.py:62,64.
+ *   hyp       int64[B, top_paths, T]  row (b, p) holds hyp_len[b, p] label ids of the p-th best prefix (repeats
+ *                                     collapsed in the output when merge_repeated, like TF)
+ *   hyp_len   int32[B, top_paths]     0 for paths beyond the number of prefixes the beam holds
+ *   log_prob  float32[B, top_paths]   log P(prefix | logits) under the log-softmax of the logits (-inf when absent)
+ * Scores are computed in float64; ties are broken by (kept prefix before new extension, prefix hash).
+ * workspace: nasr_ctc_beam_workspace_bytes(T, B, C, beam_width) bytes (the per-utterance prefix trie).
+ * Supported: beam_width * C < 2^20 and the shared-memory footprint under 200 KB (beam_width <= 1024 at C = 38,
+ * beam_width <= 256 at C = 1024); otherwise NASR_ERR_UNSUPPORTED.
+ * ---------------------------------------------------------------------------------------------- */
+int nasr_ctc_beam_workspace_bytes(int T, int B, int C, int beam_width, size_t* out_bytes);
+
+int nasr_ctc_beam_search_i64(const float* logits, int T, int B, int C, const int32_t* seq_len, int blank,
+                             int beam_width, int top_paths, int merge_repeated, int64_t* hyp,
+                             int32_t* hyp_len, float* log_prob, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
+/* Same for strided logits (see nasr_ctc_loss_grad_strided_f32). */
+int nasr_ctc_beam_search_strided_i64(const float* logits, int T, int B, int C, long long stride_t,
+                                     long long stride_b, const int32_t* seq_len, int blank, int beam_width,
+                                     int top_paths, int merge_repeated, int64_t* hyp, int32_t* hyp_len,
+                                     float* log_prob, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Dense hypotheses -> the SparseTensor triple TF returns as decoded[0] (tfnetwork.py:64):
  * hyp_offsets int32[B+1] must hold the exclusive prefix sum of hyp_len (M = hyp_offsets[B]);
  * indices int64[M,2] row-major (b, position), values int64[M], dense_shape int64[2] = [B, max len]. */

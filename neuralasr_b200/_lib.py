@@ -30,6 +30,10 @@ SIGNATURES = {
     "nasr_ctc_greedy_decode_i64": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "nasr_ctc_greedy_decode_strided_i64": (_i, [_vp, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _vp, _i, _i,
                                                 _vp, _vp, _vp, _vp]),
+    "nasr_ctc_beam_workspace_bytes": (_i, [_i, _i, _i, _i, ctypes.POINTER(_sz)]),
+    "nasr_ctc_beam_search_i64": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "nasr_ctc_beam_search_strided_i64": (_i, [_vp, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _vp, _i, _i,
+                                              _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nasr_hyp_to_sparse_i64": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "nasr_edit_distance_i64": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "nasr_edit_distance_csr_i64": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),

@@ -39,6 +39,12 @@ int hyp_to_sparse(const int64_t* hyp, int hyp_stride, const int32_t* hyp_offsets
                   int64_t* indices, int64_t* values, int64_t* dense_shape, cudaStream_t stream);
 int batch_sums(const float* loss, const float* ler, const int32_t* dist, int B, double* sums,
                cudaStream_t stream);
+// ctc_beam.cu
+int ctc_beam_workspace_bytes(int T, int B, int C, int W, size_t* out);
+int ctc_beam_search(const float* logits, int T, int B, int C, long long st_t, long long st_b,
+                    const int32_t* seq_len, int blank, int W, int P, int merge_repeated, int64_t* hyp,
+                    int32_t* hyp_len, float* log_prob, void* workspace, size_t workspace_bytes,
+                    cudaStream_t stream);
 extern int g_debug_path;   // ctc_loss.cu
 extern int g_debug_split;  // ctc_fast.cu
 extern long long* g_debug_prof;
@@ -246,6 +252,31 @@ int nasr_ctc_greedy_decode_strided_i64(const float* logits, int T, int B, int C,
                                        float* neg_sum_logits, void* stream) {
   return greedy_decode(logits, T, B, C, stride_t, stride_b, seq_len, blank, merge_repeated, hyp, hyp_len,
                        neg_sum_logits, static_cast<cudaStream_t>(stream));
+}
+
+int nasr_ctc_beam_workspace_bytes(int T, int B, int C, int beam_width, size_t* out_bytes) {
+  NASR_CHECK_ARG(out_bytes, "nasr_ctc_beam_workspace_bytes: out_bytes is NULL");
+  NASR_CHECK_ARG(T >= 0 && B >= 0 && C >= 1 && beam_width >= 1,
+                 "nasr_ctc_beam_workspace_bytes: bad shape T=%d B=%d C=%d beam_width=%d", T, B, C, beam_width);
+  return ctc_beam_workspace_bytes(T, B, C, beam_width, out_bytes);
+}
+
+int nasr_ctc_beam_search_i64(const float* logits, int T, int B, int C, const int32_t* seq_len, int blank,
+                             int beam_width, int top_paths, int merge_repeated, int64_t* hyp,
+                             int32_t* hyp_len, float* log_prob, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  return ctc_beam_search(logits, T, B, C, (long long)B * C, C, seq_len, blank, beam_width, top_paths,
+                         merge_repeated, hyp, hyp_len, log_prob, workspace, workspace_bytes,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int nasr_ctc_beam_search_strided_i64(const float* logits, int T, int B, int C, long long stride_t,
+                                     long long stride_b, const int32_t* seq_len, int blank, int beam_width,
+                                     int top_paths, int merge_repeated, int64_t* hyp, int32_t* hyp_len,
+                                     float* log_prob, void* workspace, size_t workspace_bytes, void* stream) {
+  return ctc_beam_search(logits, T, B, C, stride_t, stride_b, seq_len, blank, beam_width, top_paths,
+                         merge_repeated, hyp, hyp_len, log_prob, workspace, workspace_bytes,
+                         static_cast<cudaStream_t>(stream));
 }
 
 int nasr_hyp_to_sparse_i64(const int64_t* hyp, int hyp_stride, const int32_t* hyp_offsets, int B,

@@ -297,7 +297,7 @@ class DecodedSparse:
             values = torch.empty(M, dtype=torch.int64, device=dev)
             shape = torch.empty(2, dtype=torch.int64, device=dev)
             with torch.cuda.device(dev):
-                _lib.check(lib.nasr_hyp_to_sparse_i64(_ptr(self.hyp), T, _ptr(offs), B, _ptr(indices),
+                _lib.check(lib.nasr_hyp_to_sparse_i64(_ptr(self.hyp), self.hyp.stride(0), _ptr(offs), B, _ptr(indices),
                                                       _ptr(values), _ptr(shape), _stream_ptr(dev)),
                            "nasr_hyp_to_sparse")
             self._triple = (indices, values, shape)
@@ -339,6 +339,50 @@ def decoding(logits, seq_len, merge_repeated=True, blank=None):
 
 
 # --------------------------------------------------------------------------------------------
+# beam search decode
+# --------------------------------------------------------------------------------------------
+_BEAM_WORKSPACES = {}
+
+
+def beam_decoding(logits, seq_len, beam_width=100, top_paths=1, merge_repeated=True, blank=None):
+    """CTC beam search — ``tf.nn.ctc_beam_search_decoder(logits, seq_len, beam_width, top_paths,
+    merge_repeated)``, the op ``create_model`` runs (``networks/tfnetwork.py:62``).  Returns
+    ``(decoded, log_probability)`` like TF: ``decoded`` is a list of ``top_paths`` :class:`DecodedSparse`
+    (best first), ``log_probability`` float32 ``[B, top_paths]``."""
+    lib = _lib.load()
+    logits = _check_logits(logits)
+    T, B, C = logits.shape
+    dev = logits.device
+    blank = C - 1 if blank is None else int(blank)
+    W, P = int(beam_width), int(top_paths)
+    sl = _seq_len_tensor(seq_len, dev, B)
+    hyp = torch.empty((B, P, T), dtype=torch.int64, device=dev)
+    hyp_len = torch.empty((B, P), dtype=torch.int32, device=dev)
+    log_prob = torch.empty((B, P), dtype=torch.float32, device=dev)
+    need = ctypes.c_size_t(0)
+    _lib.check(lib.nasr_ctc_beam_workspace_bytes(T, B, C, W, ctypes.byref(need)), "beam workspace")
+    key = (dev.type, dev.index)
+    ws = _BEAM_WORKSPACES.get(key)
+    if ws is None or ws.numel() < need.value:
+        ws = torch.empty(max(need.value, 1), dtype=torch.uint8, device=dev)
+        _BEAM_WORKSPACES[key] = ws
+    with torch.cuda.device(dev):
+        _lib.check(lib.nasr_ctc_beam_search_strided_i64(_ptr(logits), T, B, C, logits.stride(0), logits.stride(1),
+                                                        _ptr(sl), blank, W, P, int(bool(merge_repeated)),
+                                                        _ptr(hyp), _ptr(hyp_len), _ptr(log_prob), _ptr(ws),
+                                                        ws.numel(), _stream_ptr(dev)), "nasr_ctc_beam_search")
+    decoded = [DecodedSparse(hyp[:, p, :], hyp_len[:, p].contiguous()) for p in range(P)]
+    return decoded, log_prob
+
+
+def create_model_beam(logits, seq_len):
+    """``create_model`` exactly as the snapshot has it (``networks/tfnetwork.py:61-64``): beam search with TF's
+    defaults, returning ``(decoded[0], log_prob)``."""
+    decoded, log_prob = beam_decoding(logits, seq_len)
+    return decoded[0], log_prob
+
+
+# --------------------------------------------------------------------------------------------
 # label error rate
 # --------------------------------------------------------------------------------------------
 def edit_distance(model, labels, normalize=True):
@@ -353,7 +397,7 @@ def edit_distance(model, labels, normalize=True):
         dist = torch.empty(B, dtype=torch.int32, device=dev)
         ler = torch.empty(B, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.nasr_edit_distance_i64(_ptr(model.hyp), T, _ptr(model.hyp_len),
+            _lib.check(lib.nasr_edit_distance_i64(_ptr(model.hyp), model.hyp.stride(0), _ptr(model.hyp_len),
                                                   _ptr(lab.values), _ptr(lab.offsets), lab.max_len, B,
                                                   int(bool(normalize)), _ptr(dist), _ptr(ler),
                                                   _stream_ptr(dev)), "nasr_edit_distance")

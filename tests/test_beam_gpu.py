@@ -1,0 +1,127 @@
+"""GPU parity of the beam search decoder (csrc/ctc_beam.cu, through the C-ABI) against oracle/beam_oracle.py.
+
+Label sequences must be identical and log probabilities equal to float32 rounding: both sides compute in
+float64 with the same formulas and the same tie-break (score, kept prefix before new extension, prefix hash),
+so they can only part on a score comparison closer than the two libms' last bit."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import beam_oracle as bo
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(x, seq_len, W=100, P=1, merge=True):
+    from neuralasr_b200.networks import common
+    dec, lp = common.beam_decoding(torch.from_numpy(x).cuda(), seq_len, beam_width=W, top_paths=P,
+                                   merge_repeated=merge)
+    torch.cuda.synchronize()
+    out = []
+    for p in range(P):
+        hyp = dec[p].hyp.cpu().numpy()
+        hl = dec[p].hyp_len.cpu().numpy()
+        out.append([hyp[b, :hl[b]].tolist() for b in range(x.shape[1])])
+    return out, lp.cpu().numpy()
+
+
+def _check(x, seq_len, W=100, P=1, merge=True):
+    got, lp = _run(x, seq_len, W, P, merge)
+    for b in range(x.shape[1]):
+        want = bo.beam_search_one(x[: int(seq_len[b]), b, :].astype(np.float64), W, merge, top_paths=P)
+        for p in range(P):
+            if p < len(want):
+                assert got[p][b] == want[p][0], (b, p)
+                assert abs(lp[b, p] - want[p][1]) <= 1e-6 * max(1.0, abs(want[p][1])), (b, p, lp[b, p], want[p][1])
+            else:
+                assert got[p][b] == [] and lp[b, p] == -np.inf
+
+
+def _peaky(rng, T, B, C, noise=1.0):
+    """Planted alignment: each label held 1-4 frames with blanks between, +8 on the planted class."""
+    x = rng.normal(size=(T, B, C)).astype(np.float32) * noise
+    for b in range(B):
+        t = 0
+        while t < T:
+            c = rng.integers(0, C - 1) if rng.random() < 0.6 else C - 1
+            hold = int(rng.integers(1, 5))
+            x[t:t + hold, b, c] += 8.0
+            t += hold
+    return x
+
+
+@pytest.mark.parametrize("T,B,C,W", [(12, 3, 5, 4), (30, 4, 38, 100), (25, 2, 38, 16), (40, 2, 7, 128), (9, 2, 3, 100)])
+def test_random_logits(T, B, C, W):
+    rng = np.random.default_rng(T * 1000 + C)
+    x = (rng.normal(size=(T, B, C)) * 3).astype(np.float32)
+    seq = np.array([T] + list(rng.integers(1, T + 1, size=B - 1)), np.int32)
+    _check(x, seq, W)
+
+
+def test_peaky_logits_c38_w100():
+    rng = np.random.default_rng(7)
+    x = _peaky(rng, 60, 3, 38)
+    _check(x, np.array([60, 45, 33], np.int32), 100)
+
+
+def test_top_paths_and_no_merge():
+    rng = np.random.default_rng(11)
+    x = (rng.normal(size=(20, 2, 6)) * 2).astype(np.float32)
+    _check(x, np.array([20, 13], np.int32), W=32, P=5, merge=True)
+    _check(x, np.array([20, 13], np.int32), W=32, P=3, merge=False)
+
+
+def test_exact_ties_uniform_logits():
+    # every extension of a frame ties exactly: the (kept first, hash) order decides, identically on both sides
+    x = np.zeros((8, 2, 6), np.float32)
+    _check(x, np.array([8, 5], np.int32), W=10, P=4, merge=False)
+
+
+def test_merge_repeated_quirk_and_empty():
+    a, b, blank = 0, 1, 2
+    x = np.full((6, 3, 3), -4.0, np.float32)
+    for t, c in enumerate([a, a, blank, a, b, b]):
+        x[t, :, c] = 4.0
+    got, lp = _run(x, np.array([6, 3, 0], np.int32), 100, 1, True)
+    assert got[0][0] == [a, b] and got[0][1] == [a] and got[0][2] == []
+    assert lp[2, 0] == 0.0
+    got, _ = _run(x, np.array([6, 3, 0], np.int32), 100, 1, False)
+    assert got[0][0] == [a, a, b]
+
+
+def test_wide_vocabulary_and_batch_major_view():
+    rng = np.random.default_rng(3)
+    xb = _peaky(rng, 24, 2, 300).transpose(1, 0, 2).copy()      # [B, T, C] as a model produces it
+    from neuralasr_b200.networks import common
+    view = common.batch_major(torch.from_numpy(xb).cuda())      # [T, B, C] strided view, no copy
+    dec, lp = common.beam_decoding(view, np.array([24, 17], np.int32), beam_width=20)
+    hyp, hl = dec[0].hyp.cpu().numpy(), dec[0].hyp_len.cpu().numpy()
+    for b, Tb in enumerate([24, 17]):
+        want = bo.beam_search_one(xb[b, :Tb].astype(np.float64), 20, True)
+        assert hyp[b, :hl[b]].tolist() == want[0]
+        assert abs(lp[b, 0].item() - want[1]) <= 1e-6 * max(1.0, abs(want[1]))
+
+
+def test_beam_feeds_label_error_rate_like_create_model_create_metric():
+    from neuralasr_b200.networks import common
+    from neuralasr_b200.utils import sparse_tuple_from
+    rng = np.random.default_rng(5)
+    x = _peaky(rng, 50, 4, 38, noise=0.5)
+    seq = np.array([50, 50, 40, 30], np.int32)
+    model, log_prob = common.create_model_beam(torch.from_numpy(x).cuda(), seq)
+    truth = [bo.beam_search_one(x[: seq[b], b].astype(np.float64))[0] or [0] for b in range(4)]
+    truth[1] = truth[1][:-1] + [(truth[1][-1] + 1) % 37]          # one substitution
+    labels = sparse_tuple_from([np.array(t) for t in truth], [len(t) for t in truth])
+    ler = common.label_error_rate(model, labels)
+    assert ler.distances.cpu().tolist()[1] == 1
+    assert log_prob.shape == (4, 1)
+    assert tuple(model.dense_shape.cpu().tolist())[0] == 4
+
+
+def test_unsupported_and_bad_arguments():
+    from neuralasr_b200.networks import common
+    x = torch.zeros((4, 1, 5), device="cuda")
+    with pytest.raises(ValueError):
+        common.beam_decoding(x, np.array([4], np.int32), beam_width=4, top_paths=8)
+    with pytest.raises(ValueError):
+        common.beam_decoding(x.cpu(), np.array([4], np.int32))
