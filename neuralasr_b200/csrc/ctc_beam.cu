@@ -30,16 +30,18 @@
 #include "nasr_common.cuh"
 
 namespace nasr {
+extern long long* g_debug_prof;  // ctc_fast.cu (nasr_debug_profile)
 namespace {
 
 typedef unsigned long long u64;
 
-constexpr int kBeamThreads = 512;
-constexpr int kBeamWarps = kBeamThreads / 32;
-constexpr int kBins = 2048;  // 11-bit digits
-constexpr int kBinsPerThread = kBins / kBeamThreads;
+constexpr int kSearchThreads = 512;                 // the warps that search
+constexpr int kSearchWarps = kSearchThreads / 32;
+constexpr int kBeamThreads = kSearchThreads + 32;   // + one warp that prepares the next frame's log-softmax
+constexpr int kIPT = 8;                             // candidate keys a search thread keeps in registers
+constexpr int kBins = 2048;                         // 11-bit digits
+constexpr int kBinsPerThread = kBins / kSearchThreads;
 constexpr u64 kRootHash = 0x243f6a8885a308d3ull;
-constexpr int kPrefetch = 2;  // logits of the next frame held in registers: C <= 2*512
 
 __host__ __device__ inline u64 mix64(u64 x) {
   x ^= x >> 30;
@@ -60,6 +62,10 @@ __device__ __forceinline__ u64 okey(double v) {
   const long long b = __double_as_longlong(v);
   return (u64)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
 }
+__device__ __forceinline__ double okey_inv(u64 k) {
+  const long long b = (long long)k;
+  return __longlong_as_double(b < 0 ? (b ^ (long long)0x8000000000000000ull) : ~b);
+}
 
 __device__ __forceinline__ double lse2(double a, double b) {
   const double ninf = neg_inf();
@@ -69,15 +75,25 @@ __device__ __forceinline__ double lse2(double a, double b) {
   return m + log1p(exp(n - m));
 }
 
+// barrier of the search warps only (the producer warp meets them once per frame at barrier 0)
+__device__ __forceinline__ void bar_search() { asm volatile("bar.sync 1, %0;" ::"n"(kSearchThreads) : "memory"); }
+
 __host__ __device__ inline size_t al16(size_t n) { return (n + 15) & ~(size_t)15; }
+__host__ __device__ inline int tab_size(int W) {
+  int s = 64;
+  while (s < 2 * W) s <<= 1;
+  return s;
+}
 
 __host__ __device__ inline size_t beam_smem_bytes(int W, int C) {
   const int CW = (C + 31) / 32;
   size_t s = 0;
-  s += al16(sizeof(double) * C) + al16(sizeof(float) * C);
+  s += al16(sizeof(double) * 2 * C);
   s += 3 * al16(sizeof(double) * 2 * W) + 2 * al16(sizeof(u64) * 2 * W) + 5 * al16(sizeof(int) * 2 * W);
   s += 3 * al16(sizeof(double) * W);
-  s += al16(sizeof(int) * W);
+  s += 3 * al16(sizeof(int) * W) + al16(sizeof(int) * C);
+  s += al16(sizeof(u64) * W);
+  s += al16(sizeof(u64) * tab_size(W)) + al16(sizeof(int) * tab_size(W));
   s += al16(sizeof(uint32_t) * (size_t)W * CW);
   s += al16(sizeof(int) * kBins);
   s += al16(sizeof(double) * 64) + al16(sizeof(u64) * 64) + al16(sizeof(int) * 64);
@@ -104,15 +120,15 @@ struct Ctx {
   // frame constants every candidate evaluation needs
   const double *lp, *pb, *pt, *ut;
   const u64* hash;
-  const int *last, *live;
+  const int *last, *liveP, *liveL;
   const uint32_t* mask;
-  int n, C, CW, blank;
-  u64 divM;  // floor(2^40 / C) + 1: j / C == (j * divM) >> 40 for j < 2^20
+  int n, nL, CW;
+  unsigned divM;  // floor((2^32-1) / nL) + 1: j / nL == umulhi(j, divM) for j < 2^20 (nL >= 2)
   double tau0;
 };
 
-// Candidate i of the frame: i < n is active prefix i itself (l = -1); otherwise extension (live[q], l) with
-// i - n = q*C + l.
+// Candidate i of the frame: i < n is active prefix i itself (l = -1); otherwise the extension of live prefix
+// liveP[q] by live label liveL[r], i - n = q*nL + r.
 __device__ __forceinline__ void item_of(const Ctx& c, int i, int& b, int& l) {
   if (i < c.n) {
     b = i;
@@ -120,33 +136,39 @@ __device__ __forceinline__ void item_of(const Ctx& c, int i, int& b, int& l) {
     return;
   }
   const unsigned j = (unsigned)(i - c.n);
-  const unsigned q = (unsigned)(((u64)j * c.divM) >> 40);
-  l = (int)(j - q * (unsigned)c.C);
-  b = c.live[q];
+  const unsigned q = c.nL == 1 ? j : __umulhi(j, c.divM);
+  b = c.liveP[q];
+  l = c.liveL[j - q * (unsigned)c.nL];
 }
 
-// Its score; false if it is not offered to the beam.
-__device__ __forceinline__ bool eval_item(const Ctx& c, int i, double& v, int& b, int& l) {
+// Its key (order-preserving image of its score), 0 if it is not offered to the beam.
+__device__ __forceinline__ u64 eval_key(const Ctx& c, int i) {
+  int b, l;
   item_of(c, i, b, l);
+  double v;
+  bool ok;
   if (l < 0) {
     v = c.ut[b];
-    return v > neg_inf();
+    ok = v > neg_inf();
+  } else {
+    const bool masked = (c.mask[b * c.CW + (l >> 5)] >> (l & 31)) & 1u;
+    v = c.lp[l] + (l == c.last[b] ? c.pb[b] : c.pt[b]);
+    ok = !masked && v > c.tau0;
   }
-  if (l == c.blank) return false;
-  if ((c.mask[b * c.CW + (l >> 5)] >> (l & 31)) & 1u) return false;
-  v = c.lp[l] + (l == c.last[b] ? c.pb[b] : c.pt[b]);
-  return v > c.tau0;
+  return ok ? okey(v) : 0ull;
 }
 
-__device__ __forceinline__ u64 item_k2(const Ctx& c, int b, int l) {
+__device__ __forceinline__ u64 item_k2(const Ctx& c, int i) {
   // active prefixes win ties against extensions (TF admits an extension only if it is strictly better than the
   // worst kept entry); then the smaller hash wins
+  int b, l;
+  item_of(c, i, b, l);
   if (l < 0) return 0x8000000000000000ull | ((~c.hash[b]) >> 1);
   return (~child_hash(c.hash[b], l)) >> 1;
 }
 
 // Find, from the top bin down, the bin in which the running count reaches `need`.  hist is left zeroed.
-// res[0] = bin, res[1] = candidates in the bins above it, res[2] = candidates in it.
+// res[0] = bin, res[1] = candidates in the bins above it, res[2] = candidates in it.  Search warps only.
 __device__ __forceinline__ void find_bin(int* hist, int nb, int need, int* wsum, int* res, int tid) {
   const int lane = tid & 31, warp = tid >> 5;
   int loc[kBinsPerThread];
@@ -163,7 +185,7 @@ __device__ __forceinline__ void find_bin(int* hist, int nb, int need, int* wsum,
   }
   int incl = warp_incl_scan(sum, lane);
   if (lane == 31) wsum[warp] = incl;
-  __syncthreads();
+  bar_search();
   for (int w = 0; w < warp; w++) incl += wsum[w];
   const int excl = incl - sum;
   if (excl < need && need <= incl) {
@@ -179,26 +201,23 @@ __device__ __forceinline__ void find_bin(int* hist, int nb, int need, int* wsum,
       cum += loc[k];
     }
   }
-  __syncthreads();
+  bar_search();
 }
 
-// IPT > 0: every thread keeps the keys of its IPT candidates in registers between the selection passes
-// (W*(C+1) <= IPT*512); IPT == 0: candidates are recomputed in every pass (any W*C the tables fit for).
-template <int IPT>
 __global__ void __launch_bounds__(kBeamThreads, 2)
 ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long st_t, long long st_b,
                 const int32_t* __restrict__ seq_len, int blank, int W, int P, int merge_repeated,
                 int64_t* hyp, int32_t* __restrict__ hyp_len, float* __restrict__ log_prob,
-                int2* nodes_all, u64 divM) {
+                int2* nodes_all, long long* prof) {
   extern __shared__ __align__(16) char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b_utt = blockIdx.x;
   const int CW = (C + 31) / 32;
+  const int TS = tab_size(W);
   const double ninf = neg_inf();
 
   char* sp = smem_raw;
-  double* s_lp = carve<double>(sp, C);
-  float* s_xs = carve<float>(sp, C);
+  double* s_lp2 = carve<double>(sp, 2 * C);  // log-softmax rows of frame t (t&1) and t+1
   // the two beam buffers are the halves [0,W) and [W,2W) of each array
   double* g_pb = carve<double>(sp, 2 * W);   // log P(prefix, ends in blank)
   double* g_pl = carve<double>(sp, 2 * W);   //                ends in its last label
@@ -213,14 +232,22 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
   double* s_ub = carve<double>(sp, W);       // this frame's update of the active prefixes
   double* s_ul = carve<double>(sp, W);
   double* s_ut = carve<double>(sp, W);
-  int* s_live = carve<int>(sp, W);           // prefixes whose extensions can still enter the beam
+  int* s_liveP = carve<int>(sp, W);          // prefixes whose extensions can still enter the beam
+  int* s_newslot = carve<int>(sp, W);        // active prefix -> its slot in the next beam (-1: dropped)
+  int* s_adm_i = carve<int>(sp, W);          // admitted candidates (item index, key)
+  int* s_liveL = carve<int>(sp, C);          // labels whose extension of the best prefix could enter
+  u64* s_adm_k = carve<u64>(sp, W);
+  u64* s_tab_key = carve<u64>(sp, TS);       // hash -> slot of the prefixes that enter the beam this frame
+  int* s_tab_slot = carve<int>(sp, TS);
   uint32_t* s_mask = carve<uint32_t>(sp, (size_t)W * CW);  // [W][CW] labels whose extension is already active
   int* s_hist = carve<int>(sp, kBins);
   double* s_redd = carve<double>(sp, 64);
   u64* s_redu = carve<u64>(sp, 64);
   int* s_redi = carve<int>(sp, 64);
-  // s_redi: [0..15] warp partials, [16..18] find_bin result, [20] new-beam counter, [21] node counter,
-  //         [22] n_live, [32..47] find_bin warp sums;  s_redd: [0..15] max, [16..31] sum, [32] tau0
+  // s_redi: [0..15] warp partials, [16..18] find_bin result, [20] admitted counter, [21] node counter,
+  //         [22] live prefixes, [23] live labels, [32..47] find_bin warp sums
+  // s_redd: [0..15] min of the updated totals, [16..31] max of the old totals, [40..41] max of lp rows t&1
+  // s_redu: [0..15] kmin, [16..31] kmax, [32..39] profile accumulators
 
   int Tb = seq_len[b_utt];
   Tb = max(0, min(T, Tb));
@@ -242,127 +269,161 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
     g_pslot[0] = -1;
     s_redi[21] = 1;
     nodes[0] = make_int2(-1, -1);
+    for (int k = 32; k < 40; k++) s_redu[k] = 0;
   }
-  if (Tb > 0)
-    for (int c = tid; c < C; c += kBeamThreads) s_xs[c] = __ldg(xrow + c);
-  __syncthreads();
 
+  if (warp == kSearchWarps) {
+    // ---- producer warp: log-softmax (fp64) of row t+1 while the others search frame t
+    for (int t = 0; t <= Tb; t++) {  // Tb + 1 barriers: before frame 0 and after every frame
+      if (t == Tb) {
+        __syncthreads();
+        break;
+      }
+      const float* x = xrow + (size_t)t * st_t;
+      if (t + 1 < Tb) {  // pull the row after this one towards L2
+        const char* nx = reinterpret_cast<const char*>(x + st_t);
+        for (int o = lane * 128; o < C * 4; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+      }
+      float mx = -INFINITY;
+      for (int c = lane; c < C; c += 32) mx = fmaxf(mx, __ldg(x + c));
+      mx = warp_max(mx);
+      const double m = (double)mx;
+      double sum = 0.0;
+      for (int c = lane; c < C; c += 32) sum += exp((double)__ldg(x + c) - m);
+      sum = warp_sum(sum);
+      const double lse = log(sum);
+      double* lp = s_lp2 + (t & 1) * C;
+      for (int c = lane; c < C; c += 32) lp[c] = ((double)__ldg(x + c) - m) - lse;
+      if (lane == 0) s_redd[40 + (t & 1)] = -lse;
+      __syncthreads();  // row t is ready (and the search of frame t-1 is over)
+    }
+    return;
+  }
+
+  // tuning hook (nasr_debug_profile): thread 0 of CTA 0 accumulates the cycles of each phase of the frame loop
+  long long tk = 0;  // the accumulators live in s_redu[32..39]
+  const bool profiling = prof != nullptr && blockIdx.x == 0 && tid == 0;
+#define BEAM_TICK(k)                    \
+  if (profiling) {                      \
+    const long long now_ = clock64();   \
+    s_redu[32 + k] += (u64)(now_ - tk); \
+    tk = now_;                          \
+  }
+  __syncthreads();  // row 0 ready, root entry written
   int n = 1, cur = 0;
   for (int t = 0; t < Tb; t++) {
+    if (profiling) tk = clock64();
     const int ao = cur * W, no = (cur ^ 1) * W;  // offsets of the active and of the next beam buffer
-    // next frame's row: in flight while this frame is searched
-    float xr[kPrefetch];
-    const bool pre = (t + 1 < Tb) && C <= kPrefetch * kBeamThreads;
-    if (pre) {
-      const float* xn = xrow + (size_t)(t + 1) * st_t;
-#pragma unroll
-      for (int k = 0; k < kPrefetch; k++) {
-        const int c = tid + k * kBeamThreads;
-        xr[k] = c < C ? __ldg(xn + c) : 0.f;
+    const double* lp = s_lp2 + (t & 1) * C;
+    const double lpmax = s_redd[40 + (t & 1)];
+    // ---- 1. active prefixes keep themselves; worst kept score and best old score by warp
+    {
+      double ut = ninf, pt_old = ninf;
+      if (tid < n) {
+        const int e = tid;
+        double nl = ninf;
+        const int last = g_last[ao + e];
+        pt_old = g_pt[ao + e];
+        if (g_len[ao + e] > 0) {
+          nl = g_pl[ao + e];
+          const int ps = g_pslot[ao + e];
+          if (ps >= 0) nl = lse2(nl, last == g_plast[ao + e] ? g_pb[ao + ps] : g_pt[ao + ps]);
+          nl += lp[last];
+        }
+        const double nb = pt_old + lp[blank];
+        ut = lse2(nb, nl);
+        s_ub[e] = nb;
+        s_ul[e] = nl;
+        s_ut[e] = ut;
+        s_newslot[e] = -1;
       }
-    }
-    // ---- 1. log-softmax of the row (fp64)
-    float mloc = -INFINITY;
-    for (int c = tid; c < C; c += kBeamThreads) mloc = fmaxf(mloc, s_xs[c]);
-    mloc = warp_max(mloc);
-    if (lane == 0) s_redd[warp] = (double)mloc;
-    __syncthreads();
-    double m = s_redd[0];
+      if (warp * 32 < n) {
+        const unsigned okb = __ballot_sync(0xffffffffu, ut > ninf);
+        double mn = ut > ninf ? ut : __longlong_as_double(0x7ff0000000000000ll), mxo = pt_old;
 #pragma unroll
-    for (int w = 1; w < kBeamWarps; w++) m = fmax(m, s_redd[w]);
-    double sloc = 0.0;
-    for (int c = tid; c < C; c += kBeamThreads) sloc += exp((double)s_xs[c] - m);
-    sloc = warp_sum(sloc);
-    if (lane == 0) s_redd[16 + warp] = sloc;
-    __syncthreads();
-    double ssum = 0.0;
-#pragma unroll
-    for (int w = 0; w < kBeamWarps; w++) ssum += s_redd[16 + w];
-    const double lse = log(ssum);
-    for (int c = tid; c < C; c += kBeamThreads) s_lp[c] = ((double)s_xs[c] - m) - lse;
-    const double lpmax = -lse;
-    __syncthreads();
-    // ---- 2. active prefixes keep themselves
-    for (int e = tid; e < n; e += kBeamThreads) {
-      double nl = ninf;
-      const int last = g_last[ao + e];
-      if (g_len[ao + e] > 0) {
-        nl = g_pl[ao + e];
-        const int ps = g_pslot[ao + e];
-        if (ps >= 0) nl = lse2(nl, last == g_plast[ao + e] ? g_pb[ao + ps] : g_pt[ao + ps]);
-        nl += s_lp[last];
-      }
-      const double nb = g_pt[ao + e] + s_lp[blank];
-      s_ub[e] = nb;
-      s_ul[e] = nl;
-      s_ut[e] = lse2(nb, nl);
-    }
-    __syncthreads();
-    // ---- is the beam full, what is its worst kept score, which prefixes can still place an extension
-    if (warp == 0) {
-      int cntv = 0;
-      double mn = __longlong_as_double(0x7ff0000000000000ll);
-      for (int e = lane; e < n; e += 32) {
-        const double v = s_ut[e];
-        if (v > ninf) {
-          cntv++;
-          mn = fmin(mn, v);
+        for (int o = 16; o > 0; o >>= 1) {
+          mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+          mxo = fmax(mxo, __shfl_xor_sync(0xffffffffu, mxo, o));
+        }
+        if (lane == 0) {
+          s_redi[warp] = __popc(okb);
+          s_redd[warp] = mn;
+          s_redd[16 + warp] = mxo;
         }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        cntv += __shfl_xor_sync(0xffffffffu, cntv, o);
-        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      for (int i = tid; i < TS; i += kSearchThreads) s_tab_key[i] = 0;
+      if (tid == 0) {
+        s_redi[20] = 0;
+        s_redi[22] = 0;
+        s_redi[23] = 0;
       }
-      const double tau0 = cntv >= W ? mn : ninf;
-      int nl = 0;
-      for (int e0 = 0; e0 < n; e0 += 32) {
-        const int e = e0 + lane;
+    }
+    bar_search();
+    BEAM_TICK(0);
+    // ---- 2. is the beam full (then only scores above its worst kept one matter); live prefixes and labels
+    double tau0;
+    {
+      int cntv = 0;
+      double mn = __longlong_as_double(0x7ff0000000000000ll), ptmax = ninf;
+      for (int w = 0; w * 32 < n; w++) {
+        cntv += s_redi[w];
+        mn = fmin(mn, s_redd[w]);
+        ptmax = fmax(ptmax, s_redd[16 + w]);
+      }
+      tau0 = cntv >= W ? mn : ninf;
+      if (warp * 32 < n) {
         bool lv = false;
-        if (e < n) {
-          const double pt = g_pt[ao + e];
-          lv = pt > ninf && (pt + lpmax > tau0);
+        if (tid < n) {
+          const double pt = g_pt[ao + tid];
+          lv = pt > ninf && pt + lpmax > tau0;
         }
         const unsigned bal = __ballot_sync(0xffffffffu, lv);
-        if (lv) s_live[nl + __popc(bal & ((1u << lane) - 1u))] = e;
-        nl += __popc(bal);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&s_redi[22], __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lv) s_liveP[base + __popc(bal & ((1u << lane) - 1u))] = tid;
       }
-      if (lane == 0) {
-        s_redi[22] = nl;
-        s_redi[20] = 0;
-        s_redd[32] = tau0;
+      for (int c0 = warp * 32; c0 < C; c0 += kSearchThreads) {
+        const int cc = c0 + lane;
+        const bool lv = cc < C && cc != blank && lp[cc] + ptmax > tau0;
+        const unsigned bal = __ballot_sync(0xffffffffu, lv);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&s_redi[23], __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lv) s_liveL[base + __popc(bal & ((1u << lane) - 1u))] = cc;
       }
     }
-    __syncthreads();
+    bar_search();
+    BEAM_TICK(1);
     Ctx c;
-    c.lp = s_lp; c.pb = g_pb + ao; c.pt = g_pt + ao; c.ut = s_ut; c.hash = g_hash + ao; c.last = g_last + ao;
-    c.live = s_live; c.mask = s_mask; c.n = n; c.C = C; c.CW = CW; c.blank = blank; c.divM = divM;
-    c.tau0 = s_redd[32];
-    const int nitems = n + s_redi[22] * C;
-    // ---- 3. the candidates' scores, how many they are, and their range
-    u64 key[IPT > 0 ? IPT : 1];
+    c.lp = lp; c.pb = g_pb + ao; c.pt = g_pt + ao; c.ut = s_ut; c.hash = g_hash + ao; c.last = g_last + ao;
+    c.liveP = s_liveP; c.liveL = s_liveL; c.mask = s_mask; c.n = n; c.nL = s_redi[23]; c.CW = CW;
+    c.divM = c.nL >= 2 ? 0xffffffffu / (unsigned)c.nL + 1u : 0u;
+    c.tau0 = tau0;
+    const int nitems = n + s_redi[22] * c.nL;
+    const bool cached = nitems <= kIPT * kSearchThreads;  // else: recompute the candidates in every pass
+    // ---- 3. the candidates' keys, how many they are, and their range
+    u64 key[kIPT];
     int cnt = 0;
     u64 kmin = ~0ull, kmax = 0;
-    if (IPT > 0) {
+    if (cached) {
 #pragma unroll
-      for (int r = 0; r < IPT; r++) {
-        const int i = tid + r * kBeamThreads;
-        double v;
-        int b, l;
+      for (int r = 0; r < kIPT; r++) {
         key[r] = 0;
-        if (i < nitems && eval_item(c, i, v, b, l)) key[r] = okey(v);
-        if (key[r]) {
-          cnt++;
-          kmin = key[r] < kmin ? key[r] : kmin;
-          kmax = key[r] > kmax ? key[r] : kmax;
+        if (r * kSearchThreads < nitems) {
+          const int i = tid + r * kSearchThreads;
+          if (i < nitems) key[r] = eval_key(c, i);
+          if (key[r]) {
+            cnt++;
+            kmin = key[r] < kmin ? key[r] : kmin;
+            kmax = key[r] > kmax ? key[r] : kmax;
+          }
         }
       }
     } else {
-      for (int i = tid; i < nitems; i += kBeamThreads) {
-        double v;
-        int b, l;
-        if (eval_item(c, i, v, b, l)) {
-          const u64 k = okey(v);
+      for (int i = tid; i < nitems; i += kSearchThreads) {
+        const u64 k = eval_key(c, i);
+        if (k) {
           cnt++;
           kmin = k < kmin ? k : kmin;
           kmax = k > kmax ? k : kmax;
@@ -381,18 +442,20 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
       s_redu[warp] = kmin;
       s_redu[16 + warp] = kmax;
     }
-    __syncthreads();
-    cnt = 0;
-    kmin = ~0ull;
-    kmax = 0;
+    bar_search();
+    cnt = s_redi[lane & 15];
+    kmin = s_redu[lane & 15];
+    kmax = s_redu[16 + (lane & 15)];
 #pragma unroll
-    for (int w = 0; w < kBeamWarps; w++) {
-      cnt += s_redi[w];
-      kmin = s_redu[w] < kmin ? s_redu[w] : kmin;
-      kmax = s_redu[16 + w] > kmax ? s_redu[16 + w] : kmax;
+    for (int o = 8; o > 0; o >>= 1) {
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      const u64 a = __shfl_xor_sync(0xffffffffu, kmin, o), z = __shfl_xor_sync(0xffffffffu, kmax, o);
+      kmin = a < kmin ? a : kmin;
+      kmax = z > kmax ? z : kmax;
     }
+    BEAM_TICK(2);
     // ---- 4. threshold of the best W: admit k >= F1, and among k == F1 (tie_mode) those with k2 >= F2
-    u64 F1 = 0, F2 = 0;
+    u64 F1 = 1, F2 = 0;
     bool tie_mode = false;
     if (cnt > W) {
       int need = W;
@@ -406,23 +469,19 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
         for (;;) {
           const int width = min(11, top), shift = top - width;
           const unsigned dmask = (1u << width) - 1u;
-          if (IPT > 0) {
+          if (cached) {
 #pragma unroll
-            for (int r = 0; r < IPT; r++) {
+            for (int r = 0; r < kIPT; r++) {
               const u64 k = key[r];
               if (k && (top >= 64 || ((k ^ prefix) >> top) == 0)) atomicAdd(&s_hist[(int)((k >> shift) & dmask)], 1);
             }
           } else {
-            for (int i = tid; i < nitems; i += kBeamThreads) {
-              double v;
-              int b, l;
-              if (eval_item(c, i, v, b, l)) {
-                const u64 k = okey(v);
-                if (top >= 64 || ((k ^ prefix) >> top) == 0) atomicAdd(&s_hist[(int)((k >> shift) & dmask)], 1);
-              }
+            for (int i = tid; i < nitems; i += kSearchThreads) {
+              const u64 k = eval_key(c, i);
+              if (k && (top >= 64 || ((k ^ prefix) >> top) == 0)) atomicAdd(&s_hist[(int)((k >> shift) & dmask)], 1);
             }
           }
-          __syncthreads();
+          bar_search();
           find_bin(s_hist, 1 << width, need, s_redi + 32, s_redi + 16, tid);
           need -= s_redi[17];
           prefix = (prefix & ~((u64)dmask << shift)) | ((u64)s_redi[16] << shift);
@@ -445,24 +504,23 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
         for (;;) {
           const int width = min(11, top), shift = top - width;
           const unsigned dmask = (1u << width) - 1u;
+          if (cached) {
 #pragma unroll
-          for (int r = 0; r < (IPT > 0 ? IPT : (nitems + kBeamThreads - 1) / kBeamThreads); r++) {
-            const int i = tid + r * kBeamThreads;
-            if (i >= nitems) break;
-            double v;
-            int b, l;
-            u64 k1;
-            if (IPT > 0) {
-              k1 = key[r];  // r is a compile-time index after unrolling only when IPT > 0
-              if (k1 != F1) continue;
-              item_of(c, i, b, l);
-            } else {
-              if (!eval_item(c, i, v, b, l) || okey(v) != F1) continue;
+            for (int r = 0; r < kIPT; r++) {
+              if (key[r] == F1) {
+                const u64 k = item_k2(c, tid + r * kSearchThreads);
+                if (top >= 64 || ((k ^ prefix) >> top) == 0) atomicAdd(&s_hist[(int)((k >> shift) & dmask)], 1);
+              }
             }
-            const u64 k = item_k2(c, b, l);
-            if (top >= 64 || ((k ^ prefix) >> top) == 0) atomicAdd(&s_hist[(int)((k >> shift) & dmask)], 1);
+          } else {
+            for (int i = tid; i < nitems; i += kSearchThreads) {
+              if (eval_key(c, i) == F1) {
+                const u64 k = item_k2(c, i);
+                if (top >= 64 || ((k ^ prefix) >> top) == 0) atomicAdd(&s_hist[(int)((k >> shift) & dmask)], 1);
+              }
+            }
           }
-          __syncthreads();
+          bar_search();
           find_bin(s_hist, 1 << width, need, s_redi + 32, s_redi + 16, tid);
           need -= s_redi[17];
           prefix = (prefix & ~((u64)dmask << shift)) | ((u64)s_redi[16] << shift);
@@ -474,29 +532,45 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
         }
       }
     }
-    // ---- 5. survivors into the other buffer
+    BEAM_TICK(3);
+    // ---- 5. the admitted candidates, as a list
+    if (cached) {
 #pragma unroll
-    for (int r = 0; r < (IPT > 0 ? IPT : (nitems + kBeamThreads - 1) / kBeamThreads); r++) {
-      const int i = tid + r * kBeamThreads;
-      if (i >= nitems) break;
-      double v;
-      int b, l;
-      u64 k;
-      if (IPT > 0) {
-        k = key[r];
-        if (k == 0 || k < F1) continue;
-        item_of(c, i, b, l);
-        const long long bits = (long long)k;  // invert okey
-        v = __longlong_as_double(bits < 0 ? (bits ^ (long long)0x8000000000000000ull) : ~bits);
-      } else {
-        if (!eval_item(c, i, v, b, l)) continue;
-        k = okey(v);
-        if (k < F1) continue;
+      for (int r = 0; r < kIPT; r++) {
+        const u64 k = key[r];
+        if (k >= F1) {
+          const int i = tid + r * kSearchThreads;
+          if (!(tie_mode && k == F1 && item_k2(c, i) < F2)) {
+            const int slot = atomicAdd(&s_redi[20], 1);
+            if (slot < W) {  // beyond W only through a hash collision among exact ties
+              s_adm_i[slot] = i;
+              s_adm_k[slot] = k;
+            }
+          }
+        }
       }
-      if (tie_mode && k == F1 && item_k2(c, b, l) < F2) continue;
-      const int slot = atomicAdd(&s_redi[20], 1);
-      if (slot >= W) continue;  // only reachable through a hash collision among exact ties
-      const int d = no + slot, a = ao + b;
+    } else {
+      for (int i = tid; i < nitems; i += kSearchThreads) {
+        const u64 k = eval_key(c, i);
+        if (k >= F1 && !(tie_mode && k == F1 && item_k2(c, i) < F2)) {
+          const int slot = atomicAdd(&s_redi[20], 1);
+          if (slot < W) {
+            s_adm_i[slot] = i;
+            s_adm_k[slot] = k;
+          }
+        }
+      }
+    }
+    bar_search();
+    BEAM_TICK(4);
+    // ---- 6. one thread per admitted candidate builds its entry of the next beam
+    const int n_new = min(s_redi[20], W);
+    bool orphan = false;
+    if (tid < n_new) {
+      int b, l;
+      item_of(c, s_adm_i[tid], b, l);
+      const double v = okey_inv(s_adm_k[tid]);
+      const int d = no + tid, a = ao + b;
       if (l < 0) {
         g_pb[d] = s_ub[b];
         g_pl[d] = s_ul[b];
@@ -507,60 +581,74 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
         g_len[d] = g_len[a];
         g_last[d] = g_last[a];
         g_plast[d] = g_plast[a];
+        const int po = g_pslot[a];  // the parent's slot in the active beam; mapped to the next beam below
+        g_pslot[d] = po;
+        orphan = po < 0 && g_len[a] > 0;
+        s_newslot[b] = tid;
       } else {
         const int id = atomicAdd(&s_redi[21], 1);
         nodes[id] = make_int2(g_node[a], l);
+        const u64 h = child_hash(g_hash[a], l);
         g_pb[d] = ninf;
         g_pl[d] = v;
         g_pt[d] = v;
-        g_hash[d] = child_hash(g_hash[a], l);
+        g_hash[d] = h;
         g_phash[d] = g_hash[a];
         g_node[d] = id;
         g_len[d] = g_len[a] + 1;
         g_last[d] = l;
         g_plast[d] = g_last[a];
+        g_pslot[d] = b;
+        // a prefix that enters the beam may be the parent of prefixes that stayed in it without it
+        unsigned idx = (unsigned)h & (unsigned)(TS - 1);
+        for (;;) {
+          const u64 old = atomicCAS(&s_tab_key[idx], 0ull, h);
+          if (old == 0ull || old == h) {
+            s_tab_slot[idx] = tid;
+            break;
+          }
+          idx = (idx + 1) & (unsigned)(TS - 1);
+        }
       }
+      for (int w = 0; w < CW; w++) s_mask[tid * CW + w] = 0;
     }
-    __syncthreads();
-    const int n_new = min(s_redi[20], W);
-    // ---- 6. parents' slots, then the per-parent sets of active extensions
-    for (int i = tid; i < n_new * CW; i += kBeamThreads) s_mask[i] = 0;
-    for (int e0 = 0; e0 < n_new; e0 += kBeamThreads / 4) {  // warp-uniform trip count: the shuffles need every lane
-      const int e = e0 + (tid >> 2);
-      int ps = -1, ln = -1;
-      if (e < n_new) {
-        const u64 ph = g_phash[no + e];
-        ln = g_len[no + e] - 1;
-        for (int j = tid & 3; j < n_new; j += 4)
-          if (g_hash[no + j] == ph && g_len[no + j] == ln) ps = j;
+    bar_search();
+    BEAM_TICK(5);
+    // ---- 7. parents' slots in the next beam, then the per-parent sets of active extensions
+    if (tid < n_new) {
+      const int d = no + tid;
+      int ps = g_pslot[d];
+      if (ps >= 0) {
+        ps = s_newslot[ps];
+      } else if (orphan) {
+        const u64 ph = g_phash[d];
+        const int ln = g_len[d] - 1;
+        unsigned idx = (unsigned)ph & (unsigned)(TS - 1);
+        for (;;) {
+          const u64 k = s_tab_key[idx];
+          if (k == 0ull) break;
+          if (k == ph && g_len[no + s_tab_slot[idx]] == ln) {
+            ps = s_tab_slot[idx];
+            break;
+          }
+          idx = (idx + 1) & (unsigned)(TS - 1);
+        }
       }
-      ps = max(ps, __shfl_xor_sync(0xffffffffu, ps, 1));
-      ps = max(ps, __shfl_xor_sync(0xffffffffu, ps, 2));
-      if (e < n_new && (tid & 3) == 0) g_pslot[no + e] = ln >= 0 ? ps : -1;
+      g_pslot[d] = ps;
+      if (ps >= 0) atomicOr(&s_mask[ps * CW + (g_last[d] >> 5)], 1u << (g_last[d] & 31));
     }
-    if (pre) {
-#pragma unroll
-      for (int k = 0; k < kPrefetch; k++) {
-        const int cc = tid + k * kBeamThreads;
-        if (cc < C) s_xs[cc] = xr[k];
-      }
-    } else if (t + 1 < Tb) {
-      const float* xn = xrow + (size_t)(t + 1) * st_t;
-      for (int cc = tid; cc < C; cc += kBeamThreads) s_xs[cc] = __ldg(xn + cc);
-    }
-    __syncthreads();
-    for (int e = tid; e < n_new; e += kBeamThreads) {
-      const int ps = g_pslot[no + e];
-      if (ps >= 0) atomicOr(&s_mask[ps * CW + (g_last[no + e] >> 5)], 1u << (g_last[no + e] & 31));
-    }
-    __syncthreads();
+    BEAM_TICK(6);
+    __syncthreads();  // frame over; the producer warp has row t+1 ready
     n = n_new;
     cur ^= 1;
   }
+  if (profiling)
+    for (int k = 0; k < 8; k++) prof[k] = (long long)s_redu[32 + k];
+#undef BEAM_TICK
 
-  // ---- read the best P prefixes back through the trie
+  // ---- read the best P prefixes back through the trie (search warps only from here on)
   const int ao = cur * W;
-  for (int e = tid; e < n; e += kBeamThreads) {
+  for (int e = tid; e < n; e += kSearchThreads) {
     const double v = g_pt[ao + e];
     const u64 h = g_hash[ao + e];
     int r = 0;
@@ -578,17 +666,17 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
         row[pos] = nd.y;
         id = nd.x;
       }
-      s_live[r] = len;  // s_live is free now (P <= W)
+      s_liveP[r] = len;  // s_liveP is free now (P <= W)
       log_prob[(size_t)b_utt * P + r] = (float)v;
     }
   }
-  for (int r = n + tid; r < P; r += kBeamThreads) {
-    s_live[r] = 0;
+  for (int r = n + tid; r < P; r += kSearchThreads) {
+    s_liveP[r] = 0;
     log_prob[(size_t)b_utt * P + r] = -INFINITY;
   }
-  __syncthreads();
-  for (int r = warp; r < P; r += kBeamWarps) {
-    const int len = s_live[r];
+  bar_search();
+  for (int r = warp; r < P; r += kSearchWarps) {
+    const int len = s_liveP[r];
     int64_t* row = hyp + ((size_t)b_utt * P + r) * T;
     int out = len;
     if (merge_repeated) {
@@ -635,27 +723,15 @@ int ctc_beam_search(const float* logits, int T, int B, int C, long long st_t, lo
     return NASR_ERR_WORKSPACE_TOO_SMALL;
   }
   const size_t smem = beam_smem_bytes(W, C);
-  if (W > 1024 || C > 8192 || (size_t)W * C >= ((size_t)1 << 20) || smem > 200 * 1024) {
-    set_error("ctc_beam_search: beam_width=%d with C=%d is not supported (needs %zu bytes of shared memory)", W, C,
-              smem);
+  if (W > kSearchThreads || C > 4095 || (size_t)W * C >= ((size_t)1 << 20) || smem > 200 * 1024) {
+    set_error("ctc_beam_search: beam_width=%d with C=%d is not supported (beam_width <= %d, C <= 4095, %zu bytes of "
+              "shared memory needed, 204800 available)", W, C, kSearchThreads, smem);
     return NASR_ERR_UNSUPPORTED;
   }
+  NASR_CUDA(cudaFuncSetAttribute(ctc_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   int2* nodes = reinterpret_cast<int2*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-  const u64 divM = (((u64)1 << 40) / (u64)C) + 1;
-  const size_t cand = (size_t)W * ((size_t)C + 1);  // most candidates a frame can have
-#define NASR_BEAM_LAUNCH(IPT)                                                                                     \
-  do {                                                                                                            \
-    NASR_CUDA(cudaFuncSetAttribute(ctc_beam_kernel<IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-    ctc_beam_kernel<IPT><<<B, kBeamThreads, smem, stream>>>(logits, T, B, C, st_t, st_b, seq_len, blank, W, P,    \
-                                                            merge_repeated, hyp, hyp_len, log_prob, nodes, divM); \
-  } while (0)
-  if (cand <= 8 * (size_t)kBeamThreads)
-    NASR_BEAM_LAUNCH(8);
-  else if (cand <= 16 * (size_t)kBeamThreads)
-    NASR_BEAM_LAUNCH(16);
-  else
-    NASR_BEAM_LAUNCH(0);
-#undef NASR_BEAM_LAUNCH
+  ctc_beam_kernel<<<B, kBeamThreads, smem, stream>>>(logits, T, B, C, st_t, st_b, seq_len, blank, W, P,
+                                                     merge_repeated, hyp, hyp_len, log_prob, nodes, g_debug_prof);
   count_launch();
   NASR_CUDA(cudaGetLastError());
   return NASR_OK;

@@ -44,3 +44,28 @@ if __name__ == "__main__":
     bench("peaky wide", peaky(800, 128, 1024))
     g = torch.Generator(device="cuda").manual_seed(1)
     bench("random*3 wide", torch.randn((200, 128, 1024), device="cuda", generator=g) * 3)
+
+
+def phases(name, x, W=100):
+    """Cycles per frame of each phase of the frame loop (CTA 0), through nasr_debug_profile."""
+    import ctypes
+    from neuralasr_b200 import _lib
+    lib = _lib.load()
+    T, B, C = x.shape
+    buf = torch.zeros(B * 16 * 4 + 4 * 200 * 8 * 2, dtype=torch.int64, device="cuda")
+    lib.nasr_debug_profile(ctypes.c_void_p(buf.data_ptr()))
+    common.beam_decoding(x, np.full(B, T, np.int32), beam_width=W)
+    torch.cuda.synchronize()
+    lib.nasr_debug_profile(None)
+    ph = buf[:8].cpu().numpy() / T
+    names = ["softmax", "update", "live", "eval", "select", "admit", "parents"]
+    print("%-20s cycles/frame: " % name + "  ".join("%s %.0f" % (k, v) for k, v in zip(names, ph)) +
+          "  total %.0f" % ph.sum(), flush=True)
+
+
+if __name__ == "__main__":
+    g = torch.Generator(device="cuda").manual_seed(1)
+    phases("random*3 B=64", torch.randn((800, 64, 38), device="cuda", generator=g) * 3)
+    phases("peaky B=64", peaky(800, 64, 38))
+    phases("peaky B=256", peaky(1000, 256, 38))
+    phases("peaky wide", peaky(200, 128, 1024))
