@@ -289,6 +289,31 @@ def run_ours(args, w, rank, world, local_rank):
         torch.cuda.synchronize()
         dec_ms = a.elapsed_time(b) / 10
 
+    # ---- beam search decode (what create_model runs today, tfnetwork.py:62: width 100, top path) + LER ----
+    beam = None
+    if rank == 0:
+        for _ in range(2):
+            dm, _ = common.create_model_beam(logits[0], seq_d)
+            common.edit_distance(dm, lab)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(5):
+            dm, _ = common.create_model_beam(logits[i % nsets], seq_d)
+            common.edit_distance(dm, lab)
+        b.record()
+        torch.cuda.synchronize()
+        beam_ms = a.elapsed_time(b) / 5
+        from oracle import c_oracle
+        n_utt = min(B, 2 * c_oracle.num_threads())       # bounded CPU sample: two utterances per host thread
+        t0 = time.perf_counter()
+        c_oracle.beam_search(x[:, :n_utt], seq[:n_utt], 100, 1, True)
+        cpu_s = time.perf_counter() - t0
+        beam = {"beam_width": 100, "top_paths": 1, "ms_per_batch": beam_ms, "frames_per_s": frames / (beam_ms * 1e-3),
+                "includes": "beam search kernel + label error rate kernel",
+                "cpu_port": {"frames_per_s": float(seq[:n_utt].sum()) / cpu_s, "cores": c_oracle.num_threads(),
+                             "sample": "%d utterances of the same batch, oracle/beam_oracle.c" % n_utt}}
+
     if rank == 0:
         peak, peak_kind = hbm_peak()
         k_ms = statistics.mean(kern_ms)
@@ -322,6 +347,7 @@ def run_ours(args, w, rank, world, local_rank):
             "gpu_launches": launches,
             "clocks": clocks,
             "decode_ler_ms": dec_ms,
+            "beam_search": beam,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -35,10 +35,13 @@ namespace {
 
 typedef unsigned long long u64;
 
-constexpr int kSearchThreads = 512;                 // the warps that search
+#ifndef NASR_BEAM_SEARCH_THREADS
+#define NASR_BEAM_SEARCH_THREADS 512
+#endif
+constexpr int kSearchThreads = NASR_BEAM_SEARCH_THREADS;  // the warps that search (a power of two, 128..512)
 constexpr int kSearchWarps = kSearchThreads / 32;
 constexpr int kBeamThreads = kSearchThreads + 32;   // + one warp that prepares the next frame's log-softmax
-constexpr int kIPT = 8;                             // candidate keys a search thread keeps in registers
+constexpr int kIPT = 4096 / kSearchThreads;         // candidate keys a search thread keeps in registers
 constexpr int kBins = 2048;                         // 11-bit digits
 constexpr int kBinsPerThread = kBins / kSearchThreads;
 constexpr u64 kRootHash = 0x243f6a8885a308d3ull;
@@ -85,26 +88,52 @@ __host__ __device__ inline int tab_size(int W) {
   return s;
 }
 
-__host__ __device__ inline size_t beam_smem_bytes(int W, int C) {
-  const int CW = (C + 31) / 32;
-  size_t s = 0;
-  s += al16(sizeof(double) * 2 * C);
-  s += 3 * al16(sizeof(double) * 2 * W) + 2 * al16(sizeof(u64) * 2 * W) + 5 * al16(sizeof(int) * 2 * W);
-  s += 3 * al16(sizeof(double) * W);
-  s += 3 * al16(sizeof(int) * W) + al16(sizeof(int) * C);
-  s += al16(sizeof(u64) * W);
-  s += al16(sizeof(u64) * tab_size(W)) + al16(sizeof(int) * tab_size(W));
-  s += al16(sizeof(uint32_t) * (size_t)W * CW);
-  s += al16(sizeof(int) * kBins);
-  s += al16(sizeof(double) * 64) + al16(sizeof(u64) * 64) + al16(sizeof(int) * 64);
-  return s;
-}
+// Shared-memory layout, computed once on the host and handed to the kernel as a __grid_constant__ parameter:
+// every array base is then a constant-bank operand instead of arithmetic on W and C redone inside the frame loop.
+struct BeamLayout {
+  int lp2, pb, pl, pt, hash, phash, node, len, last, plast, pslot, ub, ul, ut, liveP, newslot, adm_i, liveL, adm_k,
+      tab_key, tab_slot, mask, hist, redd, redu, redi;
+  int total, TS, CW;
+};
 
-template <typename T>
-__device__ __forceinline__ T* carve(char*& p, size_t n) {
-  T* r = reinterpret_cast<T*>(p);
-  p += al16(n * sizeof(T));
-  return r;
+inline BeamLayout beam_layout(int W, int C) {
+  BeamLayout L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    const size_t r = o;
+    o += al16(bytes);
+    return (int)r;
+  };
+  L.CW = (C + 31) / 32;
+  L.TS = tab_size(W);
+  L.lp2 = take(sizeof(double) * 2 * C);
+  L.pb = take(sizeof(double) * 2 * W);
+  L.pl = take(sizeof(double) * 2 * W);
+  L.pt = take(sizeof(double) * 2 * W);
+  L.hash = take(sizeof(u64) * 2 * W);
+  L.phash = take(sizeof(u64) * 2 * W);
+  L.node = take(sizeof(int) * 2 * W);
+  L.len = take(sizeof(int) * 2 * W);
+  L.last = take(sizeof(int) * 2 * W);
+  L.plast = take(sizeof(int) * 2 * W);
+  L.pslot = take(sizeof(int) * 2 * W);
+  L.ub = take(sizeof(double) * W);
+  L.ul = take(sizeof(double) * W);
+  L.ut = take(sizeof(double) * W);
+  L.liveP = take(sizeof(int) * W);
+  L.newslot = take(sizeof(int) * W);
+  L.adm_i = take(sizeof(int) * W);
+  L.liveL = take(sizeof(int) * C);
+  L.adm_k = take(sizeof(u64) * W);
+  L.tab_key = take(sizeof(u64) * L.TS);
+  L.tab_slot = take(sizeof(int) * L.TS);
+  L.mask = take(sizeof(uint32_t) * (size_t)W * L.CW);
+  L.hist = take(sizeof(int) * kBins);
+  L.redd = take(sizeof(double) * 64);
+  L.redu = take(sizeof(u64) * 64);
+  L.redi = take(sizeof(int) * 64);
+  L.total = (int)o;
+  return L;
 }
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
@@ -186,7 +215,11 @@ __device__ __forceinline__ void find_bin(int* hist, int nb, int need, int* wsum,
   int incl = warp_incl_scan(sum, lane);
   if (lane == 31) wsum[warp] = incl;
   bar_search();
-  for (int w = 0; w < warp; w++) incl += wsum[w];
+  {  // + the totals of the warps before this one
+    const int ws = warp_incl_scan(lane < kSearchWarps ? wsum[lane] : 0, lane);
+    const int before = __shfl_sync(0xffffffffu, ws, (warp + 31) & 31);
+    if (warp) incl += before;
+  }
   const int excl = incl - sum;
   if (excl < need && need <= incl) {
     int cum = excl;
@@ -208,46 +241,47 @@ __global__ void __launch_bounds__(kBeamThreads, 2)
 ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long st_t, long long st_b,
                 const int32_t* __restrict__ seq_len, int blank, int W, int P, int merge_repeated,
                 int64_t* hyp, int32_t* __restrict__ hyp_len, float* __restrict__ log_prob,
-                int2* nodes_all, long long* prof) {
+                int2* nodes_all, long long* prof, const __grid_constant__ BeamLayout L) {
   extern __shared__ __align__(16) char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b_utt = blockIdx.x;
-  const int CW = (C + 31) / 32;
-  const int TS = tab_size(W);
+  const int CW = L.CW, TS = L.TS;
   const double ninf = neg_inf();
 
-  char* sp = smem_raw;
-  double* s_lp2 = carve<double>(sp, 2 * C);  // log-softmax rows of frame t (t&1) and t+1
+#define BEAM_ARR(T, name, field) T* const name = reinterpret_cast<T*>(smem_raw + L.field)
+  BEAM_ARR(double, s_lp2, lp2);       // log-softmax rows of frame t (t&1) and t+1
   // the two beam buffers are the halves [0,W) and [W,2W) of each array
-  double* g_pb = carve<double>(sp, 2 * W);   // log P(prefix, ends in blank)
-  double* g_pl = carve<double>(sp, 2 * W);   //                ends in its last label
-  double* g_pt = carve<double>(sp, 2 * W);   //                either
-  u64* g_hash = carve<u64>(sp, 2 * W);       // prefix identity
-  u64* g_phash = carve<u64>(sp, 2 * W);      // parent prefix identity
-  int* g_node = carve<int>(sp, 2 * W);
-  int* g_len = carve<int>(sp, 2 * W);
-  int* g_last = carve<int>(sp, 2 * W);
-  int* g_plast = carve<int>(sp, 2 * W);
-  int* g_pslot = carve<int>(sp, 2 * W);
-  double* s_ub = carve<double>(sp, W);       // this frame's update of the active prefixes
-  double* s_ul = carve<double>(sp, W);
-  double* s_ut = carve<double>(sp, W);
-  int* s_liveP = carve<int>(sp, W);          // prefixes whose extensions can still enter the beam
-  int* s_newslot = carve<int>(sp, W);        // active prefix -> its slot in the next beam (-1: dropped)
-  int* s_adm_i = carve<int>(sp, W);          // admitted candidates (item index, key)
-  int* s_liveL = carve<int>(sp, C);          // labels whose extension of the best prefix could enter
-  u64* s_adm_k = carve<u64>(sp, W);
-  u64* s_tab_key = carve<u64>(sp, TS);       // hash -> slot of the prefixes that enter the beam this frame
-  int* s_tab_slot = carve<int>(sp, TS);
-  uint32_t* s_mask = carve<uint32_t>(sp, (size_t)W * CW);  // [W][CW] labels whose extension is already active
-  int* s_hist = carve<int>(sp, kBins);
-  double* s_redd = carve<double>(sp, 64);
-  u64* s_redu = carve<u64>(sp, 64);
-  int* s_redi = carve<int>(sp, 64);
-  // s_redi: [0..15] warp partials, [16..18] find_bin result, [20] admitted counter, [21] node counter,
+  BEAM_ARR(double, g_pb, pb);         // log P(prefix, ends in blank)
+  BEAM_ARR(double, g_pl, pl);         //                ends in its last label
+  BEAM_ARR(double, g_pt, pt);         //                either
+  BEAM_ARR(u64, g_hash, hash);        // prefix identity
+  BEAM_ARR(u64, g_phash, phash);      // parent prefix identity
+  BEAM_ARR(int, g_node, node);
+  BEAM_ARR(int, g_len, len);
+  BEAM_ARR(int, g_last, last);
+  BEAM_ARR(int, g_plast, plast);
+  BEAM_ARR(int, g_pslot, pslot);
+  BEAM_ARR(double, s_ub, ub);         // this frame's update of the active prefixes
+  BEAM_ARR(double, s_ul, ul);
+  BEAM_ARR(double, s_ut, ut);
+  BEAM_ARR(int, s_liveP, liveP);      // prefixes whose extensions can still enter the beam
+  BEAM_ARR(int, s_newslot, newslot);  // active prefix -> its slot in the next beam (-1: dropped)
+  BEAM_ARR(int, s_adm_i, adm_i);      // admitted candidates (item index, key)
+  BEAM_ARR(int, s_liveL, liveL);      // labels whose extension of the best prefix could enter
+  BEAM_ARR(u64, s_adm_k, adm_k);
+  BEAM_ARR(u64, s_tab_key, tab_key);  // hash -> slot of the prefixes that enter the beam this frame
+  BEAM_ARR(int, s_tab_slot, tab_slot);
+  BEAM_ARR(uint32_t, s_mask, mask);   // [W][CW] labels whose extension is already active
+  BEAM_ARR(int, s_hist, hist);
+  BEAM_ARR(double, s_redd, redd);
+  BEAM_ARR(u64, s_redu, redu);
+  BEAM_ARR(int, s_redi, redi);
+#undef BEAM_ARR
+  // s_redi: [0..15] warp partials, [16..18] find_bin result, [20] admitted counter,
   //         [22] live prefixes, [23] live labels, [32..47] find_bin warp sums
-  // s_redd: [0..15] min of the updated totals, [16..31] max of the old totals, [40..41] max of lp rows t&1
-  // s_redu: [0..15] kmin, [16..31] kmax, [32..39] profile accumulators
+  // s_redd: [0..15] min of the updated totals, [16..31] max of the old totals, [40..41] max of lp rows t&1,
+  //         [44..59] max of the updated totals
+  // s_redu: [32..39] profile accumulators
 
   int Tb = seq_len[b_utt];
   Tb = max(0, min(T, Tb));
@@ -267,7 +301,6 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
     g_last[0] = -1;
     g_plast[0] = -1;
     g_pslot[0] = -1;
-    s_redi[21] = 1;
     nodes[0] = make_int2(-1, -1);
     for (int k = 32; k < 40; k++) s_redu[k] = 0;
   }
@@ -321,17 +354,20 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
       double ut = ninf, pt_old = ninf;
       if (tid < n) {
         const int e = tid;
-        double nl = ninf;
         const int last = g_last[ao + e];
         pt_old = g_pt[ao + e];
+        double b1 = ninf, b2 = ninf;  // stay on the last label; arrive from the parent prefix
         if (g_len[ao + e] > 0) {
-          nl = g_pl[ao + e];
+          const double lpl = lp[last];
+          b1 = g_pl[ao + e] + lpl;
           const int ps = g_pslot[ao + e];
-          if (ps >= 0) nl = lse2(nl, last == g_plast[ao + e] ? g_pb[ao + ps] : g_pt[ao + ps]);
-          nl += lp[last];
+          if (ps >= 0) b2 = (last == g_plast[ao + e] ? g_pb[ao + ps] : g_pt[ao + ps]) + lpl;
         }
         const double nb = pt_old + lp[blank];
-        ut = lse2(nb, nl);
+        const double nl = lse2(b1, b2);
+        // total' as ONE three-way log-sum-exp, independent of nl's chain (oracle/beam_oracle.py does the same)
+        const double mm = fmax(nb, fmax(b1, b2));
+        ut = mm == ninf ? ninf : mm + log(exp(nb - mm) + exp(b1 - mm) + exp(b2 - mm));
         s_ub[e] = nb;
         s_ul[e] = nl;
         s_ut[e] = ut;
@@ -339,16 +375,18 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
       }
       if (warp * 32 < n) {
         const unsigned okb = __ballot_sync(0xffffffffu, ut > ninf);
-        double mn = ut > ninf ? ut : __longlong_as_double(0x7ff0000000000000ll), mxo = pt_old;
+        double mn = ut > ninf ? ut : __longlong_as_double(0x7ff0000000000000ll), mxo = pt_old, mxu = ut;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
           mxo = fmax(mxo, __shfl_xor_sync(0xffffffffu, mxo, o));
+          mxu = fmax(mxu, __shfl_xor_sync(0xffffffffu, mxu, o));
         }
         if (lane == 0) {
           s_redi[warp] = __popc(okb);
           s_redd[warp] = mn;
           s_redd[16 + warp] = mxo;
+          s_redd[44 + warp] = mxu;
         }
       }
       for (int i = tid; i < TS; i += kSearchThreads) s_tab_key[i] = 0;
@@ -361,16 +399,21 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
     bar_search();
     BEAM_TICK(0);
     // ---- 2. is the beam full (then only scores above its worst kept one matter); live prefixes and labels
-    double tau0;
-    {
+    //         (only the warps that have a list to build combine the partials)
+    if (warp * 32 < n || warp * 32 < C) {
       int cntv = 0;
-      double mn = __longlong_as_double(0x7ff0000000000000ll), ptmax = ninf;
+      double mn = __longlong_as_double(0x7ff0000000000000ll), ptmax = ninf, utmax = ninf;
       for (int w = 0; w * 32 < n; w++) {
         cntv += s_redi[w];
         mn = fmin(mn, s_redd[w]);
         ptmax = fmax(ptmax, s_redd[16 + w]);
+        utmax = fmax(utmax, s_redd[44 + w]);
       }
-      tau0 = cntv >= W ? mn : ninf;
+      const double tau0 = cntv >= W ? mn : ninf;
+      if (tid == 0) {  // every candidate's score lies in (tau0, vtop] (kept prefixes: [tau0, vtop])
+        s_redd[32] = tau0;
+        s_redd[33] = fmax(utmax, ptmax + lpmax);
+      }
       if (warp * 32 < n) {
         bool lv = false;
         if (tid < n) {
@@ -399,13 +442,13 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
     c.lp = lp; c.pb = g_pb + ao; c.pt = g_pt + ao; c.ut = s_ut; c.hash = g_hash + ao; c.last = g_last + ao;
     c.liveP = s_liveP; c.liveL = s_liveL; c.mask = s_mask; c.n = n; c.nL = s_redi[23]; c.CW = CW;
     c.divM = c.nL >= 2 ? 0xffffffffu / (unsigned)c.nL + 1u : 0u;
-    c.tau0 = tau0;
+    c.tau0 = s_redd[32];
+    const double tau0 = c.tau0, vtop = s_redd[33];
     const int nitems = n + s_redi[22] * c.nL;
     const bool cached = nitems <= kIPT * kSearchThreads;  // else: recompute the candidates in every pass
-    // ---- 3. the candidates' keys, how many they are, and their range
+    // ---- 3. the candidates' keys and how many they are
     u64 key[kIPT];
     int cnt = 0;
-    u64 kmin = ~0ull, kmax = 0;
     if (cached) {
 #pragma unroll
       for (int r = 0; r < kIPT; r++) {
@@ -413,46 +456,21 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
         if (r * kSearchThreads < nitems) {
           const int i = tid + r * kSearchThreads;
           if (i < nitems) key[r] = eval_key(c, i);
-          if (key[r]) {
-            cnt++;
-            kmin = key[r] < kmin ? key[r] : kmin;
-            kmax = key[r] > kmax ? key[r] : kmax;
-          }
+          cnt += key[r] != 0;
         }
       }
     } else {
-      for (int i = tid; i < nitems; i += kSearchThreads) {
-        const u64 k = eval_key(c, i);
-        if (k) {
-          cnt++;
-          kmin = k < kmin ? k : kmin;
-          kmax = k > kmax ? k : kmax;
-        }
-      }
+      for (int i = tid; i < nitems; i += kSearchThreads) cnt += eval_key(c, i) != 0;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-      const u64 a = __shfl_xor_sync(0xffffffffu, kmin, o), z = __shfl_xor_sync(0xffffffffu, kmax, o);
-      kmin = a < kmin ? a : kmin;
-      kmax = z > kmax ? z : kmax;
-    }
-    if (lane == 0) {
-      s_redi[warp] = cnt;
-      s_redu[warp] = kmin;
-      s_redu[16 + warp] = kmax;
-    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) s_redi[warp] = cnt;
     bar_search();
-    cnt = s_redi[lane & 15];
-    kmin = s_redu[lane & 15];
-    kmax = s_redu[16 + (lane & 15)];
+    cnt = s_redi[lane & (kSearchWarps - 1)];
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-      const u64 a = __shfl_xor_sync(0xffffffffu, kmin, o), z = __shfl_xor_sync(0xffffffffu, kmax, o);
-      kmin = a < kmin ? a : kmin;
-      kmax = z > kmax ? z : kmax;
-    }
+    for (int o = kSearchWarps / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    // bounds of the keys, known without looking at them: (key of tau0 .. key of vtop]
+    const u64 kmax = okey(vtop), kmin = tau0 > ninf ? okey(tau0) : 1ull;
     BEAM_TICK(2);
     // ---- 4. threshold of the best W: admit k >= F1, and among k == F1 (tie_mode) those with k2 >= F2
     u64 F1 = 1, F2 = 0;
@@ -473,7 +491,8 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
 #pragma unroll
             for (int r = 0; r < kIPT; r++) {
               const u64 k = key[r];
-              if (k && (top >= 64 || ((k ^ prefix) >> top) == 0)) atomicAdd(&s_hist[(int)((k >> shift) & dmask)], 1);
+              if (r * kSearchThreads < nitems && k && (top >= 64 || ((k ^ prefix) >> top) == 0))
+                atomicAdd(&s_hist[(int)((k >> shift) & dmask)], 1);
             }
           } else {
             for (int i = tid; i < nitems; i += kSearchThreads) {
@@ -535,18 +554,28 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
     BEAM_TICK(3);
     // ---- 5. the admitted candidates, as a list
     if (cached) {
+      // one shared-memory atomic per warp: the lanes' counts are scanned, lane 31 reserves the warp's slots
+      unsigned adm = 0;
 #pragma unroll
       for (int r = 0; r < kIPT; r++) {
         const u64 k = key[r];
-        if (k >= F1) {
-          const int i = tid + r * kSearchThreads;
-          if (!(tie_mode && k == F1 && item_k2(c, i) < F2)) {
-            const int slot = atomicAdd(&s_redi[20], 1);
-            if (slot < W) {  // beyond W only through a hash collision among exact ties
-              s_adm_i[slot] = i;
-              s_adm_k[slot] = k;
-            }
+        if (r * kSearchThreads < nitems && k >= F1 &&
+            !(tie_mode && k == F1 && item_k2(c, tid + r * kSearchThreads) < F2))
+          adm |= 1u << r;
+      }
+      const int mine = __popc(adm);
+      const int incl = warp_incl_scan(mine, lane);
+      int base = 0;
+      if (lane == 31 && incl) base = atomicAdd(&s_redi[20], incl);
+      int slot = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+#pragma unroll
+      for (int r = 0; r < kIPT; r++) {
+        if ((adm >> r) & 1u) {
+          if (slot < W) {  // beyond W only through a hash collision among exact ties
+            s_adm_i[slot] = tid + r * kSearchThreads;
+            s_adm_k[slot] = key[r];
           }
+          slot++;
         }
       }
     } else {
@@ -586,7 +615,7 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
         orphan = po < 0 && g_len[a] > 0;
         s_newslot[b] = tid;
       } else {
-        const int id = atomicAdd(&s_redi[21], 1);
+        const int id = 1 + t * W + tid;  // frame t owns nodes [1 + t*W, 1 + (t+1)*W)
         nodes[id] = make_int2(g_node[a], l);
         const u64 h = child_hash(g_hash[a], l);
         g_pb[d] = ninf;
@@ -722,7 +751,8 @@ int ctc_beam_search(const float* logits, int T, int B, int C, long long st_t, lo
     set_error("ctc_beam_search: workspace of %zu bytes, %zu needed", workspace_bytes, need);
     return NASR_ERR_WORKSPACE_TOO_SMALL;
   }
-  const size_t smem = beam_smem_bytes(W, C);
+  const BeamLayout L = beam_layout(W, C);
+  const size_t smem = (size_t)L.total;
   if (W > kSearchThreads || C > 4095 || (size_t)W * C >= ((size_t)1 << 20) || smem > 200 * 1024) {
     set_error("ctc_beam_search: beam_width=%d with C=%d is not supported (beam_width <= %d, C <= 4095, %zu bytes of "
               "shared memory needed, 204800 available)", W, C, kSearchThreads, smem);
@@ -731,7 +761,8 @@ int ctc_beam_search(const float* logits, int T, int B, int C, long long st_t, lo
   NASR_CUDA(cudaFuncSetAttribute(ctc_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   int2* nodes = reinterpret_cast<int2*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   ctc_beam_kernel<<<B, kBeamThreads, smem, stream>>>(logits, T, B, C, st_t, st_b, seq_len, blank, W, P,
-                                                     merge_repeated, hyp, hyp_len, log_prob, nodes, g_debug_prof);
+                                                     merge_repeated, hyp, hyp_len, log_prob, nodes, g_debug_prof,
+                                                     L);
   count_launch();
   NASR_CUDA(cudaGetLastError());
   return NASR_OK;

@@ -28,9 +28,21 @@ from .utils import sparse_tuple_from
 class CtcHead:
     """Everything a CTC model tail does after it has logits (``bilstm_ctc_net.py:47-52``)."""
 
-    def __init__(self, time_major=True):
+    def __init__(self, time_major=True, decoder="greedy", beam_width=100):
+        """``decoder``: ``"greedy"`` (the north star's ``decoding``, ``tfnetwork.py:63``) or ``"beam"`` (what the
+        snapshot's ``create_model`` runs, ``tfnetwork.py:62``: beam search, width 100, top path)."""
+        if decoder not in ("greedy", "beam"):
+            raise ValueError("decoder must be 'greedy' or 'beam', got %r" % (decoder,))
         self.time_major = time_major
+        self.decoder, self.beam_width = decoder, int(beam_width)
         self.global_step = 0
+
+    def create_model(self, logits, seq_len):
+        """``(decoded[0], log_prob)`` as ``create_model`` returns them (``tfnetwork.py:61-64``)."""
+        if self.decoder == "beam":
+            decoded, log_prob = common.beam_decoding(logits, seq_len, beam_width=self.beam_width)
+            return decoded[0], log_prob
+        return common.decoding(logits, seq_len)
 
     def _view(self, logits):
         return logits if self.time_major else common.batch_major(logits)
@@ -41,7 +53,7 @@ class CtcHead:
         x = self._view(logits)
         lab = common.prepare_labels(labels, x.device)
         loss = common.loss(x, lab, seq_len)
-        model, log_prob = common.decoding(x.detach(), seq_len)
+        model, log_prob = self.create_model(x.detach(), seq_len)
         ler = common.label_error_rate(model, lab)
         return loss, model, log_prob, ler
 
@@ -72,7 +84,7 @@ class CtcHead:
 
     def decode(self, logits, seq_len):
         with torch.no_grad():
-            model, _ = common.decoding(self._view(logits), seq_len)
+            model, _ = self.create_model(self._view(logits), seq_len)
         return model.values.cpu().numpy()
 
 

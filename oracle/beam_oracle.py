@@ -13,9 +13,11 @@ Semantics restated:
     which shifts every candidate of a frame alike: same beams, same paths, a different returned score);
   * a beam entry is a prefix (tree node) with log P(prefix ends in blank), log P(prefix ends in its last label),
     and their log-sum; blank is the last class;
-  * step: every active entry b keeps its prefix:  label' = (LSE(label, parent term) if b's parent prefix is
-    active else label) + lp[last(b)],  parent term = parent.blank if last(b) == last(parent) else parent.total,
-    blank' = total + lp[blank];  every extension (b, l) whose prefix is not already active enters with
+  * step: every active entry b keeps its prefix:  label' = LSE(label + lp[last(b)], parent term + lp[last(b)]),
+    the second only if b's parent prefix is active,  parent term = parent.blank if last(b) == last(parent) else
+    parent.total,  blank' = total + lp[blank],  total' = log(e^blank' + e^(label + lp) + e^(parent term + lp))
+    (one three-way log-sum-exp: the same value as TF's nested LogSumExp up to rounding, and a shorter
+    dependency chain in the kernel);  every extension (b, l) whose prefix is not already active enters with
     label' = lp[l] + (b.blank if l == last(b) else b.total), blank' = -inf;  the best ``beam_width`` entries by
     total survive (TF's incremental TopN with its candidate test yields exactly this set, ties aside);
   * result: the best entry's label sequence, consecutive repeats collapsed when ``merge_repeated`` (TF's
@@ -78,17 +80,16 @@ def beam_search_one(x, beam_width=100, merge_repeated=True, blank=None, top_path
         lp = log_softmax_row(x[t])
         cand = {}
         for pre, (pb, pl, pt) in beams.items():
+            b1 = b2 = NEG
             if pre:
                 par = beams.get(pre[:-1])
-                nl = pl
+                b1 = pl + lp[pre[-1]]
                 if par is not None:
-                    prev = par[0] if (len(pre) >= 2 and pre[-1] == pre[-2]) else par[2]
-                    nl = _lse(pl, prev)
-                nl = nl + lp[pre[-1]]
-            else:
-                nl = NEG
+                    b2 = (par[0] if (len(pre) >= 2 and pre[-1] == pre[-2]) else par[2]) + lp[pre[-1]]
             nb = pt + lp[blank]
-            tot = _lse(nb, nl)
+            nl = _lse(b1, b2)
+            m = max(nb, b1, b2)
+            tot = NEG if m == NEG else m + np.log(np.exp(nb - m) + np.exp(b1 - m) + np.exp(b2 - m))
             if tot > NEG:
                 cand[pre] = (nb, nl, tot, 0, hashes[pre])
         for pre, (pb, pl, pt) in beams.items():

@@ -16,8 +16,8 @@ _LIB = None
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle_ctc.so")
-    src = os.path.join(_HERE, "ctc_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("ctc_oracle.c", "beam_oracle.c", "Makefile")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle_ctc.so"],
                               stdout=subprocess.DEVNULL)
     return so
@@ -93,3 +93,27 @@ def edit_distance(hyp_values, hyp_offsets, truth_values, truth_offsets, normaliz
                                int(bool(normalize)), _p(dist, ctypes.c_int32),
                                _p(ler, ctypes.c_float), int(num_threads))
     return dist, ler
+
+
+def beam_search(logits, seq_len, beam_width=100, top_paths=1, merge_repeated=True, blank=None, num_threads=0):
+    """oracle/beam_oracle.c (TF's trie + TopN control flow).  Returns (hyp i64[B,P,T], hyp_len i32[B,P],
+    log_prob f64[B,P]); logits may be any [T,B,C] float32 view with a dense class axis."""
+    logits = np.asarray(logits, dtype=np.float32)
+    if logits.strides[2] != 4:
+        logits = np.ascontiguousarray(logits)
+    T, B, C = logits.shape
+    blank = C - 1 if blank is None else int(blank)
+    sl = np.ascontiguousarray(seq_len, dtype=np.int32)
+    P = int(top_paths)
+    hyp = np.zeros((B, P, max(T, 1)), dtype=np.int64)
+    hl = np.zeros((B, P), dtype=np.int32)
+    lp = np.zeros((B, P), dtype=np.float64)
+    fn = lib().oracle_beam_search
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_longlong,
+                   ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    fn(logits.ctypes.data, T, B, C, logits.strides[0] // 4, logits.strides[1] // 4, sl.ctypes.data, blank,
+       int(beam_width), P, int(bool(merge_repeated)), hyp.ctypes.data, hl.ctypes.data, lp.ctypes.data,
+       int(num_threads))
+    return hyp[:, :, :T] if T else hyp[:, :, :0], hl, lp

@@ -125,3 +125,69 @@ def test_unsupported_and_bad_arguments():
         common.beam_decoding(x, np.array([4], np.int32), beam_width=4, top_paths=8)
     with pytest.raises(ValueError):
         common.beam_decoding(x.cpu(), np.array([4], np.int32))
+
+
+def _check_c(x, seq, W=100, P=1, merge=True, allow=0):
+    """Against the C port (oracle/beam_oracle.c), which is fast enough for full-length utterances."""
+    from oracle import c_oracle
+    got, lp = _run(x, seq, W, P, merge)
+    hyp, hl, want_lp = c_oracle.beam_search(x, seq, W, P, merge)
+    bad = 0
+    for b in range(x.shape[1]):
+        for p in range(P):
+            same = got[p][b] == hyp[b, p, : hl[b, p]].tolist() and \
+                abs(lp[b, p] - want_lp[b, p]) <= 1e-6 * max(1.0, abs(want_lp[b, p]))
+            bad += not same
+    assert bad <= allow, "%d of %d paths differ" % (bad, x.shape[1] * P)
+
+
+def test_full_length_utterances_against_c_port():
+    # BASELINE cfg2 shape per utterance (T=800, C=38, beam 100), random and peaky, ragged lengths
+    rng = np.random.default_rng(42)
+    x = (rng.normal(size=(800, 6, 38)) * 3).astype(np.float32)
+    _check_c(x, np.array([800, 800, 641, 400, 17, 0], np.int32))
+    _check_c(_peaky(rng, 800, 6, 38), np.array([800, 799, 555, 300, 1, 64], np.int32))
+
+
+def test_cfg1_shape_and_reference_config_vocabulary():
+    rng = np.random.default_rng(43)
+    _check_c(_peaky(rng, 500, 16, 38), np.full(16, 500, np.int32))          # cfg1: B=16, T=500, C=38
+    _check_c(_peaky(rng, 300, 4, 41), np.full(4, 300, np.int32))            # C=41: 8000sr config with ^ and $
+    _check_c((rng.normal(size=(120, 3, 41)) * 3).astype(np.float32), np.full(3, 120, np.int32))  # > 4096 candidates
+
+
+def test_wide_vocabulary_against_c_port():
+    rng = np.random.default_rng(44)
+    _check_c(_peaky(rng, 200, 3, 1024), np.array([200, 150, 77], np.int32))
+    _check_c((rng.normal(size=(40, 2, 1024)) * 3).astype(np.float32), np.array([40, 33], np.int32), W=64, P=2)
+
+
+def test_wide_beam():
+    rng = np.random.default_rng(45)
+    _check_c((rng.normal(size=(60, 2, 38)) * 2).astype(np.float32), np.array([60, 41], np.int32), W=512, P=3)
+
+
+def test_step_functions_with_the_beam_decoder():
+    """evaluate()/decode() of the step-function mirror (tfnetwork.py:172-181) with create_model's real decoder."""
+    from neuralasr_b200.steps import CtcHead
+    from oracle import c_oracle
+    rng = np.random.default_rng(46)
+    T, B, C, L = 80, 4, 38, 12
+    x = _peaky(rng, T, B, C, noise=0.5)
+    seq = np.array([80, 80, 61, 47], np.int32)
+    dense = rng.integers(1, C - 1, size=(B, L))
+    lens = np.array([12, 7, 9, 3])
+    head = CtcHead(decoder="beam")
+    values, mean_loss, mean_ler = head.evaluate(torch.from_numpy(x).cuda(), dense, seq, lens)
+    hyp, hl, _ = c_oracle.beam_search(x, seq, 100, 1, True)
+    want = np.concatenate([hyp[b, 0, : hl[b, 0]] for b in range(B)])
+    assert np.array_equal(values, want)
+    assert np.array_equal(head.decode(torch.from_numpy(x).cuda(), seq), want)
+    offs = np.concatenate([[0], np.cumsum(hl[:, 0])]).astype(np.int32)
+    tv = np.concatenate([dense[b, : lens[b]] for b in range(B)]).astype(np.int32)
+    to = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    _, want_ler = c_oracle.edit_distance(want, offs, tv, to)
+    assert abs(float(mean_ler) - float(want_ler.astype(np.float64).mean())) < 1e-6
+    assert np.isfinite(mean_loss)
+    with pytest.raises(ValueError):
+        CtcHead(decoder="viterbi")

@@ -29,3 +29,40 @@ def test_merge_repeated_collapses_the_output_and_narrow_beams_still_decode():
     assert bo.beam_search_one(x, 1, merge_repeated=False)[0] == [a, a, b]     # greedy-width beam
     vals, offs, lps = bo.beam_search(x[:, None, :].repeat(2, 1), [6, 3], 100, False)
     assert offs.tolist() == [0, 3, 4] and vals.tolist() == [a, a, b, a] and (lps <= 0).all()
+
+
+# ---- the C port (TF's trie + TopN control flow) against the dictionary oracle: two differently built programs
+def _both(x, seq, W, P=1, merge=True):
+    from oracle import c_oracle
+    hyp, hl, lp = c_oracle.beam_search(x, seq, W, P, merge)
+    for b in range(x.shape[1]):
+        want = bo.beam_search_one(x[: int(seq[b]), b, :].astype(np.float64), W, merge, top_paths=P)
+        for p in range(P):
+            if p < len(want):
+                assert hyp[b, p, : hl[b, p]].tolist() == want[p][0], (b, p)
+                assert abs(lp[b, p] - want[p][1]) <= 1e-10 * max(1.0, abs(want[p][1]))
+            else:
+                assert hl[b, p] == 0 and lp[b, p] == -np.inf
+
+
+@pytest.mark.parametrize("T,B,C,W", [(30, 3, 38, 100), (40, 3, 6, 4), (25, 2, 12, 1), (60, 2, 5, 7), (20, 2, 38, 16)])
+def test_c_port_equals_dictionary_oracle(T, B, C, W):
+    rng = np.random.default_rng(100 * T + W)
+    x = (rng.normal(size=(T, B, C)) * 3).astype(np.float32)
+    seq = np.array([T] + list(rng.integers(0, T + 1, size=B - 1)), np.int32)
+    _both(x, seq, W)
+
+
+def test_c_port_ties_top_paths_and_strided_input():
+    _both(np.zeros((8, 2, 6), np.float32), np.array([8, 5], np.int32), W=10, P=4, merge=False)   # exact ties
+    rng = np.random.default_rng(9)
+    xb = (rng.normal(size=(2, 20, 7)) * 2).astype(np.float32)                                 # batch-major
+    _both(xb.transpose(1, 0, 2), np.array([20, 11], np.int32), W=12, P=3, merge=True)
+
+
+def test_c_port_narrow_beam_drops_and_readmits_prefixes():
+    # a narrow beam on flat-ish logits keeps evicting prefixes whose parents come back later
+    rng = np.random.default_rng(21)
+    x = (rng.normal(size=(80, 2, 4)) * 0.7).astype(np.float32)
+    _both(x, np.array([80, 64], np.int32), W=3, P=3, merge=False)
+    _both(x, np.array([80, 64], np.int32), W=5, P=2, merge=True)
