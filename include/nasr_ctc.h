@@ -209,9 +209,11 @@ int nasr_batch_sums_f64(const float* loss, const float* ler, const int32_t* dist
  * HOST-buffer path: what a caller that holds numpy arrays (the reference's feed_dict world,
  * tfnetwork.py:183-190) uses.  The context owns device buffers, pinned staging and one stream, sized
  * for the maxima given at creation.  One call = H2D of logits/labels/seq_len, loss+grad, greedy decode,
- * edit distance, D2H of the results, and a stream synchronise.  Large batches are processed in four blocks
- * of utterances so that the H2D copy of one block, the kernels of the previous one and the D2H copy of the one
- * before overlap.
+ * edit distance, D2H of the results, and a stream synchronise.  Large batches are processed in eight blocks
+ * of utterances on two compute streams (a workspace each) so that the H2D copy of one block, the kernels of the
+ * previous ones and the D2H copy of the ones before overlap (environment NASR_HOST_BLOCKS / NASR_HOST_STREAMS,
+ * read at context creation, change the split: measured 1.78 ms unsplit, 1.30 ms 4x1, 1.20 ms 8x2 at B=256, T=1000,
+ * C=38).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct nasr_host_ctx nasr_host_ctx;
 

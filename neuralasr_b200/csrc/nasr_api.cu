@@ -2,6 +2,7 @@
 // DLPack unwrapping, the HOST-buffer context, and dispatch into the kernels of ctc_loss.cu /
 // ctc_decode.cu.  No torch types cross this boundary.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -130,9 +131,14 @@ using namespace nasr;
 struct nasr_host_ctx {
   int device;
   int max_T, max_B, max_C, max_L;
-  cudaStream_t stream;             // compute
+  cudaStream_t stream;             // compute (block k runs on s_k[k % n_streams]; stream == s_k[0])
+  cudaStream_t s_k[4];
+  int n_streams, n_blocks;         // NASR_HOST_STREAMS (1..4, default 2), NASR_HOST_BLOCKS (1..8, default 8)
   cudaStream_t s_in, s_out;        // H2D / D2H copies of the utterance blocks
   cudaEvent_t ev_in[8], ev_done[8];
+  void* d_ws_blk[8];               // one workspace per block: blocks on different streams run concurrently
+  size_t ws_blk_bytes;
+  int blk_B;                       // most utterances a block can hold
   // device
   float *d_logits, *d_grad, *d_loss, *d_grad_loss, *d_nsl, *d_ler;
   int32_t *d_lab_vals, *d_lab_offs, *d_seq, *d_status, *d_hyp_len, *d_dist;
@@ -341,6 +347,12 @@ void nasr_host_ctx_destroy(nasr_host_ctx* c) {
     if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
     if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
   }
+  for (int i = 1; i < 4; i++)
+    if (c->s_k[i]) {
+      cudaStreamSynchronize(c->s_k[i]);
+      cudaStreamDestroy(c->s_k[i]);
+    }
+  for (int i = 0; i < 8; i++) cudaFree(c->d_ws_blk[i]);
   if (c->s_in) cudaStreamDestroy(c->s_in);
   if (c->s_out) cudaStreamDestroy(c->s_out);
   cudaFree(c->d_logits); cudaFree(c->d_grad); cudaFree(c->d_loss); cudaFree(c->d_grad_loss);
@@ -380,6 +392,23 @@ int nasr_host_ctx_create(int device, int max_T, int max_B, int max_C, int max_la
     }                                                                                   \
   } while (0)
   NASR_CTX_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->s_k[0] = c->stream;
+  for (int i = 1; i < 4; i++) NASR_CTX_TRY(cudaStreamCreateWithFlags(&c->s_k[i], cudaStreamNonBlocking));
+  {
+    const char* e = getenv("NASR_HOST_STREAMS");
+    c->n_streams = e ? atoi(e) : 2;
+    c->n_streams = c->n_streams < 1 ? 1 : (c->n_streams > 4 ? 4 : c->n_streams);
+    e = getenv("NASR_HOST_BLOCKS");
+    c->n_blocks = e ? atoi(e) : 8;
+    c->n_blocks = c->n_blocks < 1 ? 1 : (c->n_blocks > 8 ? 8 : c->n_blocks);
+    c->blk_B = (max_B + c->n_blocks - 1) / c->n_blocks + 1;
+    rc = ctc_workspace_bytes(max_T, c->blk_B, max_C, max_label_len, &c->ws_blk_bytes);
+    if (rc != NASR_OK) {
+      nasr_host_ctx_destroy(c);
+      return rc;
+    }
+    for (int i = 0; i < c->n_blocks; i++) NASR_CTX_TRY(cudaMalloc(&c->d_ws_blk[i], c->ws_blk_bytes));
+  }
   NASR_CTX_TRY(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
   NASR_CTX_TRY(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
   for (int i = 0; i < 8; i++) {
@@ -456,7 +485,10 @@ int nasr_host_ctc_step(nasr_host_ctx* c, const float* logits, int T, int B, int 
   NASR_CUDA(cudaMemcpyAsync(c->d_seq, c->h_small + o_seq, sizeof(int32_t) * B, cudaMemcpyHostToDevice, sin));
   if (grad_loss) NASR_CUDA(cudaMemcpyAsync(c->d_grad_loss, c->h_small + o_gl, sizeof(float) * B, cudaMemcpyHostToDevice, sin));
   const bool want_decode = hyp || hyp_len || neg_sum_logits || dist || ler;
-  const int nblk = (nlog * sizeof(float) >= ((size_t)8 << 20) && B >= 8) ? 4 : 1;
+  // Blocks run on up to four compute streams with a workspace each: a block's kernels are bound by the length of
+  // one utterance's recursion, not by the number of utterances, so the kernels of consecutive blocks overlap
+  // and the call is left with the H2D copy of the whole batch plus one block's kernels and D2H copy.
+  const int nblk = (nlog * sizeof(float) >= ((size_t)8 << 20) && B >= 8 * c->n_blocks) ? c->n_blocks : 1;
   const size_t pitch = sizeof(float) * (size_t)B * C;
   for (int k = 0; k < nblk; k++) {
     const int b0 = (int)((long long)B * k / nblk), b1 = (int)((long long)B * (k + 1) / nblk);
@@ -466,10 +498,13 @@ int nasr_host_ctc_step(nasr_host_ctx* c, const float* logits, int T, int B, int 
     NASR_CUDA(cudaMemcpy2DAsync(c->d_logits + off, pitch, c->h_logits + off, pitch, sizeof(float) * (size_t)Bk * C,
                                 (size_t)T, cudaMemcpyHostToDevice, sin));
     NASR_CUDA(cudaEventRecord(c->ev_in[k], sin));
+    s = nblk > 1 ? c->s_k[k % c->n_streams] : c->stream;
+    void* ws = nblk > 1 ? c->d_ws_blk[k] : c->d_ws;
+    const size_t ws_bytes = nblk > 1 ? c->ws_blk_bytes : c->ws_bytes;
     NASR_CUDA(cudaStreamWaitEvent(s, c->ev_in[k], 0));
     int rc = ctc_loss_grad(c->d_logits + off, T, Bk, C, (long long)B * C, C, c->d_lab_vals, c->d_lab_offs + b0, Lmax,
                            c->d_seq + b0, blank, c->d_loss + b0, grad ? c->d_grad + off : nullptr,
-                           grad_loss ? c->d_grad_loss + b0 : nullptr, c->d_status + b0, c->d_ws, c->ws_bytes, s);
+                           grad_loss ? c->d_grad_loss + b0 : nullptr, c->d_status + b0, ws, ws_bytes, s);
     if (rc != NASR_OK) return rc;
     if (want_decode) {
       rc = greedy_decode(c->d_logits + off, T, Bk, C, (long long)B * C, C, c->d_seq + b0, blank, 1,

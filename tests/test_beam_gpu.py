@@ -191,3 +191,27 @@ def test_step_functions_with_the_beam_decoder():
     assert np.isfinite(mean_loss)
     with pytest.raises(ValueError):
         CtcHead(decoder="viterbi")
+
+
+def test_full_size_properties_cfg3():
+    """BASELINE cfg3 (B=256, T=1000, C=38, width 100): size-independent properties instead of an oracle run.
+    With a sharply planted alignment the most probable labelling is the collapsed arg-max path, so the beam's top
+    path (repeats NOT merged in the output) must equal the greedy decoder's; the search is deterministic; log
+    probabilities are <= 0 and ordered."""
+    from neuralasr_b200.networks import common
+    g = torch.Generator(device="cuda").manual_seed(5)
+    T, B, C = 1000, 256, 38
+    x = torch.randn((T, B, C), device="cuda", generator=g)
+    cls = torch.randint(0, C, (T // 2, B), device="cuda", generator=g).repeat_interleave(2, 0)
+    x.scatter_add_(2, cls.unsqueeze(-1), torch.full((T, B, 1), 30.0, device="cuda"))
+    seq = torch.full((B,), T, dtype=torch.int32)
+    seq[1], seq[2] = 517, 1
+    dec, lp = common.beam_decoding(x, seq, beam_width=100, top_paths=2, merge_repeated=False)
+    greedy, _ = common.decoding(x, seq)
+    assert torch.equal(dec[0].hyp_len, greedy.hyp_len)
+    keep = torch.arange(T, device="cuda")[None, :] < greedy.hyp_len[:, None]
+    assert torch.equal(dec[0].hyp[keep], greedy.hyp[keep])
+    assert (lp <= 0).all() and (lp[:, 0] >= lp[:, 1]).all() and (lp[:, 0] > -1e-3).all()
+    dec2, lp2 = common.beam_decoding(x, seq, beam_width=100, top_paths=2, merge_repeated=False)
+    assert torch.equal(lp, lp2) and torch.equal(dec[1].hyp_len, dec2[1].hyp_len)
+    assert torch.equal(dec[0].hyp[keep], dec2[0].hyp[keep])
