@@ -271,6 +271,20 @@ def run_ours(args, w, rank, world, local_rank):
     e2e_value = frames * world * e2e_steps / e2e_s
     h2d = x.nbytes + vals.nbytes + offs.nbytes + seq.nbytes + 4 * B
     d2h = x.nbytes + 4 * B + 4 * B
+    # the snapshot's whole train() fetch (tfnetwork.py:183-190): loss, gradient AND mean label error rate of the
+    # beam search decoder, host buffers in and out — reported beside the headline, rank 0 only
+    train_step = None
+    if rank == 0:
+        ctx.set_decoder("beam", 100)
+        for _ in range(2):
+            out = ctx.step(pin, vals, offs, seq, grad_loss=np.full(B, 1.0 / B, np.float32), want_decode=True)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            out = ctx.step(pin, vals, offs, seq, grad_loss=np.full(B, 1.0 / B, np.float32), want_decode=True)
+        ts = (time.perf_counter() - t0) / 5
+        train_step = {"ms_per_step": ts * 1e3, "frames_per_s": frames / ts, "mean_ler": float(out["ler"].mean()),
+                      "what": "nasr_host_ctc_step with the beam decoder (width 100): H2D, loss+grad, beam search, "
+                              "label error rate, D2H of grad/loss/ler"}
     ctx.close()
 
     # ---- decode + LER, reported beside the headline (not folded into it) ----
@@ -348,6 +362,7 @@ def run_ours(args, w, rank, world, local_rank):
             "clocks": clocks,
             "decode_ler_ms": dec_ms,
             "beam_search": beam,
+            "e2e_train_step": train_step,
         }))
     if world > 1:
         dist.destroy_process_group()

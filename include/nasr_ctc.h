@@ -220,6 +220,10 @@ typedef struct nasr_host_ctx nasr_host_ctx;
 int nasr_host_ctx_create(int device, int max_T, int max_B, int max_C, int max_label_len,
                          nasr_host_ctx** out);
 void nasr_host_ctx_destroy(nasr_host_ctx* ctx);
+/* Which decoder nasr_host_ctc_step runs: 0 = greedy (tfnetwork.py:63, the default), 1 = beam search of width
+ * beam_width, top path, merge_repeated (tfnetwork.py:62, what train()/evaluate() fetch in the snapshot); with the beam
+ * decoder the step's neg_sum_logits output carries the top path's log probability.  Allocates the beam workspace. */
+int nasr_host_ctx_set_decoder(nasr_host_ctx* ctx, int decoder, int beam_width);
 /* Pinned host staging the caller may fill directly to skip one host copy: logits float[max_T*max_B*max_C],
  * grad float[same]. */
 float* nasr_host_ctx_pinned_logits(nasr_host_ctx* ctx);

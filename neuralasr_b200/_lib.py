@@ -40,6 +40,7 @@ SIGNATURES = {
     "nasr_batch_sums_f64": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "nasr_host_ctx_create": (_i, [_i, _i, _i, _i, _i, ctypes.POINTER(_vp)]),
     "nasr_host_ctx_destroy": (None, [_vp]),
+    "nasr_host_ctx_set_decoder": (_i, [_vp, _i, _i]),
     "nasr_host_ctx_pinned_logits": (_vp, [_vp]),
     "nasr_host_ctx_pinned_grad": (_vp, [_vp]),
     "nasr_host_ctc_step": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -139,6 +139,11 @@ struct nasr_host_ctx {
   void* d_ws_blk[8];               // one workspace per block: blocks on different streams run concurrently
   size_t ws_blk_bytes;
   int blk_B;                       // most utterances a block can hold
+  int decoder, beam_width;         // nasr_host_ctx_set_decoder: 0 greedy (default), 1 beam search
+  cudaStream_t s_beam;
+  cudaEvent_t ev_beam;
+  void* d_ws_beam;
+  size_t ws_beam_bytes;
   // device
   float *d_logits, *d_grad, *d_loss, *d_grad_loss, *d_nsl, *d_ler;
   int32_t *d_lab_vals, *d_lab_offs, *d_seq, *d_status, *d_hyp_len, *d_dist;
@@ -353,6 +358,12 @@ void nasr_host_ctx_destroy(nasr_host_ctx* c) {
       cudaStreamDestroy(c->s_k[i]);
     }
   for (int i = 0; i < 8; i++) cudaFree(c->d_ws_blk[i]);
+  if (c->s_beam) {
+    cudaStreamSynchronize(c->s_beam);
+    cudaStreamDestroy(c->s_beam);
+  }
+  if (c->ev_beam) cudaEventDestroy(c->ev_beam);
+  cudaFree(c->d_ws_beam);
   if (c->s_in) cudaStreamDestroy(c->s_in);
   if (c->s_out) cudaStreamDestroy(c->s_out);
   cudaFree(c->d_logits); cudaFree(c->d_grad); cudaFree(c->d_loss); cudaFree(c->d_grad_loss);
@@ -438,6 +449,30 @@ int nasr_host_ctx_create(int device, int max_T, int max_B, int max_C, int max_la
   return NASR_OK;
 }
 
+int nasr_host_ctx_set_decoder(nasr_host_ctx* c, int decoder, int beam_width) {
+  NASR_CHECK_ARG(c, "nasr_host_ctx_set_decoder: ctx is NULL");
+  NASR_CHECK_ARG(decoder == 0 || decoder == 1, "nasr_host_ctx_set_decoder: decoder must be 0 (greedy) or 1 (beam)");
+  if (decoder == 1) {
+    NASR_CHECK_ARG(beam_width >= 1, "nasr_host_ctx_set_decoder: beam_width must be >= 1");
+    NASR_CUDA(cudaSetDevice(c->device));
+    size_t need = 0;
+    int rc = ctc_beam_workspace_bytes(c->max_T, c->max_B, c->max_C, beam_width, &need);
+    if (rc != NASR_OK) return rc;
+    if (need > c->ws_beam_bytes) {
+      cudaFree(c->d_ws_beam);
+      c->d_ws_beam = nullptr;
+      c->ws_beam_bytes = 0;
+      NASR_CUDA(cudaMalloc(&c->d_ws_beam, need));
+      c->ws_beam_bytes = need;
+    }
+    if (!c->s_beam) NASR_CUDA(cudaStreamCreateWithFlags(&c->s_beam, cudaStreamNonBlocking));
+    if (!c->ev_beam) NASR_CUDA(cudaEventCreateWithFlags(&c->ev_beam, cudaEventDisableTiming));
+  }
+  c->decoder = decoder;
+  c->beam_width = beam_width;
+  return NASR_OK;
+}
+
 float* nasr_host_ctx_pinned_logits(nasr_host_ctx* c) { return c ? c->h_logits : nullptr; }
 float* nasr_host_ctx_pinned_grad(nasr_host_ctx* c) { return c ? c->h_grad : nullptr; }
 
@@ -506,7 +541,7 @@ int nasr_host_ctc_step(nasr_host_ctx* c, const float* logits, int T, int B, int 
                            c->d_seq + b0, blank, c->d_loss + b0, grad ? c->d_grad + off : nullptr,
                            grad_loss ? c->d_grad_loss + b0 : nullptr, c->d_status + b0, ws, ws_bytes, s);
     if (rc != NASR_OK) return rc;
-    if (want_decode) {
+    if (want_decode && c->decoder == 0) {
       rc = greedy_decode(c->d_logits + off, T, Bk, C, (long long)B * C, C, c->d_seq + b0, blank, 1,
                          c->d_hyp + (size_t)b0 * T, c->d_hyp_len + b0, c->d_nsl + b0, s);
       if (rc != NASR_OK) return rc;
@@ -521,6 +556,21 @@ int nasr_host_ctc_step(nasr_host_ctx* c, const float* logits, int T, int B, int 
     if (grad)
       NASR_CUDA(cudaMemcpy2DAsync(c->h_grad + off, pitch, c->d_grad + off, pitch, sizeof(float) * (size_t)Bk * C,
                                   (size_t)T, cudaMemcpyDeviceToHost, sout));
+  }
+  if (want_decode && c->decoder == 1) {
+    // Beam search: one launch over the whole batch on its own stream once the last block has arrived (a launch per
+    // block would put eight latency-bound searches in a row), concurrent with the blocks' loss/gradient kernels.
+    NASR_CUDA(cudaStreamWaitEvent(c->s_beam, c->ev_in[nblk - 1], 0));
+    int rc = ctc_beam_search(c->d_logits, T, B, C, (long long)B * C, C, c->d_seq, blank, c->beam_width, 1, 1, c->d_hyp,
+                             c->d_hyp_len, c->d_nsl, c->d_ws_beam, c->ws_beam_bytes, c->s_beam);
+    if (rc != NASR_OK) return rc;
+    if (dist || ler) {
+      rc = edit_distance_dense(c->d_hyp, T, c->d_hyp_len, c->d_lab_vals, c->d_lab_offs, Lmax, B, 1, c->d_dist,
+                               c->d_ler, c->s_beam);
+      if (rc != NASR_OK) return rc;
+    }
+    NASR_CUDA(cudaEventRecord(c->ev_beam, c->s_beam));
+    NASR_CUDA(cudaStreamWaitEvent(sout, c->ev_beam, 0));
   }
   s = sout;  // everything below is ordered after the last block's kernels
   NASR_CUDA(cudaMemcpyAsync(c->h_small + o_loss, c->d_loss, sizeof(float) * B, cudaMemcpyDeviceToHost, s));

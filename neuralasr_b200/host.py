@@ -19,7 +19,9 @@ def _p(a):
 
 
 class HostContext:
-    def __init__(self, device, max_T, max_B, max_C, max_label_len):
+    def __init__(self, device, max_T, max_B, max_C, max_label_len, decoder="greedy", beam_width=100):
+        """``decoder``: ``"greedy"`` (``tfnetwork.py:63``) or ``"beam"`` (``tfnetwork.py:62``: what the snapshot's
+        ``train``/``evaluate`` fetch; ``neg_sum_logits`` of a step is then the top path's log probability)."""
         self._lib = _lib.load()
         self._ctx = ctypes.c_void_p()
         _lib.check(self._lib.nasr_host_ctx_create(int(device), int(max_T), int(max_B), int(max_C),
@@ -32,6 +34,14 @@ class HostContext:
             ctypes.cast(self._lib.nasr_host_ctx_pinned_logits(self._ctx), fl), shape=(n,))
         self.pinned_grad = np.ctypeslib.as_array(
             ctypes.cast(self._lib.nasr_host_ctx_pinned_grad(self._ctx), fl), shape=(n,))
+        self.set_decoder(decoder, beam_width)
+
+    def set_decoder(self, decoder="greedy", beam_width=100):
+        if decoder not in ("greedy", "beam"):
+            raise ValueError("decoder must be 'greedy' or 'beam', got %r" % (decoder,))
+        _lib.check(self._lib.nasr_host_ctx_set_decoder(self._ctx, int(decoder == "beam"), int(beam_width)),
+                   "nasr_host_ctx_set_decoder")
+        self.decoder = decoder
 
     def step(self, logits, label_values, label_offsets, seq_len, blank=None, grad_loss=None,
              want_grad=True, want_decode=True, want_hyp=False, grad_out=None):

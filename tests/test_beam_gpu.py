@@ -215,3 +215,34 @@ def test_full_size_properties_cfg3():
     dec2, lp2 = common.beam_decoding(x, seq, beam_width=100, top_paths=2, merge_repeated=False)
     assert torch.equal(lp, lp2) and torch.equal(dec[1].hyp_len, dec2[1].hyp_len)
     assert torch.equal(dec[0].hyp[keep], dec2[0].hyp[keep])
+
+
+def test_host_buffer_step_with_the_beam_decoder():
+    """nasr_host_ctc_step after nasr_host_ctx_set_decoder(beam): numpy in, what train() fetches out."""
+    from neuralasr_b200 import host
+    from oracle import c_oracle
+    rng = np.random.default_rng(47)
+    T, B, C, L = 120, 24, 38, 10
+    x = _peaky(rng, T, B, C, noise=0.7)
+    seq = rng.integers(60, T + 1, size=B).astype(np.int32)
+    lens = rng.integers(1, L + 1, size=B)
+    vals = rng.integers(0, C - 1, size=int(lens.sum())).astype(np.int32)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    ctx = host.HostContext(0, T, B, C, L, decoder="beam", beam_width=50)
+    out = ctx.step(x, vals, offs, seq, want_hyp=True)
+    hyp, hl, lp = c_oracle.beam_search(x, seq, 50, 1, True)
+    assert np.array_equal(out["hyp_len"], hl[:, 0])
+    for b in range(B):
+        assert np.array_equal(out["hyp"][b, : hl[b, 0]], hyp[b, 0, : hl[b, 0]])
+    assert np.allclose(out["neg_sum_logits"], lp[:, 0], rtol=1e-6)
+    hv = np.concatenate([hyp[b, 0, : hl[b, 0]] for b in range(B)])
+    ho = np.concatenate([[0], np.cumsum(hl[:, 0])]).astype(np.int32)
+    want_d, want_ler = c_oracle.edit_distance(hv, ho, vals, offs)
+    assert np.array_equal(out["dist"], want_d) and np.allclose(out["ler"], want_ler)
+    want_loss, _, _ = c_oracle.ctc_loss_grad(x, vals, offs, seq, precision="f64", want_grad=False)
+    assert np.allclose(out["loss"], want_loss, rtol=1e-4)
+    ctx.set_decoder("greedy")
+    g = ctx.step(x, vals, offs, seq)
+    gv, go, _ = c_oracle.greedy_decode(x, seq)
+    assert np.array_equal(g["hyp_len"], np.diff(go))
+    ctx.close()
