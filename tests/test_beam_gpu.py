@@ -246,3 +246,22 @@ def test_host_buffer_step_with_the_beam_decoder():
     gv, go, _ = c_oracle.greedy_decode(x, seq)
     assert np.array_equal(g["hyp_len"], np.diff(go))
     ctx.close()
+
+
+def test_kernel_reproduces_the_golden_fixture():
+    """tests/golden/beam_bruteforce.npz: exact labelling probabilities by enumeration of every alignment.  Width 512
+    is at least the number of prefixes of these utterances, so the kernel's search is exhaustive here."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "beam_bruteforce.npz"))
+    checked = 0
+    for i in range(int(g["cases"])):
+        x, n = g["x%d" % i], int(g["n%d" % i])
+        T, C = x.shape
+        assert sum((C - 1) ** k for k in range(T + 1)) <= 512
+        got, lp = _run(x[:, None, :].copy(), np.array([T], np.int32), W=512, P=max(n, 1), merge=False)
+        for j in range(n):
+            want = g["labels%d" % i][j, : g["lens%d" % i][j]].tolist()
+            assert got[j][0] == want, (i, j)
+            assert abs(lp[0, j] - g["logp%d" % i][j]) <= 1e-6 * max(1.0, abs(g["logp%d" % i][j]))
+            checked += 1
+    assert checked >= 40

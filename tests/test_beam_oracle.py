@@ -66,3 +66,25 @@ def test_c_port_narrow_beam_drops_and_readmits_prefixes():
     x = (rng.normal(size=(80, 2, 4)) * 0.7).astype(np.float32)
     _both(x, np.array([80, 64], np.int32), W=3, P=3, merge=False)
     _both(x, np.array([80, 64], np.int32), W=5, P=2, merge=True)
+
+
+# ---- committed golden fixture: exact labelling probabilities of tiny utterances (tests/golden/make_beam_golden.py)
+def _golden():
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "beam_bruteforce.npz"))
+    for i in range(int(g["cases"])):
+        n = int(g["n%d" % i])
+        want = [(g["labels%d" % i][j, : g["lens%d" % i][j]].tolist(), float(g["logp%d" % i][j])) for j in range(n)]
+        yield g["x%d" % i], want
+
+
+def test_both_oracles_reproduce_the_golden_fixture():
+    from oracle import c_oracle
+    cases = list(_golden())
+    assert len(cases) >= 16 and sum(len(w) for _, w in cases) >= 40
+    for x, want in cases:
+        got = bo.beam_search_one(x.astype(np.float64), beam_width=10 ** 5, merge_repeated=False, top_paths=len(want))
+        hyp, hl, lp = c_oracle.beam_search(x[:, None, :], [x.shape[0]], 10 ** 5, len(want), False)
+        for j, (lab, v) in enumerate(want):
+            assert got[j][0] == lab and abs(got[j][1] - v) < 1e-9
+            assert hyp[0, j, : hl[0, j]].tolist() == lab and abs(lp[0, j] - v) < 1e-9
