@@ -43,6 +43,7 @@ constexpr int kSearchWarps = kSearchThreads / 32;
 constexpr int kBeamThreads = kSearchThreads + 32;   // + one warp that prepares the next frame's log-softmax
 constexpr int kIPT = 4096 / kSearchThreads;         // candidate keys a search thread keeps in registers
 constexpr int kBins = 2048;                         // 11-bit digits
+constexpr int kStage2MinC = 64;                     // vocabularies wider than this get the second-stage bound
 constexpr int kBinsPerThread = kBins / kSearchThreads;
 constexpr u64 kRootHash = 0x243f6a8885a308d3ull;
 
@@ -92,7 +93,7 @@ __host__ __device__ inline int tab_size(int W) {
 // every array base is then a constant-bank operand instead of arithmetic on W and C redone inside the frame loop.
 struct BeamLayout {
   int lp2, pb, pl, pt, hash, phash, node, len, last, plast, pslot, ub, ul, ut, liveP, newslot, adm_i, liveL, adm_k,
-      tab_key, tab_slot, mask, hist, redd, redu, redi;
+      tab_key, tab_slot, mask, hist, redd, redu, redi, c1, c2;
   int total, TS, CW;
 };
 
@@ -132,6 +133,8 @@ inline BeamLayout beam_layout(int W, int C) {
   L.redd = take(sizeof(double) * 64);
   L.redu = take(sizeof(u64) * 64);
   L.redi = take(sizeof(int) * 64);
+  L.c1 = take(sizeof(double) * W);
+  L.c2 = take(sizeof(double) * W);
   L.total = (int)o;
   return L;
 }
@@ -153,7 +156,7 @@ struct Ctx {
   const uint32_t* mask;
   int n, nL, CW;
   unsigned divM;  // floor((2^32-1) / nL) + 1: j / nL == umulhi(j, divM) for j < 2^20 (nL >= 2)
-  double tau0;
+  u64 kkeep, kext;  // smallest key a kept prefix / an extension must have to be a candidate
 };
 
 // Candidate i of the frame: i < n is active prefix i itself (l = -1); otherwise the extension of live prefix
@@ -176,15 +179,19 @@ __device__ __forceinline__ u64 eval_key(const Ctx& c, int i) {
   item_of(c, i, b, l);
   double v;
   bool ok;
+  u64 kmin;
   if (l < 0) {
     v = c.ut[b];
-    ok = v > neg_inf();
+    ok = true;
+    kmin = c.kkeep;
   } else {
     const bool masked = (c.mask[b * c.CW + (l >> 5)] >> (l & 31)) & 1u;
     v = c.lp[l] + (l == c.last[b] ? c.pb[b] : c.pt[b]);
-    ok = !masked && v > c.tau0;
+    ok = !masked;
+    kmin = c.kext;
   }
-  return ok ? okey(v) : 0ull;
+  const u64 k = okey(v);
+  return ok && k >= kmin ? k : 0ull;
 }
 
 __device__ __forceinline__ u64 item_k2(const Ctx& c, int i) {
@@ -237,6 +244,9 @@ __device__ __forceinline__ void find_bin(int* hist, int nb, int need, int* wsum,
   bar_search();
 }
 
+// STAGE2: second-stage bound on the frame's threshold (phase 2); pays for wide vocabularies, where it shortens the
+// live-label list by one to two orders of magnitude; at C = 38 the lists are short anyway and it costs what it saves.
+template <bool STAGE2>
 __global__ void __launch_bounds__(kBeamThreads, 2)
 ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long st_t, long long st_b,
                 const int32_t* __restrict__ seq_len, int blank, int W, int P, int merge_repeated,
@@ -276,9 +286,11 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
   BEAM_ARR(double, s_redd, redd);
   BEAM_ARR(u64, s_redu, redu);
   BEAM_ARR(int, s_redi, redi);
+  BEAM_ARR(double, s_c1, c1);         // score of each prefix's extension by the frame's best / second label
+  BEAM_ARR(double, s_c2, c2);
 #undef BEAM_ARR
   // s_redi: [0..15] warp partials, [16..18] find_bin result, [20] admitted counter,
-  //         [22] live prefixes, [23] live labels, [32..47] find_bin warp sums
+  //         [22] live prefixes, [23] live labels, [32..47] find_bin warp sums, [56..59] the two best labels of rows t&1
   // s_redd: [0..15] min of the updated totals, [16..31] max of the old totals, [40..41] max of lp rows t&1,
   //         [44..59] max of the updated totals
   // s_redu: [32..39] profile accumulators
@@ -327,7 +339,36 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
       const double lse = log(sum);
       double* lp = s_lp2 + (t & 1) * C;
       for (int c = lane; c < C; c += 32) lp[c] = ((double)__ldg(x + c) - m) - lse;
-      if (lane == 0) s_redd[40 + (t & 1)] = -lse;
+      // the two best labels (blank aside; ties: the smaller index), for the second-stage bound of phase 2
+      float v1 = -INFINITY, v2 = -INFINITY;
+      int i1 = -1, i2 = -1;
+      for (int c = lane; STAGE2 && c < C; c += 32) {
+        const float v = __ldg(x + c);
+        if (c == blank) continue;
+        if (v > v1) {
+          v2 = v1; i2 = i1; v1 = v; i1 = c;
+        } else if (v > v2) {
+          v2 = v; i2 = c;
+        }
+      }
+#pragma unroll
+      for (int o = 16; STAGE2 && o > 0; o >>= 1) {
+        const float w1 = __shfl_xor_sync(0xffffffffu, v1, o), w2 = __shfl_xor_sync(0xffffffffu, v2, o);
+        const int j1 = __shfl_xor_sync(0xffffffffu, i1, o), j2 = __shfl_xor_sync(0xffffffffu, i2, o);
+        const bool first = w1 > v1 || (w1 == v1 && (unsigned)j1 < (unsigned)i1);  // the partner's best is the best
+        const float a1 = first ? w1 : v1, b1 = first ? v1 : w1;  // b1: the loser of the two bests
+        const int ai = first ? j1 : i1, bi = first ? i1 : j1;
+        const float c2v = first ? w2 : v2;                       // the winner's own second
+        const int c2i = first ? j2 : i2;
+        const bool bsecond = b1 > c2v || (b1 == c2v && (unsigned)bi < (unsigned)c2i);
+        v1 = a1; i1 = ai;
+        v2 = bsecond ? b1 : c2v; i2 = bsecond ? bi : c2i;
+      }
+      if (lane == 0) {
+        s_redd[40 + (t & 1)] = -lse;
+        s_redi[56 + 2 * (t & 1)] = i1;
+        s_redi[57 + 2 * (t & 1)] = i2;
+      }
       __syncthreads();  // row t is ready (and the search of frame t-1 is over)
     }
     return;
@@ -349,6 +390,7 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
     const int ao = cur * W, no = (cur ^ 1) * W;  // offsets of the active and of the next beam buffer
     const double* lp = s_lp2 + (t & 1) * C;
     const double lpmax = s_redd[40 + (t & 1)];
+    const int top1 = s_redi[56 + 2 * (t & 1)], top2 = s_redi[57 + 2 * (t & 1)];
     // ---- 1. active prefixes keep themselves; worst kept score and best old score by warp
     {
       double ut = ninf, pt_old = ninf;
@@ -372,6 +414,16 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
         s_ul[e] = nl;
         s_ut[e] = ut;
         s_newslot[e] = -1;
+        // this prefix's extensions by the frame's two best labels: true candidates of the frame (phase 2)
+        double c1 = ninf, c2 = ninf;
+        if (STAGE2 && top1 >= 0 && !((s_mask[e * CW + (top1 >> 5)] >> (top1 & 31)) & 1u))
+          c1 = lp[top1] + (top1 == last ? g_pb[ao + e] : pt_old);
+        if (STAGE2 && top2 >= 0 && !((s_mask[e * CW + (top2 >> 5)] >> (top2 & 31)) & 1u))
+          c2 = lp[top2] + (top2 == last ? g_pb[ao + e] : pt_old);
+        if (STAGE2) {
+          s_c1[e] = c1;
+          s_c2[e] = c2;
+        }
       }
       if (warp * 32 < n) {
         const unsigned okb = __ballot_sync(0xffffffffu, ut > ninf);
@@ -398,52 +450,125 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
     }
     bar_search();
     BEAM_TICK(0);
-    // ---- 2. is the beam full (then only scores above its worst kept one matter); live prefixes and labels
-    //         (only the warps that have a list to build combine the partials)
-    if (warp * 32 < n || warp * 32 < C) {
-      int cntv = 0;
-      double mn = __longlong_as_double(0x7ff0000000000000ll), ptmax = ninf, utmax = ninf;
-      for (int w = 0; w * 32 < n; w++) {
-        cntv += s_redi[w];
-        mn = fmin(mn, s_redd[w]);
-        ptmax = fmax(ptmax, s_redd[16 + w]);
-        utmax = fmax(utmax, s_redd[44 + w]);
-      }
-      const double tau0 = cntv >= W ? mn : ninf;
-      if (tid == 0) {  // every candidate's score lies in (tau0, vtop] (kept prefixes: [tau0, vtop])
-        s_redd[32] = tau0;
-        s_redd[33] = fmax(utmax, ptmax + lpmax);
-      }
-      if (warp * 32 < n) {
-        bool lv = false;
-        if (tid < n) {
-          const double pt = g_pt[ao + tid];
-          lv = pt > ninf && pt + lpmax > tau0;
+    // ---- 2. is the beam full (then only scores above its worst kept one, tau0, matter); wide vocabularies: a
+    //         second-stage bound; live prefixes and labels
+    double tau0, vtop;  // every candidate's score lies in (tau0, vtop] (kept prefixes: [tau0, vtop])
+    u64 kfloor = 0;     // second-stage bound (key domain), 0 = none
+    if (STAGE2) {
+      // every thread combines the warps' partials itself
+      double ptmax = ninf;
+      {
+        int cntv = 0;
+        double mn = __longlong_as_double(0x7ff0000000000000ll), utmax = ninf;
+        for (int w = 0; w * 32 < n; w++) {
+          cntv += s_redi[w];
+          mn = fmin(mn, s_redd[w]);
+          ptmax = fmax(ptmax, s_redd[16 + w]);
+          utmax = fmax(utmax, s_redd[44 + w]);
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, lv);
-        int base = 0;
-        if (lane == 0 && bal) base = atomicAdd(&s_redi[22], __popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (lv) s_liveP[base + __popc(bal & ((1u << lane) - 1u))] = tid;
+        tau0 = cntv >= W ? mn : ninf;
+        vtop = fmax(utmax, ptmax + lpmax);
       }
-      for (int c0 = warp * 32; c0 < C; c0 += kSearchThreads) {
-        const int cc = c0 + lane;
-        const bool lv = cc < C && cc != blank && lp[cc] + ptmax > tau0;
-        const unsigned bal = __ballot_sync(0xffffffffu, lv);
-        int base = 0;
-        if (lane == 0 && bal) base = atomicAdd(&s_redi[23], __popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (lv) s_liveL[base + __popc(bal & ((1u << lane) - 1u))] = cc;
+      // Second stage.  S = the W updated kept prefixes + every prefix's extensions by the frame's two best labels:
+      // all true candidates, so the W-th best of S is a lower bound of the frame's threshold, and usually a tight one
+      // (measured: live labels 441 -> 5 at C = 1024, 16 -> 2 at C = 38 on N(0,1)*3 logits; 425 -> 20 and 18 -> 6 on
+      // planted alignments).  One histogram pass over S gives the bin of its W-th best; the bin's lower edge, kfloor,
+      // is the bound used from here on: a candidate below it is below at least W candidates.
+      const u64 kt0 = okey(tau0), ktop = okey(vtop);
+      if (tau0 > ninf && kt0 != ktop) {
+        const int top0 = 64 - __clzll((long long)(kt0 ^ ktop));
+        const int width0 = min(11, top0), shift0 = top0 - width0;
+        const unsigned dmask0 = (1u << width0) - 1u;
+        if (tid < n) {
+          atomicAdd(&s_hist[(int)((okey(s_ut[tid]) >> shift0) & dmask0)], 1);
+          const double c1 = s_c1[tid], c2 = s_c2[tid];
+          if (c1 > tau0) atomicAdd(&s_hist[(int)((okey(c1) >> shift0) & dmask0)], 1);
+          if (c2 > tau0) atomicAdd(&s_hist[(int)((okey(c2) >> shift0) & dmask0)], 1);
+        }
+        bar_search();
+        find_bin(s_hist, 1 << width0, W, s_redi + 32, s_redi + 16, tid);
+        kfloor = (ktop & ~(((u64)1 << top0) - 1)) | ((u64)s_redi[16] << shift0);
+      }
+      const u64 kext = kfloor > kt0 + 1ull ? kfloor : kt0 + 1ull;
+      {
+        const double tl = okey_inv(kext);  // lists are supersets: non-strict comparisons against the bound
+        if (warp * 32 < n) {
+          bool lv = false;
+          if (tid < n) {
+            const double pt = g_pt[ao + tid];
+            lv = pt > ninf && pt + lpmax >= tl;
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, lv);
+          int base = 0;
+          if (lane == 0 && bal) base = atomicAdd(&s_redi[22], __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (lv) s_liveP[base + __popc(bal & ((1u << lane) - 1u))] = tid;
+        }
+        for (int c0 = warp * 32; c0 < C; c0 += kSearchThreads) {
+          const int cc = c0 + lane;
+          const bool lv = cc < C && cc != blank && lp[cc] + ptmax >= tl;
+          const unsigned bal = __ballot_sync(0xffffffffu, lv);
+          int base = 0;
+          if (lane == 0 && bal) base = atomicAdd(&s_redi[23], __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (lv) s_liveL[base + __popc(bal & ((1u << lane) - 1u))] = cc;
+        }
+      }
+    } else {
+      // only the warps that have a list to build combine the partials; thread 0 publishes tau0 and vtop
+      if (warp * 32 < n || warp * 32 < C) {
+        int cntv = 0;
+        double mn = __longlong_as_double(0x7ff0000000000000ll), ptmax = ninf, utmax = ninf;
+        for (int w = 0; w * 32 < n; w++) {
+          cntv += s_redi[w];
+          mn = fmin(mn, s_redd[w]);
+          ptmax = fmax(ptmax, s_redd[16 + w]);
+          utmax = fmax(utmax, s_redd[44 + w]);
+        }
+        const double tau0 = cntv >= W ? mn : ninf;
+        if (tid == 0) {  // every candidate's score lies in (tau0, vtop] (kept prefixes: [tau0, vtop])
+          s_redd[32] = tau0;
+          s_redd[33] = fmax(utmax, ptmax + lpmax);
+        }
+        if (warp * 32 < n) {
+          bool lv = false;
+          if (tid < n) {
+            const double pt = g_pt[ao + tid];
+            lv = pt > ninf && pt + lpmax > tau0;
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, lv);
+          int base = 0;
+          if (lane == 0 && bal) base = atomicAdd(&s_redi[22], __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (lv) s_liveP[base + __popc(bal & ((1u << lane) - 1u))] = tid;
+        }
+        for (int c0 = warp * 32; c0 < C; c0 += kSearchThreads) {
+          const int cc = c0 + lane;
+          const bool lv = cc < C && cc != blank && lp[cc] + ptmax > tau0;
+          const unsigned bal = __ballot_sync(0xffffffffu, lv);
+          int base = 0;
+          if (lane == 0 && bal) base = atomicAdd(&s_redi[23], __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (lv) s_liveL[base + __popc(bal & ((1u << lane) - 1u))] = cc;
+        }
       }
     }
     bar_search();
+    if (!STAGE2) {
+      tau0 = s_redd[32];
+      vtop = s_redd[33];
+    }
     BEAM_TICK(1);
+    // okey(-inf) + 1 is the key of the smallest finite score
+    const u64 kfin = okey(ninf) + 1ull, kt0 = okey(tau0), ktop = okey(vtop);
+    const u64 kkeep = kfloor > kfin ? kfloor : kfin;             // kept prefixes: any finite score, or the bound
+    const u64 kext = kfloor > kt0 + 1ull ? kfloor : kt0 + 1ull;  // extensions: strictly above tau0, and the bound
     Ctx c;
     c.lp = lp; c.pb = g_pb + ao; c.pt = g_pt + ao; c.ut = s_ut; c.hash = g_hash + ao; c.last = g_last + ao;
     c.liveP = s_liveP; c.liveL = s_liveL; c.mask = s_mask; c.n = n; c.nL = s_redi[23]; c.CW = CW;
     c.divM = c.nL >= 2 ? 0xffffffffu / (unsigned)c.nL + 1u : 0u;
-    c.tau0 = s_redd[32];
-    const double tau0 = c.tau0, vtop = s_redd[33];
+    c.kkeep = kkeep;
+    c.kext = kext;
     const int nitems = n + s_redi[22] * c.nL;
     const bool cached = nitems <= kIPT * kSearchThreads;  // else: recompute the candidates in every pass
     // ---- 3. the candidates' keys and how many they are
@@ -470,7 +595,8 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
 #pragma unroll
     for (int o = kSearchWarps / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     // bounds of the keys, known without looking at them: (key of tau0 .. key of vtop]
-    const u64 kmax = okey(vtop), kmin = tau0 > ninf ? okey(tau0) : 1ull;
+    // with a full beam no candidate is below the worst kept total (key kt0), nor below the second-stage bound
+    const u64 kmax = ktop, kmin = tau0 > ninf ? (kfloor > kt0 ? kfloor : kt0) : kfin;
     BEAM_TICK(2);
     // ---- 4. threshold of the best W: admit k >= F1, and among k == F1 (tie_mode) those with k2 >= F2
     u64 F1 = 1, F2 = 0;
@@ -758,11 +884,18 @@ int ctc_beam_search(const float* logits, int T, int B, int C, long long st_t, lo
               "shared memory needed, 204800 available)", W, C, kSearchThreads, smem);
     return NASR_ERR_UNSUPPORTED;
   }
-  NASR_CUDA(cudaFuncSetAttribute(ctc_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const bool stage2 = C > kStage2MinC;
+  NASR_CUDA(cudaFuncSetAttribute(stage2 ? ctc_beam_kernel<true> : ctc_beam_kernel<false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   int2* nodes = reinterpret_cast<int2*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-  ctc_beam_kernel<<<B, kBeamThreads, smem, stream>>>(logits, T, B, C, st_t, st_b, seq_len, blank, W, P,
-                                                     merge_repeated, hyp, hyp_len, log_prob, nodes, g_debug_prof,
-                                                     L);
+  if (stage2)
+    ctc_beam_kernel<true><<<B, kBeamThreads, smem, stream>>>(logits, T, B, C, st_t, st_b, seq_len, blank, W, P,
+                                                             merge_repeated, hyp, hyp_len, log_prob, nodes,
+                                                             g_debug_prof, L);
+  else
+    ctc_beam_kernel<false><<<B, kBeamThreads, smem, stream>>>(logits, T, B, C, st_t, st_b, seq_len, blank, W, P,
+                                                              merge_repeated, hyp, hyp_len, log_prob, nodes,
+                                                              g_debug_prof, L);
   count_launch();
   NASR_CUDA(cudaGetLastError());
   return NASR_OK;
