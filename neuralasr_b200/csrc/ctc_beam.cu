@@ -4,21 +4,24 @@
 // the decoder the reference's create_model actually runs in every train step (networks/tfnetwork.py:62,64);
 // semantics per oracle/beam_oracle.py (TF 1.x core/util/ctc/ctc_beam_search.h restated).
 //
-// One CTA per utterance walks the frames.  Per frame:
-//   1. log-softmax of the logits row in fp64 (next row prefetched into registers meanwhile);
-//   2. every active prefix keeps itself: label' = (LSE(label, parent term) if its parent prefix is active) + lp[last],
-//      blank' = total + lp[blank];
-//   3. candidates = those W updated prefixes + every extension (prefix b, label l) that is not already an active
-//      prefix: W*(C-1) scores  lp[l] + (l == last(b) ? blank(b) : total(b)).  They are never materialised: each
-//      selection pass recomputes them from two shared-memory tables (3800 candidates at W=100, C=38);
-//   4. the best W by (score, existing-before-new, prefix hash) are found with an MSB-first radix select over the
-//      order-preserving 64-bit image of the fp64 score (11-bit digits, histogram in shared memory, starting at
-//      the first bit where the candidates differ; exact ties go on through the hash), after TF's own pruning
-//      (a full beam admits only extensions that beat its worst kept prefix, so prefixes whose best possible
-//      extension cannot are skipped wholesale);
-//   5. survivors are compacted into the other beam buffer; new prefixes get a node (parent node, label) in a
-//      per-utterance trie in the workspace; each prefix finds its parent's slot by hash, and each parent gets
-//      the bit set of labels whose extension is already active.
+// One CTA per utterance walks the frames: 16 search warps and one producer warp that has the log-softmax (fp64) of
+// the next frame's row ready when the search of the current one ends.  Per frame, phases separated by a named
+// barrier of the search warps:
+//   1. update: one thread per active prefix: blank' = total + lp[blank], label' = LSE(label + lp[last], parent term
+//      + lp[last]) if its parent prefix is active (slot kept per prefix), total' as one three-way log-sum-exp;
+//   2. lists: a full beam admits only scores above its worst kept total tau0 (TF's candidate test), so prefixes with
+//      total + max lp <= tau0 and labels with lp + max total <= tau0 are dropped and the rest compacted by ballot;
+//      wide vocabularies first tighten tau0 to the W-th best of {kept prefixes, extensions by the two best labels};
+//   3. keys: candidates = kept prefixes + live prefixes x live labels that are not already active prefixes (bit set
+//      per prefix): lp[l] + (l == last(b) ? blank(b) : total(b)).  Each search thread evaluates up to 8 and keeps the
+//      order-preserving 64-bit image of the fp64 score in registers (more than 4096: recomputed in every pass);
+//   4. select: MSB-first radix select of the W-th best key (11-bit digits, shared-memory histogram, from the first
+//      bit in which the known bounds differ); exact ties go on through (kept-before-new, prefix hash);
+//   5. admit: keys at or above the threshold -> a list (one shared atomic per warp);
+//   6. build: one thread per admitted candidate writes its entry of the other beam buffer; a new prefix gets node
+//      1 + t*W + slot = (parent node, label) of a per-utterance trie in the workspace and enters a small hash table;
+//   7. parents: each entry's parent slot in the new beam (old->new slot map, or the hash table when the parent has
+//      just re-entered the beam) and the per-parent bit sets of active extensions.
 // Prefix identity is a 64-bit hash chain (root constant, child = mix(parent + K*(label+1))) plus the prefix length:
 // two different prefixes of equal length colliding inside one beam is a 2^-64-per-pair event and would merge them.
 // After the last frame the top_paths best prefixes are read back through the trie, repeats collapsed when
@@ -43,7 +46,10 @@ constexpr int kSearchWarps = kSearchThreads / 32;
 constexpr int kBeamThreads = kSearchThreads + 32;   // + one warp that prepares the next frame's log-softmax
 constexpr int kIPT = 4096 / kSearchThreads;         // candidate keys a search thread keeps in registers
 constexpr int kBins = 2048;                         // 11-bit digits
-constexpr int kStage2MinC = 64;                     // vocabularies wider than this get the second-stage bound
+#ifndef NASR_BEAM_STAGE2_MINC
+#define NASR_BEAM_STAGE2_MINC 64
+#endif
+constexpr int kStage2MinC = NASR_BEAM_STAGE2_MINC;  // vocabularies wider than this get the second-stage bound
 constexpr int kBinsPerThread = kBins / kSearchThreads;
 constexpr u64 kRootHash = 0x243f6a8885a308d3ull;
 
