@@ -190,7 +190,13 @@ def run_ours(args, w, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    saved_stdout = None
     if world > 1:
+        # stdout carries the one JSON line only: NCCL prints its "NCCL version ..." banner to fd 1 when the
+        # communicator comes up, so fd 1 points at stderr until the warm-up (first collective included) is over
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     T, B, C = w["T"], w["B"], w["C"]
@@ -224,6 +230,12 @@ def run_ours(args, w, rank, world, local_rank):
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()
+    if saved_stdout is not None:
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sampler = ClockSampler(local_rank)
     if world > 1:
