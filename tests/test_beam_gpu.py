@@ -265,3 +265,36 @@ def test_kernel_reproduces_the_golden_fixture():
             assert abs(lp[0, j] - g["logp%d" % i][j]) <= 1e-6 * max(1.0, abs(g["logp%d" % i][j]))
             checked += 1
     assert checked >= 40
+
+
+@pytest.mark.parametrize("W", [1, 2, 3])
+def test_narrowest_beams(W):
+    rng = np.random.default_rng(50 + W)
+    x = (rng.normal(size=(30, 3, 6)) * 1.5).astype(np.float32)
+    _check_c(x, np.array([30, 21, 9], np.int32), W=W, P=W, merge=False)
+
+
+def test_blank_elsewhere_than_last_class():
+    from neuralasr_b200.networks import common
+    rng = np.random.default_rng(53)
+    x = (rng.normal(size=(25, 2, 7)) * 2).astype(np.float32)
+    seq = np.array([25, 14], np.int32)
+    for blank in (0, 3):
+        dec, lp = common.beam_decoding(torch.from_numpy(x).cuda(), seq, beam_width=20, blank=blank)
+        hyp, hl = dec[0].hyp.cpu().numpy(), dec[0].hyp_len.cpu().numpy()
+        for b in range(2):
+            want = bo.beam_search_one(x[: seq[b], b].astype(np.float64), 20, True, blank=blank)
+            assert hyp[b, : hl[b]].tolist() == want[0]
+            assert abs(lp[b, 0].item() - want[1]) <= 1e-6 * max(1.0, abs(want[1]))
+
+
+def test_wide_vocabulary_ties_through_the_second_stage_bound():
+    # C > 64 runs ctc_beam_kernel<true>: exact ties (uniform rows, and rows with a few equal peaks) must come out as
+    # in the oracle whatever the second-stage bound prunes
+    x = np.zeros((6, 2, 100), np.float32)
+    _check_c(x, np.array([6, 4], np.int32), W=10, P=4, merge=False)
+    x[:, :, [3, 17, 64]] = 5.0
+    x[2:, 0, 99] = 5.0
+    _check_c(x, np.array([6, 6], np.int32), W=10, P=4, merge=False)
+    rng = np.random.default_rng(54)
+    _check_c((rng.normal(size=(50, 3, 65)) * 3).astype(np.float32), np.array([50, 50, 31], np.int32), W=100, P=2)
