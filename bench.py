@@ -340,6 +340,38 @@ def run_ours(args, w, rank, world, local_rank):
                 "cpu_port": {"frames_per_s": float(seq[:n_utt].sum()) / cpu_s, "cores": c_oracle.num_threads(),
                              "sample": "%d utterances of the same batch, oracle/beam_oracle.c" % n_utt}}
 
+    # ---- library baseline on the same GPU: torch's CUDA log_softmax + ctc_loss + backward (a number for context,
+    #      and an independent check of the mean loss), rank 0 only
+    lib_base = None
+    if rank == 0:
+        try:
+            xt = logits[0].detach().clone().requires_grad_(True)
+            tgt = torch.from_numpy(vals.astype(np.int64)).to(dev)
+            tl = torch.from_numpy(lens.astype(np.int64)).to(dev)
+            il = torch.from_numpy(seq.astype(np.int64)).to(dev)
+
+            def torch_step():
+                xt.grad = None
+                lsm = torch.log_softmax(xt, dim=2)
+                l_b = torch.nn.functional.ctc_loss(lsm, tgt, il, tl, blank=C - 1, reduction="none", zero_infinity=False)
+                l_b.mean().backward()
+                return l_b
+
+            for _ in range(3):
+                l_b = torch_step()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(10):
+                l_b = torch_step()
+            b.record()
+            torch.cuda.synchronize()
+            lib_base = {"what": "torch log_softmax + nn.functional.ctc_loss (CUDA) + backward, same batch",
+                        "ms_per_step": a.elapsed_time(b) / 10, "mean_loss": float(l_b.mean().item())}
+            del xt, l_b
+        except Exception as e:  # a context number, never a reason to fail the bench
+            lib_base = {"unavailable": repr(e)[:200]}
+
     if rank == 0:
         peak, peak_kind = hbm_peak()
         k_ms = statistics.mean(kern_ms)
@@ -375,6 +407,7 @@ def run_ours(args, w, rank, world, local_rank):
             "decode_ler_ms": dec_ms,
             "beam_search": beam,
             "e2e_train_step": train_step,
+            "library_baseline": lib_base,
         }))
     if world > 1:
         dist.destroy_process_group()
