@@ -16,6 +16,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _library_present():
+    """A fresh checkout has no built artefacts (they are git-ignored): compile libnasr_ctc.so for sm_100a once if it
+    is missing (nvcc cross-compiles without a GPU).  Never a fallback: the tests still go through the library."""
+    from neuralasr_b200 import _build
+    if not os.path.exists(_build.LIB_PATH):
+        _build.build_library(force=True)
+
+
 def load_golden(name):
     with np.load(os.path.join(GOLDEN_DIR, name + ".npz")) as z:
         return {k: z[k] for k in z.files}
