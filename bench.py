@@ -198,6 +198,9 @@ def run_ours(args, w, rank, world, local_rank):
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
+    from neuralasr_b200 import _build
+    if not os.path.exists(_build.LIB_PATH) and world == 1:
+        _build.build_library(force=True)   # fresh checkout: built artefacts are git-ignored (N > 1: run build() first)
     lib = _lib.load()
     T, B, C = w["T"], w["B"], w["C"]
     x, vals, offs, seq = synth(w, 1234 + rank)
