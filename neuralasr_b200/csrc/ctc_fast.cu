@@ -94,6 +94,8 @@ __host__ __device__ constexpr int row_yoff(int cmax) { return (cmax + 1) * 4; }
 // record does not grow with C), there is no raw-logits ring, every producer warp owns one row of C floats
 // (rowbuf), and the gradient warps get a table of the distinct classes of the transcript (dtab).
 constexpr int kWideProducers = 8;
+constexpr int kWideRegC = 1024;   // widest row a producer warp holds in registers (32 floats per lane)
+constexpr int kWideMaxC = 8192;   // widest row of the wide variant: beyond kWideRegC the producers stream the row
 __host__ __device__ inline Smem smem_layout(int NL, int cmax, int wideC = 0) {
   Smem s;
   const int Lcap = NL * 32;
@@ -103,8 +105,9 @@ __host__ __device__ inline Smem smem_layout(int NL, int cmax, int wideC = 0) {
   size_t o = 0;
   s.rows = o;      o = al16(o + (size_t)2 * 4 * KC * rowbytes);              // [side][4 slots][KC] records
   s.raw = o;       o = al16(o + (wideC ? 0 : (size_t)2 * 4 * KC * cmax * 4)); // [side][4 slots][KC][cmax] raw logits
-  s.rowbuf = o;    o = al16(o + (wideC ? (size_t)kWideProducers * wideC * 4 : 0));
-  s.stage = o;     o = al16(o + (wideC ? (size_t)kWideProducers * 2 * wideC * 4 : 0));  // raw rows in flight
+  const int stagedC = wideC <= kWideRegC ? wideC : 0;  // streamed rows are never staged
+  s.rowbuf = o;    o = al16(o + (size_t)kWideProducers * stagedC * 4);
+  s.stage = o;     o = al16(o + (size_t)kWideProducers * 2 * stagedC * 4);  // raw rows in flight
   s.dtab = o;      o = al16(o + (wideC ? (size_t)3 * Lcap * 4 : 0));
   s.obuf = o;      o = al16(o + (size_t)2 * 2 * KC * NL * 32 * 4);           // [side][2][KC][NL][32] high words
   s.gbuf = o;      o = al16(o + (size_t)2 * 2 * KC * s.gstride * 4);         // [side][2][KC][gstride] posteriors
@@ -497,6 +500,86 @@ __device__ __forceinline__ float wide_row(const WideRow& r, float* rowbuf, uint3
   return __logf(nbl) - __logf(ssum);
 }
 
+// Rows wider than kWideRegC (C % 4 == 0, C <= kWideMaxC): the producer warp streams the row from global memory in
+// slices of 1024 classes instead of holding it -- one pass for the maximum, one for the sum of e^(x-m) and, in
+// phase 2, one that writes the provisional gradient; the second and third pass find the row in L2 (a row is at
+// most 32 KB).  The emissions of the transcript's classes are gathered straight from the row.  Same arithmetic as
+// wide_row (ex2.approx on fma(x, log2 e, -m log2 e)), so the two produce the same records for the same row.
+template <int NL>
+__device__ __forceinline__ float huge_row(const float* __restrict__ x, uint32_t* rec, const int (&pcls)[NL],
+                                          float* grow, float gs, int C, int blank, int lane, int& alarm) {
+  const float kL2E = 1.4426950408889634f;
+  const float4 ninf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  float m = -INFINITY;
+  for (int c0 = 0; c0 < C; c0 += 1024) {
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int c = c0 + 4 * lane + 128 * i;
+      v[i] = c < C ? __ldg(reinterpret_cast<const float4*>(x + c)) : ninf4;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) m = fmaxf(m, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+  }
+  m = warp_max(m);
+  const float ml2 = m * kL2E;
+  float ssum = 0.f;
+  for (int c0 = 0; c0 < C; c0 += 1024) {
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int c = c0 + 4 * lane + 128 * i;
+      v[i] = c < C ? __ldg(reinterpret_cast<const float4*>(x + c)) : ninf4;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      ssum += (ex2_approx(fmaf(v[i].x, kL2E, -ml2)) + ex2_approx(fmaf(v[i].y, kL2E, -ml2))) +
+              (ex2_approx(fmaf(v[i].z, kL2E, -ml2)) + ex2_approx(fmaf(v[i].w, kL2E, -ml2)));
+  }
+  ssum = warp_sum(ssum);
+  const float nbl = ex2_approx(fmaf(__ldg(x + blank), kL2E, -ml2));
+  const float inv_nb = __fdividef(1.0f, nbl);
+  bool bad = !(nbl >= 1.0e-38f && ssum <= 3.0e38f);
+#pragma unroll
+  for (int k = 0; k < NL; k++) {
+    uint32_t w = 0u;
+    if (pcls[k] >= 0) {
+      const float rr = ex2_approx(fmaf(__ldg(x + pcls[k]), kL2E, -ml2)) * inv_nb;
+      bad |= !(rr >= 1.1754944e-38f && rr <= 1.0e38f);   // only the transcript's classes have to stay normal
+      w = ((__float_as_uint(rr) + 4u) >> 3) + (896u << 20);
+    }
+    rec[k * 32 + lane] = w;
+  }
+  if (bad) alarm |= AL_EMISSION;
+  if (grow) {
+    const float sc = gs * __fdividef(1.0f, ssum);
+    for (int c0 = 0; c0 < C; c0 += 1024) {
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int c = c0 + 4 * lane + 128 * i;
+        v[i] = c < C ? __ldg(reinterpret_cast<const float4*>(x + c)) : ninf4;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int c = c0 + 4 * lane + 128 * i;
+        if (c < C)
+          __stcg(reinterpret_cast<float4*>(grow + c),
+                 make_float4(ex2_approx(fmaf(v[i].x, kL2E, -ml2)) * sc, ex2_approx(fmaf(v[i].y, kL2E, -ml2)) * sc,
+                             ex2_approx(fmaf(v[i].z, kL2E, -ml2)) * sc, ex2_approx(fmaf(v[i].w, kL2E, -ml2)) * sc));
+      }
+    }
+  }
+  __syncwarp();
+  return __logf(nbl) - __logf(ssum);
+}
+
+// pull a row towards L2 (one 128-byte line per lane and step)
+__device__ __forceinline__ void l2_prefetch_row(const float* x, int C, int lane) {
+  const char* pch = reinterpret_cast<const char*>(x);
+  for (int o = lane * 128; o < C * 4; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pch + o));
+}
+
 template <int NL>
 __device__ __forceinline__ uint32_t* ckpt_ptr(const Params& p, int b, int d, int c) {
   return p.ckpt + (((size_t)b * 2 + d) * p.maxch + c) * (size_t)((2 * NL + 1) * 32);
@@ -516,14 +599,14 @@ __device__ __forceinline__ uint32_t gcell(int pos) {
 // four schedulers.
 __device__ int g_sm_arrivals[1024];
 
-// EPL = 0 instantiates the wide-vocabulary variant (64 < C <= 1024, C % 4 == 0): 16 warps, one CTA per SM.
+// EPL = 0 instantiates the wide-vocabulary variant (64 < C <= 8192, C % 4 == 0): 16 warps, one CTA per SM.
 template <int NL, int EPL>
 __global__ void __launch_bounds__((EPL ? NTHREADS : NTHREADS_WIDE), ((EPL && NL <= 8) ? 2 : 1))
 ctc_fast_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr bool WIDE = EPL == 0;
   constexpr int NT = WIDE ? NTHREADS_WIDE : NTHREADS;
-  constexpr int CMAX = WIDE ? 1024 : 8 * EPL;
+  constexpr int CMAX = WIDE ? kWideMaxC : 8 * EPL;
   constexpr int ROWB = WIDE ? NL * 32 * 4 : row_bytes(CMAX);
   constexpr int YOFF = row_yoff(CMAX);
   const Smem sl = smem_layout(NL, CMAX, WIDE ? p.C : 0);
@@ -886,7 +969,7 @@ ctc_fast_kernel(const Params p) {
       // recursion needs it; the row that follows is requested while the current one is processed, and the
       // rows of two chunks later are prefetched into L2.
       const int pj = (warp - 8) >> 1;
-      float* rowbuf = s_rowbuf + (size_t)(warp - 8) * C;
+      float* rowbuf = s_rowbuf + (size_t)(warp - 8) * min(C, kWideRegC);
       int pcls[NL];
       {
         const int pad = N - L - 1;
@@ -902,15 +985,16 @@ ctc_fast_kernel(const Params p) {
         }
       }
       double lsum = 0.0;
-      float* stA = s_stage + (size_t)(warp - 8) * 2 * C;   // staging rows of this warp: row pj and row pj+4
-      float* stB = stA + C;
+      float* stA = s_stage + (size_t)(warp - 8) * 2 * min(C, kWideRegC);   // staging rows of this warp: row pj and row pj+4
+      float* stB = stA + min(C, kWideRegC);
       auto row_ptr = [&](const Chunk& ci, int f) {
         const int ff = min(f, ci.len - 1);
         const int t = d ? ci.base - ff : ci.base + ff;
         return p.logits + (size_t)t * p.st_t + (size_t)b * p.st_b;
       };
       auto wanted = [&](const Chunk& ci) { return ci.phase != 0 && (ci.phase == 1 || want_grad); };
-      {
+      const bool streamed = C > kWideRegC;  // rows too wide for registers: streamed from global / L2 (huge_row)
+      if (!streamed) {
         const Chunk c0 = chunk_at(S, d, IFIRST + 2);
         if (wanted(c0)) {
           wide_issue(stA, row_ptr(c0, pj), C, lane);
@@ -925,6 +1009,26 @@ ctc_fast_kernel(const Params p) {
         const Chunk cn = chunk_at(S, d, I + 3);
         const bool on = wanted(ci), onn = wanted(cn);
         uint32_t* recs = reinterpret_cast<uint32_t*>(s_rows + (size_t)(d * 4 + ((I + 2) & 3)) * KC * rowbytes);
+        if (streamed) {
+          if (onn) {  // next iteration's two rows on their way to L2 while this iteration's are processed
+            l2_prefetch_row(row_ptr(cn, pj), C, lane);
+            l2_prefetch_row(row_ptr(cn, pj + 4), C, lane);
+          }
+#pragma unroll 1
+          for (int h = 0; h < 2; h++) {
+            const int f = pj + 4 * h;
+            if (on && f < ci.len) {
+              const int t = d ? ci.base - f : ci.base + f;
+              float* grow = (ci.phase == 2) ? gbase + (size_t)t * rstride : nullptr;
+              const float ly = huge_row<NL>(row_ptr(ci, f), recs + f * N, pcls, grow, gs, C, blank, lane, alarm);
+              if (ci.phase == 1) lsum += (double)ly;
+            }
+          }
+          if (lane == 0) s_psum[warp - 8] = lsum;
+          NASR_PROF_END();
+          cta_sync();
+          continue;
+        }
         cp_async_wait<0>();   // the rows of this iteration were requested one iteration ago
         __syncwarp();
         WideRow r;
@@ -1132,7 +1236,7 @@ int pick_nl(int Lmax) {
   return 0;
 }
 
-bool is_wide(int C) { return C > 64 && C <= 1024 && (C & 3) == 0; }
+bool is_wide(int C) { return C > 64 && C <= fast::kWideMaxC && (C & 3) == 0; }
 
 // the wide-vocabulary variant is instantiated for these slot counts only (L <= 126, 158, 222)
 int pick_nl_wide(int Lmax) {
@@ -1178,6 +1282,8 @@ static int max_chunks(int T) {
   const int half = (T + 2 * fast::KC - 1) / (2 * fast::KC) + 2;
   return g_debug_split ? (T + fast::KC - 1) / fast::KC + 2 : half;
 }
+
+bool ctc_fast_is_wide(int C) { return is_wide(C); }
 
 bool ctc_fast_supported(int T, int C, int Lmax) {
   if (T < 2 * fast::KC) return false;

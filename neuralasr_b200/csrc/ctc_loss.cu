@@ -76,8 +76,8 @@ bool make_plan(int T, int B, int C, int Lmax, Plan* p) {
   int U = 2 * Lmax + 1;
   p->Upad = (U + 1) & ~1;
   p->Cpad = (C + 3) & ~3;
-  p->K = 16;
-  if (smem_layout(p->K, p->Upad, p->Cpad, Lmax).total > kSmemBudget) p->K = 8;
+  p->K = 16;  // frames per segment: as many as fit (a segment holds K softmax rows of Cpad floats)
+  while (p->K > 2 && smem_layout(p->K, p->Upad, p->Cpad, Lmax).total > kSmemBudget) p->K >>= 1;
   SmemLayout s = smem_layout(p->K, p->Upad, p->Cpad, Lmax);
   if (s.total > kSmemBudget) return false;
   p->smem = s.total;
@@ -480,6 +480,7 @@ __global__ void __launch_bounds__(512) ctc_robust_kernel(const Params p) {
 
 // implemented in ctc_fast.cu
 bool ctc_fast_supported(int T, int C, int Lmax);
+bool ctc_fast_is_wide(int C);
 size_t ctc_fast_workspace_bytes(int T, int B, int C, int Lmax);
 int ctc_fast_launch(const float* logits, int T, int B, int C, long long st_t, long long st_b,
                     const int32_t* label_values, const int32_t* label_offsets, int Lmax, const int32_t* seq_len, int blank, float* loss,
@@ -532,7 +533,10 @@ int ctc_loss_grad(const float* logits, int T, int B, int C, long long st_t, long
   void* fast_ckpt = reinterpret_cast<void*>(base);
   base += align256(ctc_fast_workspace_bytes(T, B, C, Lmax));
 
-  const bool use_fast = g_debug_path != 1 && ctc_fast_supported(T, C, Lmax);
+  // the wide-vocabulary variant moves rows with 16-byte accesses: logits and grad rows must be 16-byte aligned
+  const bool aligned = !ctc_fast_is_wide(C) || ((((uintptr_t)logits | (uintptr_t)grad) & 15) == 0 && (st_t & 3) == 0 &&
+                                                (st_b & 3) == 0);
+  const bool use_fast = g_debug_path != 1 && aligned && ctc_fast_supported(T, C, Lmax);
   if (use_fast) {
     int rc = ctc_fast_launch(logits, T, B, C, st_t, st_b, label_values, label_offsets, Lmax, seq_len, blank, loss, grad,
                              grad_loss, status, retry, fast_ckpt, stream);

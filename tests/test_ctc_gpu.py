@@ -245,6 +245,10 @@ def _flags(common, B):
     dict(T=200, B=6, C=1024, Lmax=40, mode="ragged"),                 # wide-vocabulary variant (BASELINE cfg5 classes)
     dict(T=400, B=4, C=132, Lmax=150, mode="ragged"),                 # wide variant, C not a multiple of 128
     dict(T=300, B=3, C=512, Lmax=200, mode="full", empty_row=False),
+    dict(T=120, B=3, C=1028, Lmax=30, mode="ragged"),                 # just past the register-held row: streamed rows
+    dict(T=150, B=4, C=3000, Lmax=60, mode="ragged", peaky=True),     # the reference's trigram vocabularies
+    dict(T=90, B=2, C=6000, Lmax=20, mode="ragged"),                  # retry kernel plans 4-frame segments here
+    dict(T=70, B=2, C=8192, Lmax=12, mode="ragged"),                  # widest row the throughput kernel takes
 ])
 def test_each_kernel_alone_matches_oracle(common, debug_paths, kw):
     g = make_batch(4242, **kw)
@@ -425,3 +429,16 @@ def test_step_functions_follow_the_reference_conventions(common):
     m = common.label_error_rate(dense_to_sparse(pred), dense_to_sparse(lab1))
     want = [o.levenshtein((hv[ho[b]:ho[b + 1]][:40]).tolist(), g["labels_dense"][b].tolist()) for b in range(5)]
     assert m.distances.cpu().numpy().tolist() == want
+
+
+def test_unaligned_wide_rows_fall_back_to_the_robust_kernel(common):
+    """The wide-vocabulary variant moves rows with 16-byte accesses; a view whose rows are not 16-byte aligned must
+    still be answered correctly (by the robust kernel), never faulted on."""
+    g = make_batch(77, T=60, B=3, C=132, Lmax=12, mode="ragged")
+    big = torch.zeros((60, 3, 135), device="cuda")
+    view = big[:, :, 1:133]                       # class axis dense, rows start 4 bytes off a 16-byte boundary
+    view.copy_(torch.from_numpy(g["logits"]))
+    want_loss, want_grad, want_status = c_oracle.ctc_loss_grad(
+        g["logits"], g["label_values"], g["label_offsets"], g["seq_len"], precision="f64")
+    loss, grad, status = common.ctc_loss_and_grad(view, _triple(g), g["seq_len"])
+    _assert_loss_grad(loss.cpu().numpy(), grad.cpu().numpy(), status.cpu().numpy(), want_loss, want_grad, want_status)

@@ -1,0 +1,45 @@
+"""The reference's own 16000sr config uses character trigrams (label_context=1): C in the thousands, B = 8 x 4 GPUs.
+Check parity and time of loss+grad (robust kernel: C > 1024), greedy decode, beam search at such a shape."""
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+sys.path.insert(0, "tests")
+from conftest import make_batch  # noqa: E402
+from neuralasr_b200.networks import common  # noqa: E402
+from oracle import c_oracle  # noqa: E402
+
+for (T, B, C, L) in [(500, 32, 3000, 100), (500, 32, 1024, 100), (500, 32, 4000, 60)]:
+    g = make_batch(7, T, B, C, L, mode="ragged", peaky=True)
+    x = torch.from_numpy(g["logits"]).cuda()
+    lab = common.LabelsCSR(torch.from_numpy(g["label_values"]).cuda(), torch.from_numpy(g["label_offsets"]).cuda(),
+                           L, B)
+    seq = torch.from_numpy(g["seq_len"]).cuda()
+
+    def timed(fn, n=5):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            out = fn()
+        torch.cuda.synchronize()
+        return out, (time.perf_counter() - t0) / n * 1e3
+
+    (loss_b, grad, status), ms_loss = timed(lambda: common.ctc_loss_and_grad(x, lab, seq))
+    (dec, _), ms_greedy = timed(lambda: common.decoding(x, seq))
+    (bdec, blp), ms_beam = timed(lambda: common.beam_decoding(x, seq, beam_width=100), n=2)
+    nb = 4
+    want_loss, want_grad, _ = c_oracle.ctc_loss_grad(g["logits"][:, :nb], g["label_values"][: g["label_offsets"][nb]],
+                                                     g["label_offsets"][: nb + 1], g["seq_len"][:nb], precision="f64")
+    el = np.abs(loss_b[:nb].cpu().numpy() - want_loss).max() / np.abs(want_loss).max()
+    eg = np.abs(grad[:, :nb].cpu().numpy() - want_grad).max()
+    hyp, hl, lp = c_oracle.beam_search(g["logits"][:, :nb], g["seq_len"][:nb], 100, 1, True)
+    same = all(bdec[0].hyp[b, : hl[b, 0]].cpu().tolist() == hyp[b, 0, : hl[b, 0]].tolist() and
+               int(bdec[0].hyp_len[b]) == int(hl[b, 0]) for b in range(nb))
+    print("T=%d B=%d C=%d: loss+grad %.2f ms (rel loss err %.1e, abs grad err %.1e, status %s), greedy %.2f ms, "
+          "beam %.2f ms (first %d utterances == C port: %s)" % (T, B, C, ms_loss, el, eg,
+                                                               sorted(set(status.cpu().tolist())), ms_greedy, ms_beam,
+                                                               nb, same), flush=True)
