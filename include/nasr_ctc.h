@@ -130,7 +130,8 @@ int nasr_ctc_loss_grad_dl(const DLTensor* logits, const DLTensor* label_values,
  * Greedy decode.  Replaces tf.nn.ctc_greedy_decoder(logits, seq_len, merge_repeated) — the `decoding`
  * of the north star, networks/tfnetwork.py:63.
  *   hyp            int64[B, T]  row b holds hyp_len[b] label ids (first-index argmax of the RAW logits
- *                               per frame, blank dropped, repeats merged); the rest of the row is untouched
+ *                               per frame, blank dropped, repeats merged); the rest of the row is undefined
+ *                               (wide rows use it as scratch)
  *   hyp_len        int32[B]
  *   neg_sum_logits float32[B]   -(sum over frames of the max logit)   (TF's second output, [B,1])
  * Frames t >= seq_len[b] are ignored; seq_len is clamped to [0, T].

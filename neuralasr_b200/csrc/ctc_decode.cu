@@ -16,11 +16,12 @@ constexpr int kDecodeChunk = 2048;  // frames staged per pass (argmax ids + max 
 // One CTA per utterance.  Phase 1: one warp per frame finds the first-index argmax of the raw logits
 // (coalesced row read).  Phase 2: warp 0 collapses (drop blank, merge repeats) with ballot compaction
 // while lane 0 of warp 1 accumulates -max in frame order.
+// packed != 0: phase 1 was done by greedy_argmax_wide_kernel, which left (max logit bits << 32 | class id) of frame
+// t in hyp[b][t]; the collapse then compacts the row in place (it never writes past what it has read).
 __global__ void __launch_bounds__(kDecodeThreads)
 greedy_decode_kernel(const float* __restrict__ logits, int T, int B, int C, long long st_t, long long st_b,
                      const int32_t* __restrict__ seq_len, int blank, int merge_repeated,
-                     int64_t* __restrict__ hyp, int32_t* __restrict__ hyp_len,
-                     float* __restrict__ neg_sum_logits) {
+                     int64_t* hyp, int32_t* __restrict__ hyp_len, float* __restrict__ neg_sum_logits, int packed) {
   __shared__ int s_id[kDecodeChunk];
   __shared__ float s_mx[kDecodeChunk];
   const int b = blockIdx.x;
@@ -32,7 +33,13 @@ greedy_decode_kernel(const float* __restrict__ logits, int T, int B, int C, long
   float acc = 0.f;     // warp 1 lane 0
   for (int base = 0; base < Tb; base += kDecodeChunk) {
     const int n = min(kDecodeChunk, Tb - base);
-    if (C <= 64) {
+    if (packed) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long v = (unsigned long long)__ldcg(hyp + (size_t)b * T + base + i);
+        s_id[i] = (int)(unsigned)(v & 0xffffffffull);
+        s_mx[i] = __uint_as_float((unsigned)(v >> 32));
+      }
+    } else if (C <= 64) {
       // narrow rows (a row is 152 B at C=38): 8 lanes per frame, 4 frames per warp instruction and 4 such
       // groups in flight, so that 32 independent loads per lane cover the DRAM latency
       const int sub = lane & 7, rl = lane >> 3;
@@ -120,6 +127,70 @@ greedy_decode_kernel(const float* __restrict__ logits, int T, int B, int C, long
   }
   if (warp == 0 && lane == 0) hyp_len[b] = count;
   if (warp == 1 && lane == 0 && neg_sum_logits) neg_sum_logits[b] = acc;
+}
+
+// Wide rows (C > 64): the arg-max phase of the greedy decoder spread over gridDim.x CTAs per utterance, because one
+// CTA per utterance cannot pull a batch of few, wide utterances through one SM each (B=32, C=3000: 192 MB).
+// One warp per frame, 16-byte loads when the rows are 16-byte aligned (vec4), four loads in flight per lane;
+// first-index arg-max like Eigen's maxCoeff; the result goes to hyp[b][t] as (max bits << 32 | id).
+__global__ void __launch_bounds__(kDecodeThreads)
+greedy_argmax_wide_kernel(const float* __restrict__ logits, int T, int C, long long st_t, long long st_b,
+                          const int32_t* __restrict__ seq_len, int frames_per_cta, int vec4, int64_t* hyp) {
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  int Tb = seq_len[b];
+  Tb = max(0, min(T, Tb));
+  const int t0 = blockIdx.x * frames_per_cta, t1 = min(Tb, t0 + frames_per_cta);
+  for (int t = t0 + warp; t < t1; t += nw) {
+    const float* x = logits + (size_t)t * st_t + (size_t)b * st_b;
+    float m = -INFINITY;
+    int am = 0x7fffffff;
+    if (vec4) {
+      for (int c0 = 4 * lane; c0 < C; c0 += 4 * 128) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int c = c0 + 128 * u;
+          v[u] = c < C ? __ldg(reinterpret_cast<const float4*>(x + c))
+                       : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int c = c0 + 128 * u;
+          const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+            if (c + q < C && (am == 0x7fffffff || e[q] > m)) {  // strict '>' keeps the earliest index within a lane
+              m = e[q];
+              am = c + q;
+            }
+        }
+      }
+    } else {
+      for (int c0 = lane; c0 < C; c0 += 4 * 32) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = c0 + 32 * u < C ? __ldg(x + c0 + 32 * u) : -INFINITY;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (c0 + 32 * u < C && (am == 0x7fffffff || v[u] > m)) {
+            m = v[u];
+            am = c0 + 32 * u;
+          }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, m, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+      if (om > m || (om == m && oa < am)) {
+        m = om;
+        am = oa;
+      }
+    }
+    if (lane == 0)
+      hyp[(size_t)b * T + t] = (int64_t)(((unsigned long long)__float_as_uint(m) << 32) | (unsigned)am);
+  }
 }
 
 // One warp per utterance.  Fast path: Myers' bit-vector algorithm in its block form -- lane w owns bits
@@ -356,8 +427,19 @@ int greedy_decode(const float* logits, int T, int B, int C, long long st_t, long
   if (B == 0) return NASR_OK;
   NASR_CHECK_ARG((logits || T == 0) && seq_len && hyp_len && (hyp || T == 0),
                  "nasr_ctc_greedy_decode: NULL argument");
+  int packed = 0;
+  if (C > 64 && T > 0) {
+    // wide rows: arg-max over about four CTAs per SM (148 SMs), at least 32 frames each; then the collapse
+    const int splits = max(1, min((592 + B - 1) / B, (T + 31) / 32));
+    const int fpc = (T + splits - 1) / splits;
+    const int vec4 = ((uintptr_t)logits & 15) == 0 && (C & 3) == 0 && (st_t & 3) == 0 && (st_b & 3) == 0;
+    greedy_argmax_wide_kernel<<<dim3((T + fpc - 1) / fpc, B), kDecodeThreads, 0, stream>>>(logits, T, C, st_t, st_b,
+                                                                                         seq_len, fpc, vec4, hyp);
+    count_launch();
+    packed = 1;
+  }
   greedy_decode_kernel<<<B, kDecodeThreads, 0, stream>>>(logits, T, B, C, st_t, st_b, seq_len, blank,
-                                                        merge_repeated, hyp, hyp_len, neg_sum_logits);
+                                                        merge_repeated, hyp, hyp_len, neg_sum_logits, packed);
   count_launch();
   NASR_CUDA(cudaGetLastError());
   return NASR_OK;

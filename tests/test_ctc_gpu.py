@@ -442,3 +442,21 @@ def test_unaligned_wide_rows_fall_back_to_the_robust_kernel(common):
         g["logits"], g["label_values"], g["label_offsets"], g["seq_len"], precision="f64")
     loss, grad, status = common.ctc_loss_and_grad(view, _triple(g), g["seq_len"])
     _assert_loss_grad(loss.cpu().numpy(), grad.cpu().numpy(), status.cpu().numpy(), want_loss, want_grad, want_status)
+
+
+@pytest.mark.parametrize("C", [130, 132, 1024, 3001])
+def test_greedy_decode_wide_rows_first_index_ties(common, C):
+    """Wide rows go through the split arg-max kernel (16-byte loads when aligned, scalar otherwise): decoded ids,
+    lengths and -sum(max logit) must equal the oracle's bit for bit, ties included (the earliest class wins)."""
+    rng = np.random.default_rng(C)
+    T, B = 70, 5
+    x = rng.standard_normal((T, B, C)).astype(np.float32)
+    x[::3, :, 7] = 9.0
+    x[::3, :, C - 2] = 9.0            # two equal maxima in every third frame: class 7 must win
+    x[5:9, 1, C - 1] = 12.0           # a run of blanks
+    seq = np.array([T, 33, 1, 0, 64], np.int32)
+    dec, nsl = common.decoding(torch.from_numpy(x).cuda(), seq)
+    hv, ho, want_nsl = c_oracle.greedy_decode(x, seq)
+    assert np.array_equal(dec.hyp_len.cpu().numpy(), np.diff(ho))
+    assert np.array_equal(dec.values.cpu().numpy(), hv)
+    assert np.array_equal(nsl.cpu().numpy().reshape(-1), want_nsl)
