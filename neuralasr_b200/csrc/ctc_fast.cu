@@ -600,7 +600,8 @@ __device__ __forceinline__ uint32_t gcell(int pos) {
 __device__ int g_sm_arrivals[1024];
 
 // EPL = 0 instantiates the wide-vocabulary variant (64 < C <= 8192, C % 4 == 0): 16 warps, one CTA per SM.
-template <int NL, int EPL>
+// STREAM (wide variant only): rows wider than kWideRegC, streamed by the producers instead of held in registers.
+template <int NL, int EPL, bool STREAM = false>
 __global__ void __launch_bounds__((EPL ? NTHREADS : NTHREADS_WIDE), ((EPL && NL <= 8) ? 2 : 1))
 ctc_fast_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -643,7 +644,8 @@ ctc_fast_kernel(const Params p) {
   const int L = p.lab_offs[b + 1] - l0;
 
   // ---- can this kernel take the utterance? everything unusual goes to the robust kernel -----------
-  int bad = (Tb < 2 * KC) | (Tb > T) | (L < 0) | (L > Lcap) | (C > CMAX) | (WIDE && (C & 3));
+  int bad = (Tb < 2 * KC) | (Tb > T) | (L < 0) | (L > Lcap) | (C > CMAX) | (WIDE && (C & 3)) |
+            (WIDE && (STREAM != (C > kWideRegC)));
   if (tid < 16) {
     if (tid < 8) s_scal[tid] = 0;
     s_psum[tid] = 0.0;
@@ -993,7 +995,7 @@ ctc_fast_kernel(const Params p) {
         return p.logits + (size_t)t * p.st_t + (size_t)b * p.st_b;
       };
       auto wanted = [&](const Chunk& ci) { return ci.phase != 0 && (ci.phase == 1 || want_grad); };
-      const bool streamed = C > kWideRegC;  // rows too wide for registers: streamed from global / L2 (huge_row)
+      constexpr bool streamed = STREAM;  // rows too wide for registers: streamed from global / L2 (huge_row)
       if (!streamed) {
         const Chunk c0 = chunk_at(S, d, IFIRST + 2);
         if (wanted(c0)) {
@@ -1246,12 +1248,12 @@ int pick_nl_wide(int Lmax) {
   return 0;
 }
 
-template <int NL, int EPL>
+template <int NL, int EPL, bool STREAM = false>
 int launch_fast(const fast::Params& p, cudaStream_t stream) {
   const fast::Smem sl = fast::smem_layout(NL, 8 * EPL, EPL ? 0 : p.C);
   static bool attr_set = false;
   if (!attr_set) {
-    NASR_CUDA(cudaFuncSetAttribute(fast::ctc_fast_kernel<NL, EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NASR_CUDA(cudaFuncSetAttribute(fast::ctc_fast_kernel<NL, EPL, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    kMaxSmem));
     attr_set = true;
   }
@@ -1259,7 +1261,7 @@ int launch_fast(const fast::Params& p, cudaStream_t stream) {
     set_error("nasr_ctc: fast kernel shared memory %zu too large", sl.total);
     return NASR_ERR_UNSUPPORTED;
   }
-  fast::ctc_fast_kernel<NL, EPL><<<p.B, EPL ? fast::NTHREADS : fast::NTHREADS_WIDE, sl.total, stream>>>(p);
+  fast::ctc_fast_kernel<NL, EPL, STREAM><<<p.B, EPL ? fast::NTHREADS : fast::NTHREADS_WIDE, sl.total, stream>>>(p);
   count_launch();
   NASR_CUDA(cudaGetLastError());
   return NASR_OK;
@@ -1326,9 +1328,9 @@ int ctc_fast_launch(const float* logits, int T, int B, int C, long long st_t, lo
   p.num_sms = num_sms;
   if (is_wide(C)) {
     switch (pick_nl_wide(Lmax)) {
-      case 4: return launch_fast<4, 0>(p, stream);
-      case 5: return launch_fast<5, 0>(p, stream);
-      case 7: return launch_fast<7, 0>(p, stream);
+      case 4: return C > fast::kWideRegC ? launch_fast<4, 0, true>(p, stream) : launch_fast<4, 0>(p, stream);
+      case 5: return C > fast::kWideRegC ? launch_fast<5, 0, true>(p, stream) : launch_fast<5, 0>(p, stream);
+      case 7: return C > fast::kWideRegC ? launch_fast<7, 0, true>(p, stream) : launch_fast<7, 0>(p, stream);
     }
   }
   switch (pick_nl(Lmax)) {
