@@ -96,7 +96,7 @@ __host__ __device__ constexpr int row_yoff(int cmax) { return (cmax + 1) * 4; }
 constexpr int kWideProducers = 8;
 constexpr int kWideRegC = 1024;   // widest row a producer warp holds in registers (32 floats per lane)
 constexpr int kWideMaxC = 8192;   // widest row of the wide variant: beyond kWideRegC the producers stream the row
-__host__ __device__ inline Smem smem_layout(int NL, int cmax, int wideC = 0) {
+__host__ __device__ inline Smem smem_layout(int NL, int cmax, int wideC = 0, bool stream = false) {
   Smem s;
   const int Lcap = NL * 32;
   const int rowbytes = wideC ? NL * 32 * 4 : row_bytes(cmax);
@@ -105,7 +105,7 @@ __host__ __device__ inline Smem smem_layout(int NL, int cmax, int wideC = 0) {
   size_t o = 0;
   s.rows = o;      o = al16(o + (size_t)2 * 4 * KC * rowbytes);              // [side][4 slots][KC] records
   s.raw = o;       o = al16(o + (wideC ? 0 : (size_t)2 * 4 * KC * cmax * 4)); // [side][4 slots][KC][cmax] raw logits
-  const int stagedC = wideC <= kWideRegC ? wideC : 0;  // streamed rows are never staged
+  const int stagedC = stream ? 0 : wideC;  // streamed rows are never staged
   s.rowbuf = o;    o = al16(o + (size_t)kWideProducers * stagedC * 4);
   s.stage = o;     o = al16(o + (size_t)kWideProducers * 2 * stagedC * 4);  // raw rows in flight
   s.dtab = o;      o = al16(o + (wideC ? (size_t)3 * Lcap * 4 : 0));
@@ -500,36 +500,45 @@ __device__ __forceinline__ float wide_row(const WideRow& r, float* rowbuf, uint3
   return __logf(nbl) - __logf(ssum);
 }
 
-// Rows wider than kWideRegC (C % 4 == 0, C <= kWideMaxC): the producer warp streams the row from global memory in
-// slices of 1024 classes instead of holding it -- one pass for the maximum, one for the sum of e^(x-m) and, in
-// phase 2, one that writes the provisional gradient; the second and third pass find the row in L2 (a row is at
-// most 32 KB).  The emissions of the transcript's classes are gathered straight from the row.  Same arithmetic as
-// wide_row (ex2.approx on fma(x, log2 e, -m log2 e)), so the two produce the same records for the same row.
+// Streamed rows (wide variant, STREAM): rows wider than kWideRegC, or whose length is not a multiple of four, or that
+// are not 16-byte aligned.  The producer warp streams the row from global memory instead of holding it -- one pass
+// for the maximum, one for the sum of e^(x-m) and, in phase 2, one that writes the provisional gradient; the second
+// and third pass find the row in L2 (a row is at most 32 KB).  Up to three scalars are peeled off at either end so
+// that the body moves in aligned 16-byte accesses whatever the row's address (the gradient row has the same
+// misalignment: the host checks that the two base pointers agree modulo 16).  The emissions of the transcript's
+// classes are gathered straight from the row.  Same arithmetic as wide_row (ex2.approx on fma(x, log2 e, -m log2 e)).
 template <int NL>
 __device__ __forceinline__ float huge_row(const float* __restrict__ x, uint32_t* rec, const int (&pcls)[NL],
                                           float* grow, float gs, int C, int blank, int lane, int& alarm) {
   const float kL2E = 1.4426950408889634f;
   const float4 ninf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-  float m = -INFINITY;
-  for (int c0 = 0; c0 < C; c0 += 1024) {
+  const int head = min(C, (int)((4u - (unsigned)(((uintptr_t)x >> 2) & 3u)) & 3u));  // scalars before the boundary
+  const int nv = (C - head) >> 2;                                                   // aligned float4 of the body
+  const int tail0 = head + 4 * nv, ntail = C - tail0;                               // up to three scalars after it
+  const float4* xv = reinterpret_cast<const float4*>(x + head);
+  const bool edge = lane < head || (lane >= 4 && lane - 4 < ntail);                 // lanes 0-2: head, 4-6: tail
+  const int ec = lane < 4 ? lane : tail0 + lane - 4;
+  const float xe = edge ? __ldg(x + ec) : -INFINITY;
+  float m = xe;
+  for (int k0 = 0; k0 < nv; k0 += 256) {
     float4 v[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      const int c = c0 + 4 * lane + 128 * i;
-      v[i] = c < C ? __ldg(reinterpret_cast<const float4*>(x + c)) : ninf4;
+      const int k = k0 + lane + 32 * i;
+      v[i] = k < nv ? __ldg(xv + k) : ninf4;
     }
 #pragma unroll
     for (int i = 0; i < 8; i++) m = fmaxf(m, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
   }
   m = warp_max(m);
   const float ml2 = m * kL2E;
-  float ssum = 0.f;
-  for (int c0 = 0; c0 < C; c0 += 1024) {
+  float ssum = ex2_approx(fmaf(xe, kL2E, -ml2));  // e^(-inf) = 0 for the lanes without an edge element
+  for (int k0 = 0; k0 < nv; k0 += 256) {
     float4 v[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      const int c = c0 + 4 * lane + 128 * i;
-      v[i] = c < C ? __ldg(reinterpret_cast<const float4*>(x + c)) : ninf4;
+      const int k = k0 + lane + 32 * i;
+      v[i] = k < nv ? __ldg(xv + k) : ninf4;
     }
 #pragma unroll
     for (int i = 0; i < 8; i++)
@@ -553,18 +562,20 @@ __device__ __forceinline__ float huge_row(const float* __restrict__ x, uint32_t*
   if (bad) alarm |= AL_EMISSION;
   if (grow) {
     const float sc = gs * __fdividef(1.0f, ssum);
-    for (int c0 = 0; c0 < C; c0 += 1024) {
+    if (edge) __stcg(grow + ec, ex2_approx(fmaf(xe, kL2E, -ml2)) * sc);
+    float4* gv = reinterpret_cast<float4*>(grow + head);
+    for (int k0 = 0; k0 < nv; k0 += 256) {
       float4 v[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) {
-        const int c = c0 + 4 * lane + 128 * i;
-        v[i] = c < C ? __ldg(reinterpret_cast<const float4*>(x + c)) : ninf4;
+        const int k = k0 + lane + 32 * i;
+        v[i] = k < nv ? __ldg(xv + k) : ninf4;
       }
 #pragma unroll
       for (int i = 0; i < 8; i++) {
-        const int c = c0 + 4 * lane + 128 * i;
-        if (c < C)
-          __stcg(reinterpret_cast<float4*>(grow + c),
+        const int k = k0 + lane + 32 * i;
+        if (k < nv)
+          __stcg(gv + k,
                  make_float4(ex2_approx(fmaf(v[i].x, kL2E, -ml2)) * sc, ex2_approx(fmaf(v[i].y, kL2E, -ml2)) * sc,
                              ex2_approx(fmaf(v[i].z, kL2E, -ml2)) * sc, ex2_approx(fmaf(v[i].w, kL2E, -ml2)) * sc));
       }
@@ -599,7 +610,7 @@ __device__ __forceinline__ uint32_t gcell(int pos) {
 // four schedulers.
 __device__ int g_sm_arrivals[1024];
 
-// EPL = 0 instantiates the wide-vocabulary variant (64 < C <= 8192, C % 4 == 0): 16 warps, one CTA per SM.
+// EPL = 0 instantiates the wide-vocabulary variant (64 < C <= 8192): 16 warps, one CTA per SM.
 // STREAM (wide variant only): rows wider than kWideRegC, streamed by the producers instead of held in registers.
 template <int NL, int EPL, bool STREAM = false>
 __global__ void __launch_bounds__((EPL ? NTHREADS : NTHREADS_WIDE), ((EPL && NL <= 8) ? 2 : 1))
@@ -610,7 +621,7 @@ ctc_fast_kernel(const Params p) {
   constexpr int CMAX = WIDE ? kWideMaxC : 8 * EPL;
   constexpr int ROWB = WIDE ? NL * 32 * 4 : row_bytes(CMAX);
   constexpr int YOFF = row_yoff(CMAX);
-  const Smem sl = smem_layout(NL, CMAX, WIDE ? p.C : 0);
+  const Smem sl = smem_layout(NL, CMAX, WIDE ? p.C : 0, STREAM);
   unsigned char* s_rows = smem + sl.rows;
   float* s_raw = reinterpret_cast<float*>(smem + sl.raw);
   float* s_rowbuf = reinterpret_cast<float*>(smem + sl.rowbuf);
@@ -644,8 +655,8 @@ ctc_fast_kernel(const Params p) {
   const int L = p.lab_offs[b + 1] - l0;
 
   // ---- can this kernel take the utterance? everything unusual goes to the robust kernel -----------
-  int bad = (Tb < 2 * KC) | (Tb > T) | (L < 0) | (L > Lcap) | (C > CMAX) | (WIDE && (C & 3)) |
-            (WIDE && (STREAM != (C > kWideRegC)));
+  int bad = (Tb < 2 * KC) | (Tb > T) | (L < 0) | (L > Lcap) | (C > CMAX) |
+            (WIDE && !STREAM && ((C & 3) || C > kWideRegC));  // (the launcher also checks the rows' alignment)
   if (tid < 16) {
     if (tid < 8) s_scal[tid] = 0;
     s_psum[tid] = 0.0;
@@ -971,7 +982,7 @@ ctc_fast_kernel(const Params p) {
       // recursion needs it; the row that follows is requested while the current one is processed, and the
       // rows of two chunks later are prefetched into L2.
       const int pj = (warp - 8) >> 1;
-      float* rowbuf = s_rowbuf + (size_t)(warp - 8) * min(C, kWideRegC);
+      float* rowbuf = s_rowbuf + (size_t)(warp - 8) * (STREAM ? 0 : C);
       int pcls[NL];
       {
         const int pad = N - L - 1;
@@ -987,8 +998,8 @@ ctc_fast_kernel(const Params p) {
         }
       }
       double lsum = 0.0;
-      float* stA = s_stage + (size_t)(warp - 8) * 2 * min(C, kWideRegC);   // staging rows of this warp: row pj and row pj+4
-      float* stB = stA + min(C, kWideRegC);
+      float* stA = s_stage + (size_t)(warp - 8) * 2 * (STREAM ? 0 : C);   // staging rows of this warp: row pj and row pj+4
+      float* stB = stA + (STREAM ? 0 : C);
       auto row_ptr = [&](const Chunk& ci, int f) {
         const int ff = min(f, ci.len - 1);
         const int t = d ? ci.base - ff : ci.base + ff;
@@ -1238,7 +1249,9 @@ int pick_nl(int Lmax) {
   return 0;
 }
 
-bool is_wide(int C) { return C > 64 && C <= fast::kWideMaxC && (C & 3) == 0; }
+bool is_wide(int C) { return C > 64 && C <= fast::kWideMaxC; }
+// shapes only the streaming producers take; aligned narrower rows are held in registers
+bool stream_only(int C) { return C > fast::kWideRegC || (C & 3) != 0; }
 
 // the wide-vocabulary variant is instantiated for these slot counts only (L <= 126, 158, 222)
 int pick_nl_wide(int Lmax) {
@@ -1250,7 +1263,7 @@ int pick_nl_wide(int Lmax) {
 
 template <int NL, int EPL, bool STREAM = false>
 int launch_fast(const fast::Params& p, cudaStream_t stream) {
-  const fast::Smem sl = fast::smem_layout(NL, 8 * EPL, EPL ? 0 : p.C);
+  const fast::Smem sl = fast::smem_layout(NL, 8 * EPL, EPL ? 0 : p.C, STREAM);
   static bool attr_set = false;
   if (!attr_set) {
     NASR_CUDA(cudaFuncSetAttribute(fast::ctc_fast_kernel<NL, EPL, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1291,7 +1304,7 @@ bool ctc_fast_supported(int T, int C, int Lmax) {
   if (T < 2 * fast::KC) return false;
   if (is_wide(C)) {
     const int NL = pick_nl_wide(Lmax);
-    return NL != 0 && fast::smem_layout(NL, 0, C).total <= (size_t)kMaxSmem;
+    return NL != 0 && fast::smem_layout(NL, 0, C, stream_only(C)).total <= (size_t)kMaxSmem;
   }
   const int NL = pick_nl(Lmax);
   if (C > 64 || NL == 0) return false;
@@ -1327,10 +1340,12 @@ int ctc_fast_launch(const float* logits, int T, int B, int C, long long st_t, lo
   }
   p.num_sms = num_sms;
   if (is_wide(C)) {
+    // rows the register-held path cannot take (too wide, not a multiple of four, not 16-byte aligned) are streamed
+    const bool streamed = stream_only(C) || ((uintptr_t)logits & 15) != 0 || (st_t & 3) != 0 || (st_b & 3) != 0;
     switch (pick_nl_wide(Lmax)) {
-      case 4: return C > fast::kWideRegC ? launch_fast<4, 0, true>(p, stream) : launch_fast<4, 0>(p, stream);
-      case 5: return C > fast::kWideRegC ? launch_fast<5, 0, true>(p, stream) : launch_fast<5, 0>(p, stream);
-      case 7: return C > fast::kWideRegC ? launch_fast<7, 0, true>(p, stream) : launch_fast<7, 0>(p, stream);
+      case 4: return streamed ? launch_fast<4, 0, true>(p, stream) : launch_fast<4, 0>(p, stream);
+      case 5: return streamed ? launch_fast<5, 0, true>(p, stream) : launch_fast<5, 0>(p, stream);
+      case 7: return streamed ? launch_fast<7, 0, true>(p, stream) : launch_fast<7, 0>(p, stream);
     }
   }
   switch (pick_nl(Lmax)) {

@@ -533,9 +533,9 @@ int ctc_loss_grad(const float* logits, int T, int B, int C, long long st_t, long
   void* fast_ckpt = reinterpret_cast<void*>(base);
   base += align256(ctc_fast_workspace_bytes(T, B, C, Lmax));
 
-  // the wide-vocabulary variant moves rows with 16-byte accesses: logits and grad rows must be 16-byte aligned
-  const bool aligned = !ctc_fast_is_wide(C) || ((((uintptr_t)logits | (uintptr_t)grad) & 15) == 0 && (st_t & 3) == 0 &&
-                                                (st_b & 3) == 0);
+  // the wide-vocabulary variant moves rows in 16-byte pieces after peeling to a boundary: logits and grad rows must
+  // have the same misalignment, i.e. the two base pointers must agree modulo 16
+  const bool aligned = !ctc_fast_is_wide(C) || !grad || ((((uintptr_t)logits ^ (uintptr_t)grad) & 15) == 0);
   const bool use_fast = g_debug_path != 1 && aligned && ctc_fast_supported(T, C, Lmax);
   if (use_fast) {
     int rc = ctc_fast_launch(logits, T, B, C, st_t, st_b, label_values, label_offsets, Lmax, seq_len, blank, loss, grad,

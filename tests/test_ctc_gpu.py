@@ -249,6 +249,9 @@ def _flags(common, B):
     dict(T=150, B=4, C=3000, Lmax=60, mode="ragged", peaky=True),     # the reference's trigram vocabularies
     dict(T=90, B=2, C=6000, Lmax=20, mode="ragged"),                  # retry kernel plans 4-frame segments here
     dict(T=70, B=2, C=8192, Lmax=12, mode="ragged"),                  # widest row the throughput kernel takes
+    dict(T=100, B=5, C=131, Lmax=25, mode="ragged"),                  # C % 4 != 0: rows at every misalignment, streamed
+    dict(T=80, B=3, C=1001, Lmax=20, mode="ragged", peaky=True),
+    dict(T=60, B=3, C=3187, Lmax=15, mode="ragged"),
 ])
 def test_each_kernel_alone_matches_oracle(common, debug_paths, kw):
     g = make_batch(4242, **kw)
@@ -431,9 +434,10 @@ def test_step_functions_follow_the_reference_conventions(common):
     assert m.distances.cpu().numpy().tolist() == want
 
 
-def test_unaligned_wide_rows_fall_back_to_the_robust_kernel(common):
+def test_unaligned_wide_rows(common):
     """The wide-vocabulary variant moves rows with 16-byte accesses; a view whose rows are not 16-byte aligned must
-    still be answered correctly (by the robust kernel), never faulted on."""
+    still be answered correctly (streamed rows peel to the boundary; a gradient buffer with another misalignment
+    than the logits sends the call to the robust kernel), never faulted on."""
     g = make_batch(77, T=60, B=3, C=132, Lmax=12, mode="ragged")
     big = torch.zeros((60, 3, 135), device="cuda")
     view = big[:, :, 1:133]                       # class axis dense, rows start 4 bytes off a 16-byte boundary
@@ -442,6 +446,10 @@ def test_unaligned_wide_rows_fall_back_to_the_robust_kernel(common):
         g["logits"], g["label_values"], g["label_offsets"], g["seq_len"], precision="f64")
     loss, grad, status = common.ctc_loss_and_grad(view, _triple(g), g["seq_len"])
     _assert_loss_grad(loss.cpu().numpy(), grad.cpu().numpy(), status.cpu().numpy(), want_loss, want_grad, want_status)
+    gbig = torch.zeros((60, 3, 135), device="cuda")
+    gview = gbig[:, :, 2:134]                     # same strides as the logits view, another misalignment
+    loss, grad, status = common.ctc_loss_and_grad(view, _triple(g), g["seq_len"], out_grad=gview)
+    _assert_loss_grad(loss.cpu().numpy(), gview.cpu().numpy(), status.cpu().numpy(), want_loss, want_grad, want_status)
 
 
 @pytest.mark.parametrize("C", [130, 132, 1024, 3001])
