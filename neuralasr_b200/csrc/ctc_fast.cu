@@ -502,11 +502,11 @@ __device__ __forceinline__ float wide_row(const WideRow& r, float* rowbuf, uint3
 
 // Streamed rows (wide variant, STREAM): rows wider than kWideRegC, or whose length is not a multiple of four, or that
 // are not 16-byte aligned.  The producer warp streams the row from global memory instead of holding it -- one pass
-// for the maximum, one for the sum of e^(x-m) and, in phase 2, one that writes the provisional gradient; the second
-// and third pass find the row in L2 (a row is at most 32 KB).  Up to three scalars are peeled off at either end so
+// for the maximum and the sum of e^(x-m) together (running maximum per lane, sum rescaled when it rises) and, in
+// phase 2, one that writes the provisional gradient and finds the row in L2 (a row is at most 32 KB).  Up to three scalars are peeled off at either end so
 // that the body moves in aligned 16-byte accesses whatever the row's address (the gradient row has the same
 // misalignment: the host checks that the two base pointers agree modulo 16).  The emissions of the transcript's
-// classes are gathered straight from the row.  Same arithmetic as wide_row (ex2.approx on fma(x, log2 e, -m log2 e)).
+// classes are gathered straight from the row.  ex2.approx on fma(x, log2 e, -m log2 e) like wide_row.
 template <int NL>
 __device__ __forceinline__ float huge_row(const float* __restrict__ x, uint32_t* rec, const int (&pcls)[NL],
                                           float* grow, float gs, int C, int blank, int lane, int& alarm) {
@@ -519,7 +519,9 @@ __device__ __forceinline__ float huge_row(const float* __restrict__ x, uint32_t*
   const bool edge = lane < head || (lane >= 4 && lane - 4 < ntail);                 // lanes 0-2: head, 4-6: tail
   const int ec = lane < 4 ? lane : tail0 + lane - 4;
   const float xe = edge ? __ldg(x + ec) : -INFINITY;
-  float m = xe;
+  // one pass for both the maximum and the sum: every lane keeps a running maximum ml and the sum of e^(x - ml) of
+  // what it has seen, rescaled whenever a slice raises the maximum; the lanes are combined at the end
+  float ml = xe, sl = edge ? 1.f : 0.f;
   for (int k0 = 0; k0 < nv; k0 += 256) {
     float4 v[8];
 #pragma unroll
@@ -527,25 +529,23 @@ __device__ __forceinline__ float huge_row(const float* __restrict__ x, uint32_t*
       const int k = k0 + lane + 32 * i;
       v[i] = k < nv ? __ldg(xv + k) : ninf4;
     }
+    float cm = ml;
 #pragma unroll
-    for (int i = 0; i < 8; i++) m = fmaxf(m, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+    for (int i = 0; i < 8; i++) cm = fmaxf(cm, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+    if (cm > -INFINITY) {  // (a lane that has seen nothing finite yet keeps sl = 0)
+      const float cl2 = cm * kL2E;
+      float acc = sl * ex2_approx(fmaf(ml, kL2E, -cl2));  // ml = -inf: e^(-inf) = 0 times sl = 0
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        acc += (ex2_approx(fmaf(v[i].x, kL2E, -cl2)) + ex2_approx(fmaf(v[i].y, kL2E, -cl2))) +
+               (ex2_approx(fmaf(v[i].z, kL2E, -cl2)) + ex2_approx(fmaf(v[i].w, kL2E, -cl2)));
+      sl = acc;
+      ml = cm;
+    }
   }
-  m = warp_max(m);
+  const float m = warp_max(ml);
   const float ml2 = m * kL2E;
-  float ssum = ex2_approx(fmaf(xe, kL2E, -ml2));  // e^(-inf) = 0 for the lanes without an edge element
-  for (int k0 = 0; k0 < nv; k0 += 256) {
-    float4 v[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const int k = k0 + lane + 32 * i;
-      v[i] = k < nv ? __ldg(xv + k) : ninf4;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-      ssum += (ex2_approx(fmaf(v[i].x, kL2E, -ml2)) + ex2_approx(fmaf(v[i].y, kL2E, -ml2))) +
-              (ex2_approx(fmaf(v[i].z, kL2E, -ml2)) + ex2_approx(fmaf(v[i].w, kL2E, -ml2)));
-  }
-  ssum = warp_sum(ssum);
+  float ssum = warp_sum(ml > -INFINITY ? sl * ex2_approx(fmaf(ml, kL2E, -ml2)) : 0.f);
   const float nbl = ex2_approx(fmaf(__ldg(x + blank), kL2E, -ml2));
   const float inv_nb = __fdividef(1.0f, nbl);
   bool bad = !(nbl >= 1.0e-38f && ssum <= 3.0e38f);
