@@ -507,6 +507,7 @@ __device__ __forceinline__ float wide_row(const WideRow& r, float* rowbuf, uint3
 // that the body moves in aligned 16-byte accesses whatever the row's address (the gradient row has the same
 // misalignment: the host checks that the two base pointers agree modulo 16).  The emissions of the transcript's
 // classes are gathered straight from the row.  ex2.approx on fma(x, log2 e, -m log2 e) like wide_row.
+constexpr int kHV = 16;  // 16-byte loads a lane keeps in flight per slice of a streamed row
 template <int NL>
 __device__ __forceinline__ float huge_row(const float* __restrict__ x, uint32_t* rec, const int (&pcls)[NL],
                                           float* grow, float gs, int C, int blank, int lane, int& alarm) {
@@ -522,21 +523,21 @@ __device__ __forceinline__ float huge_row(const float* __restrict__ x, uint32_t*
   // one pass for both the maximum and the sum: every lane keeps a running maximum ml and the sum of e^(x - ml) of
   // what it has seen, rescaled whenever a slice raises the maximum; the lanes are combined at the end
   float ml = xe, sl = edge ? 1.f : 0.f;
-  for (int k0 = 0; k0 < nv; k0 += 256) {
-    float4 v[8];
+  for (int k0 = 0; k0 < nv; k0 += 32 * kHV) {
+    float4 v[kHV];
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < kHV; i++) {
       const int k = k0 + lane + 32 * i;
       v[i] = k < nv ? __ldg(xv + k) : ninf4;
     }
     float cm = ml;
 #pragma unroll
-    for (int i = 0; i < 8; i++) cm = fmaxf(cm, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+    for (int i = 0; i < kHV; i++) cm = fmaxf(cm, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
     if (cm > -INFINITY) {  // (a lane that has seen nothing finite yet keeps sl = 0)
       const float cl2 = cm * kL2E;
       float acc = sl * ex2_approx(fmaf(ml, kL2E, -cl2));  // ml = -inf: e^(-inf) = 0 times sl = 0
 #pragma unroll
-      for (int i = 0; i < 8; i++)
+      for (int i = 0; i < kHV; i++)
         acc += (ex2_approx(fmaf(v[i].x, kL2E, -cl2)) + ex2_approx(fmaf(v[i].y, kL2E, -cl2))) +
                (ex2_approx(fmaf(v[i].z, kL2E, -cl2)) + ex2_approx(fmaf(v[i].w, kL2E, -cl2)));
       sl = acc;
@@ -564,15 +565,15 @@ __device__ __forceinline__ float huge_row(const float* __restrict__ x, uint32_t*
     const float sc = gs * __fdividef(1.0f, ssum);
     if (edge) __stcg(grow + ec, ex2_approx(fmaf(xe, kL2E, -ml2)) * sc);
     float4* gv = reinterpret_cast<float4*>(grow + head);
-    for (int k0 = 0; k0 < nv; k0 += 256) {
-      float4 v[8];
+    for (int k0 = 0; k0 < nv; k0 += 32 * kHV) {
+      float4 v[kHV];
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
+      for (int i = 0; i < kHV; i++) {
         const int k = k0 + lane + 32 * i;
         v[i] = k < nv ? __ldg(xv + k) : ninf4;
       }
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
+      for (int i = 0; i < kHV; i++) {
         const int k = k0 + lane + 32 * i;
         if (k < nv)
           __stcg(gv + k,
