@@ -219,6 +219,8 @@ def run_ours(args, w, rank, world, local_rank):
     gl = torch.full((B,), 1.0 / B, dtype=torch.float32, device=dev)
     alg_bytes = algorithmic_bytes(w, seq, vals.size)
 
+    pending = []
+
     def step(i, ev=None):
         k = i % nsets
         if ev is not None:
@@ -227,11 +229,18 @@ def run_ours(args, w, rank, world, local_rank):
         if ev is not None:
             ev[1].record()
         sums = common.batch_sums(loss_b=loss_b)
-        towers.all_reduce_sums(sums)    # the path's one collective: 4 float64 scalars over NCCL
+        # the path's one collective: 4 float64 scalars over NCCL, asynchronous like the logging it feeds
+        # (the next step's kernels do not wait for it; every reduction is waited for before the clock stops)
+        _, work = towers.all_reduce_sums(sums, async_op=True)
+        if work is not None:
+            pending.append(work)
         return sums
 
     for i in range(args.warmup):
         step(i)
+    for wk in pending:
+        wk.wait()
+    pending.clear()
     torch.cuda.synchronize()
     if saved_stdout is not None:
         dist.barrier()
@@ -250,6 +259,9 @@ def run_ours(args, w, rank, world, local_rank):
     t_start.record()
     for i in range(args.steps):
         sums = step(args.warmup + i, evs[i])
+    for wk in pending:
+        wk.wait()              # the compute stream now waits for every step's reduction
+    pending.clear()
     t_stop.record()
     torch.cuda.synchronize()
     if world > 1:

@@ -8,8 +8,8 @@ every rank owns a local contiguous ``[T, B/G, C]`` logits tensor, its rows of th
 local batch indices, and its ``seq_len``.  Losses, gradients, hypotheses and per-utterance error rates
 never leave their GPU; the only exchange is one all-reduce(sum) of the float64 4-vector
 ``[sum loss, sum ler, sum edit distance, utterance count]`` that ``common.batch_sums`` builds on the
-device — 32 bytes, latency-bound, so it is a plain NCCL all-reduce on the compute stream rather than a
-fused kernel.
+device — 32 bytes, latency-bound, so it is a plain NCCL all-reduce rather than a fused kernel; issued
+asynchronously it overlaps the next step's kernels.
 """
 from __future__ import annotations
 
@@ -42,12 +42,18 @@ def shard_inputs(labels, seq_len, rank, world, logits=None):
     return out
 
 
-def all_reduce_sums(sums, group=None):
+def all_reduce_sums(sums, group=None, async_op=False):
     """Sum the ``[sum loss, sum ler, sum dist, count]`` vectors of all towers in place (no-op without an
-    initialised process group).  Works on CUDA tensors over NCCL and on CPU tensors over gloo."""
+    initialised process group).  Works on CUDA tensors over NCCL and on CPU tensors over gloo.
+
+    ``async_op=True`` returns ``(sums, work)``: the reduction is ordered after what the current stream has
+    enqueued but the stream does not wait for it, so the next step's kernels start while the 32 bytes travel
+    (the scalars are only read for logging, ``train.py``); call ``work.wait()`` — ``work`` is ``None`` without a
+    process group — before reading ``sums``."""
+    work = None
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-    return sums
+        work = dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    return (sums, work) if async_op else sums
 
 
 def step_scalars(sums):
