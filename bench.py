@@ -279,6 +279,7 @@ def run_ours(args, w, rank, world, local_rank):
     value = frames * world * args.steps / (ms_total * 1e-3)
 
     # ---- e2e through the HOST-buffer C-ABI call (pinned H2D + kernel + D2H per step) ----
+    numa_cpus = host.bind_to_gpu_numa_node(local_rank) if world > 1 else None   # pinned staging on the GPU's node
     ctx = host.HostContext(local_rank, T, B, C, w["Lmax"])
     pin = ctx.pinned_logits[: x.size].reshape(T, B, C)
     pin[...] = x
@@ -416,7 +417,8 @@ def run_ours(args, w, rank, world, local_rank):
                          "algorithmic_bytes_per_launch": alg_bytes},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps},
+                    "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
+                    "numa_bound_cpus": len(numa_cpus) if numa_cpus else None},
             "gpu_launches": launches,
             "clocks": clocks,
             "decode_ler_ms": dec_ms,

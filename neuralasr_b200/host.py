@@ -18,6 +18,30 @@ def _p(a):
     return ctypes.c_void_p(a.ctypes.data) if a is not None else None
 
 
+def bind_to_gpu_numa_node(device):
+    """Restrict this process to the CPUs NVML reports as local to GPU ``device``, so that the pinned staging a
+    :class:`HostContext` allocates next (and the threads that fill it) sit on the NUMA node the GPU's PCIe link
+    hangs off.  With one process per GPU on a two-socket box this keeps H2D/D2H traffic off the socket
+    interconnect.  Returns the CPU set, or None if NVML or the affinity call is unavailable (never an error)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[device]) if visible and visible.split(",")[device].isdigit() else int(device)
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 class HostContext:
     def __init__(self, device, max_T, max_B, max_C, max_label_len, decoder="greedy", beam_width=100):
         """``decoder``: ``"greedy"`` (``tfnetwork.py:63``) or ``"beam"`` (``tfnetwork.py:62``: what the snapshot's
