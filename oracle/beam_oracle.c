@@ -125,8 +125,13 @@ static int new_entry(beam_t* s, int parent, int label) {
 static void reset_prob(prob_t* p) { p->blank = p->label = p->total = LOG0; }
 
 /* one utterance: x rows at stride st_t, Tb frames */
+/* margin (may be NULL): smallest |difference of totals| over all decisions taken -- a candidate tested against the
+ * beam's worst entry, and the order of the paths returned.  A result whose margin is within rounding of zero
+ * depends on the last bit of exp/log and may legitimately differ between two correct implementations. */
 static void beam_one(const float* x, long long st_t, int Tb, int C, int blank, int W, int P, int merge,
-                     long long* hyp /*[P][T]*/, int T, int* hyp_len /*[P]*/, double* log_prob /*[P]*/) {
+                     long long* hyp /*[P][T]*/, int T, int* hyp_len /*[P]*/, double* log_prob /*[P]*/,
+                     double* margin) {
+  double mg = INFINITY;
   beam_t s;
   s.cap = 1024;
   s.n = 0;
@@ -182,7 +187,12 @@ static void beam_one(const float* x, long long st_t, int Tb, int C, int blank, i
       const int bi = branches[i];
       if (!(s.e[bi].oldp.total > LOG0)) continue;
       /* TF: skip b unless oldp.total > bottom.total; '<' here so that exact ties reach the per-child test */
-      if (s.hn == W && s.e[bi].oldp.total < s.e[s.heap[0]].newp.total) continue;
+      if (s.hn == W && s.e[bi].oldp.total < s.e[s.heap[0]].newp.total) {
+        /* the skipped prefix's best extension is at most oldp.total + max lp: its distance to the bottom counts */
+        const double dm = fabs(s.e[s.heap[0]].newp.total - s.e[bi].oldp.total);
+        if (dm < mg) mg = dm;
+        continue;
+      }
       if (!s.e[bi].children) {
         int* ch = (int*)malloc(sizeof(int) * (size_t)C);
         for (int c = 0; c < C; c++) ch[c] = -1;
@@ -199,6 +209,10 @@ static void beam_one(const float* x, long long st_t, int Tb, int C, int blank, i
         probe.is_new = 1;
         probe.hash = child_hash(s.e[bi].hash, l);
         const int cand = s.hn < W || worse(&s.e[s.heap[0]], &probe);
+        if (s.hn == W) {
+          const double dm = fabs(v - s.e[s.heap[0]].newp.total);
+          if (dm < mg) mg = dm;
+        }
         if (cand) {
           if (ci < 0) {
             ci = new_entry(&s, bi, l); /* may move s.e */
@@ -239,6 +253,11 @@ static void beam_one(const float* x, long long st_t, int Tb, int C, int blank, i
     }
     order[j + 1] = k;
   }
+  for (int p = 0; p + 1 < nl && p < P; p++) {
+    const double dm = fabs(s.e[order[p]].newp.total - s.e[order[p + 1]].newp.total);
+    if (dm < mg) mg = dm;
+  }
+  if (margin) *margin = mg;
   for (int p = 0; p < P; p++) {
     long long* out = hyp + (size_t)p * T;
     if (p >= nl) {
@@ -278,6 +297,7 @@ typedef struct {
   long long* hyp;
   int* hyp_len;
   double* log_prob;
+  double* margin;
   int next;
 } job_t;
 
@@ -289,22 +309,24 @@ static void* worker(void* p) {
     int Tb = j->seq_len[b];
     Tb = Tb < 0 ? 0 : (Tb > j->T ? j->T : Tb);
     beam_one(j->logits + (size_t)b * j->st_b, j->st_t, Tb, j->C, j->blank, j->W, j->P, j->merge,
-             j->hyp + (size_t)b * j->P * j->T, j->T, j->hyp_len + (size_t)b * j->P, j->log_prob + (size_t)b * j->P);
+             j->hyp + (size_t)b * j->P * j->T, j->T, j->hyp_len + (size_t)b * j->P, j->log_prob + (size_t)b * j->P,
+             j->margin ? j->margin + b : NULL);
   }
   return NULL;
 }
 
 /* logits float32 [T,B,C] at element strides (st_t, st_b, 1); hyp int64 [B,P,T]; hyp_len int32 [B,P];
  * log_prob float64 [B,P].  Utterances are spread over num_threads threads (<= 0: all cores). */
-int oracle_beam_search(const float* logits, int T, int B, int C, long long st_t, long long st_b,
-                       const int32_t* seq_len, int blank, int W, int P, int merge, long long* hyp, int* hyp_len,
-                       double* log_prob, int num_threads) {
+/* margin: NULL or float64 [B] (see beam_one). */
+int oracle_beam_search_margin(const float* logits, int T, int B, int C, long long st_t, long long st_b,
+                              const int32_t* seq_len, int blank, int W, int P, int merge, long long* hyp,
+                              int* hyp_len, double* log_prob, double* margin, int num_threads) {
   if (num_threads <= 0) {
     long n = sysconf(_SC_NPROCESSORS_ONLN);
     num_threads = n > 0 ? (int)n : 1;
   }
   if (num_threads > B) num_threads = B;
-  job_t job = {logits, T, B, C, st_t, st_b, seq_len, blank, W, P, merge, hyp, hyp_len, log_prob, 0};
+  job_t job = {logits, T, B, C, st_t, st_b, seq_len, blank, W, P, merge, hyp, hyp_len, log_prob, margin, 0};
   if (num_threads <= 1) {
     worker(&job);
     return 0;
@@ -317,4 +339,11 @@ int oracle_beam_search(const float* logits, int T, int B, int C, long long st_t,
   for (int i = 0; i < started; i++) pthread_join(th[i], NULL);
   free(th);
   return 0;
+}
+
+int oracle_beam_search(const float* logits, int T, int B, int C, long long st_t, long long st_b,
+                       const int32_t* seq_len, int blank, int W, int P, int merge, long long* hyp, int* hyp_len,
+                       double* log_prob, int num_threads) {
+  return oracle_beam_search_margin(logits, T, B, C, st_t, st_b, seq_len, blank, W, P, merge, hyp, hyp_len, log_prob,
+                                   NULL, num_threads);
 }

@@ -95,9 +95,12 @@ def edit_distance(hyp_values, hyp_offsets, truth_values, truth_offsets, normaliz
     return dist, ler
 
 
-def beam_search(logits, seq_len, beam_width=100, top_paths=1, merge_repeated=True, blank=None, num_threads=0):
+def beam_search(logits, seq_len, beam_width=100, top_paths=1, merge_repeated=True, blank=None, num_threads=0,
+                with_margin=False):
     """oracle/beam_oracle.c (TF's trie + TopN control flow).  Returns (hyp i64[B,P,T], hyp_len i32[B,P],
-    log_prob f64[B,P]); logits may be any [T,B,C] float32 view with a dense class axis."""
+    log_prob f64[B,P]); logits may be any [T,B,C] float32 view with a dense class axis.  ``with_margin`` adds
+    margin f64[B]: the smallest difference of totals over all decisions the search took for that utterance — a
+    result whose margin is within rounding of zero hangs on the last bit of exp/log."""
     logits = np.asarray(logits, dtype=np.float32)
     if logits.strides[2] != 4:
         logits = np.ascontiguousarray(logits)
@@ -108,12 +111,14 @@ def beam_search(logits, seq_len, beam_width=100, top_paths=1, merge_repeated=Tru
     hyp = np.zeros((B, P, max(T, 1)), dtype=np.int64)
     hl = np.zeros((B, P), dtype=np.int32)
     lp = np.zeros((B, P), dtype=np.float64)
-    fn = lib().oracle_beam_search
+    margin = np.full(B, np.inf, dtype=np.float64)
+    fn = lib().oracle_beam_search_margin
     fn.restype = ctypes.c_int
     fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_longlong,
                    ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
-                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     fn(logits.ctypes.data, T, B, C, logits.strides[0] // 4, logits.strides[1] // 4, sl.ctypes.data, blank,
        int(beam_width), P, int(bool(merge_repeated)), hyp.ctypes.data, hl.ctypes.data, lp.ctypes.data,
-       int(num_threads))
-    return hyp[:, :, :T] if T else hyp[:, :, :0], hl, lp
+       margin.ctypes.data, int(num_threads))
+    out = (hyp[:, :, :T] if T else hyp[:, :, :0], hl, lp)
+    return out + (margin,) if with_margin else out

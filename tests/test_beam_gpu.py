@@ -298,3 +298,51 @@ def test_wide_vocabulary_ties_through_the_second_stage_bound():
     _check_c(x, np.array([6, 6], np.int32), W=10, P=4, merge=False)
     rng = np.random.default_rng(54)
     _check_c((rng.normal(size=(50, 3, 65)) * 3).astype(np.float32), np.array([50, 50, 31], np.int32), W=100, P=2)
+
+
+def test_randomised_shapes_against_the_c_port():
+    """Seeded sweep over shapes, widths, blank positions and four kinds of logits.  The C port reports the smallest
+    difference of totals over all decisions it took for an utterance; where that margin is within rounding of zero
+    (quantised logits make different prefixes mathematically equal) the outcome hangs on the last bit of exp/log and
+    the comparison is skipped — everywhere else the paths must be identical."""
+    from neuralasr_b200.networks import common
+    from oracle import c_oracle
+    rng = np.random.default_rng(20240)
+    compared = skipped = 0
+    for case in range(240):
+        C = int(rng.choice([2, 3, 5, 12, 38, 41, 64, 65, 100, 300, 1024]))
+        T = int(rng.integers(1, 70))
+        B = int(rng.integers(1, 5))
+        W = int(rng.choice([1, 2, 3, 7, 16, 100, 128, 300]))
+        P = int(min(W, rng.integers(1, 4)))
+        merge = bool(rng.integers(0, 2))
+        kind = case % 4
+        if kind == 0:
+            x = (rng.normal(size=(T, B, C)) * rng.choice([0.3, 1.0, 3.0, 8.0])).astype(np.float32)
+        elif kind == 1:                                   # planted alignment
+            x = rng.normal(size=(T, B, C)).astype(np.float32)
+            np.put_along_axis(x, rng.integers(0, C, size=(T, B))[:, :, None], 8.0, axis=2)
+        elif kind == 2:                                   # quantised logits: many exact and near ties
+            x = rng.integers(-2, 3, size=(T, B, C)).astype(np.float32)
+        else:                                             # extreme range
+            x = (rng.normal(size=(T, B, C)) * 40).astype(np.float32)
+        seq = rng.integers(0, T + 1, size=B).astype(np.int32)
+        seq[0] = T
+        blank = C - 1 if case % 5 else int(rng.integers(0, C))
+        dec, lp = common.beam_decoding(torch.from_numpy(x).cuda(), seq, beam_width=W, top_paths=P,
+                                       merge_repeated=merge, blank=blank)
+        hyp, hl, want, margin = c_oracle.beam_search(x, seq, W, P, merge, blank=blank, with_margin=True)
+        lp = lp.cpu().numpy()
+        for b in range(B):
+            if margin[b] < 1e-9:
+                skipped += 1
+                continue
+            compared += 1
+            for p in range(P):
+                gh, gl = dec[p].hyp[b].cpu().numpy(), int(dec[p].hyp_len[b])
+                assert gl == hl[b, p] and np.array_equal(gh[:gl], hyp[b, p, : hl[b, p]]), (case, kind, b, p)
+                if np.isfinite(want[b, p]):
+                    assert abs(lp[b, p] - want[b, p]) <= 1e-6 * max(1.0, abs(want[b, p])), (case, kind, b, p)
+                else:
+                    assert lp[b, p] == want[b, p]
+    assert compared >= 350 and skipped <= compared // 2, (compared, skipped)
