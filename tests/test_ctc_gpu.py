@@ -468,3 +468,45 @@ def test_greedy_decode_wide_rows_first_index_ties(common, C):
     assert np.array_equal(dec.hyp_len.cpu().numpy(), np.diff(ho))
     assert np.array_equal(dec.values.cpu().numpy(), hv)
     assert np.array_equal(nsl.cpu().numpy().reshape(-1), want_nsl)
+
+
+def test_loss_grad_and_decode_capture_into_a_cuda_graph(common):
+    """include/nasr_ctc.h promises that the entry points only enqueue work on the given stream: a step (loss+grad,
+    batch sums, greedy decode, beam search, label error rate) must be capturable into a CUDA graph and replay
+    correctly on new logits."""
+    g = make_batch(31, T=90, B=6, C=38, Lmax=20, mode="ragged")
+    dev = torch.device("cuda", 0)
+    x = torch.from_numpy(g["logits"]).to(dev)
+    lab = common.prepare_labels(_triple(g), dev)
+    seq = torch.from_numpy(g["seq_len"]).to(dev)
+    gbuf = torch.empty_like(x)
+
+    def step():
+        loss_b, grad, status = common.ctc_loss_and_grad(x, lab, seq, out_grad=gbuf)
+        sums = common.batch_sums(loss_b=loss_b)
+        dec, nsl = common.decoding(x, seq)
+        dist, ler = common.edit_distance(dec, lab)
+        bdec, blp = common.beam_decoding(x, seq, beam_width=16)
+        return loss_b, status, sums, dec, dist, bdec, blp
+
+    step()                                   # warm-up outside the capture: workspaces, function attributes
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        loss_b, status, sums, dec, dist, bdec, blp = step()
+    g2 = make_batch(32, T=90, B=6, C=38, Lmax=20, mode="ragged")
+    x.copy_(torch.from_numpy(g2["logits"]))  # same labels and lengths, new logits
+    graph.replay()
+    torch.cuda.synchronize()
+    want_loss, want_grad, _ = c_oracle.ctc_loss_grad(g2["logits"], g["label_values"], g["label_offsets"], g["seq_len"],
+                                                     precision="f64")
+    np.testing.assert_allclose(loss_b.cpu().numpy(), want_loss, rtol=LOSS_RTOL)
+    assert np.abs(gbuf.cpu().numpy() - want_grad).max() <= GRAD_ATOL
+    assert abs(sums[0].item() - want_loss.sum()) <= LOSS_RTOL * want_loss.sum()
+    hv, ho, _ = c_oracle.greedy_decode(g2["logits"], g["seq_len"])
+    assert np.array_equal(dec.hyp_len.cpu().numpy(), np.diff(ho))
+    want_d, _ = c_oracle.edit_distance(hv, ho, g["label_values"], g["label_offsets"])
+    assert np.array_equal(dist.cpu().numpy(), want_d)
+    hyp, hl, lp = c_oracle.beam_search(g2["logits"], g["seq_len"], 16, 1, True)
+    assert np.array_equal(bdec[0].hyp_len.cpu().numpy(), hl[:, 0])
+    assert np.allclose(blp.cpu().numpy()[:, 0], lp[:, 0], rtol=1e-6)
