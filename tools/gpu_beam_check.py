@@ -58,7 +58,7 @@ def phases(name, x, W=100):
     torch.cuda.synchronize()
     lib.nasr_debug_profile(None)
     ph = buf[:8].cpu().numpy() / T
-    names = ["softmax", "update", "live", "eval", "select", "admit", "parents"]
+    names = ["update", "lists", "keys", "select", "admit", "build", "parents"]
     print("%-20s cycles/frame: " % name + "  ".join("%s %.0f" % (k, v) for k, v in zip(names, ph)) +
           "  total %.0f" % ph.sum(), flush=True)
 
