@@ -125,13 +125,18 @@ static int new_entry(beam_t* s, int parent, int label) {
 static void reset_prob(prob_t* p) { p->blank = p->label = p->total = LOG0; }
 
 /* one utterance: x rows at stride st_t, Tb frames */
-/* margin (may be NULL): smallest |difference of totals| over all decisions taken -- a candidate tested against the
- * beam's worst entry, and the order of the paths returned.  A result whose margin is within rounding of zero
- * depends on the last bit of exp/log and may legitimately differ between two correct implementations. */
+/* margin (may be NULL): margin[0] = smallest NONZERO |difference of totals| over all decisions taken -- a candidate
+ * tested against the beam's worst entry, and the order of the paths returned; margin[1] = number of decisions between
+ * bitwise-equal totals.  A result whose margin[0] is within rounding of zero depends on the last bit of exp/log and
+ * may legitimately differ between two correct implementations.  Bitwise-equal totals are of two kinds: twins -- the
+ * same operations on equal inputs (two labels with equal logits in a frame, and everything that grows from such a
+ * pair once their parents have left the beam), which every implementation ties and the hash decides identically --
+ * and, with quantised logits, different prefixes that happen to be equal here and one ulp apart elsewhere. */
 static void beam_one(const float* x, long long st_t, int Tb, int C, int blank, int W, int P, int merge,
                      long long* hyp /*[P][T]*/, int T, int* hyp_len /*[P]*/, double* log_prob /*[P]*/,
                      double* margin) {
-  double mg = INFINITY;
+  double mg = INFINITY, nzero = 0.0;
+#define NASR_MARGIN(dm_) do { const double d__ = (dm_); if (d__ == 0.0) nzero += 1.0; else if (d__ < mg) mg = d__; } while (0)
   beam_t s;
   s.cap = 1024;
   s.n = 0;
@@ -189,8 +194,7 @@ static void beam_one(const float* x, long long st_t, int Tb, int C, int blank, i
       /* TF: skip b unless oldp.total > bottom.total; '<' here so that exact ties reach the per-child test */
       if (s.hn == W && s.e[bi].oldp.total < s.e[s.heap[0]].newp.total) {
         /* the skipped prefix's best extension is at most oldp.total + max lp: its distance to the bottom counts */
-        const double dm = fabs(s.e[s.heap[0]].newp.total - s.e[bi].oldp.total);
-        if (dm < mg) mg = dm;
+        NASR_MARGIN(fabs(s.e[s.heap[0]].newp.total - s.e[bi].oldp.total));
         continue;
       }
       if (!s.e[bi].children) {
@@ -210,8 +214,7 @@ static void beam_one(const float* x, long long st_t, int Tb, int C, int blank, i
         probe.hash = child_hash(s.e[bi].hash, l);
         const int cand = s.hn < W || worse(&s.e[s.heap[0]], &probe);
         if (s.hn == W) {
-          const double dm = fabs(v - s.e[s.heap[0]].newp.total);
-          if (dm < mg) mg = dm;
+          NASR_MARGIN(fabs(v - s.e[s.heap[0]].newp.total));
         }
         if (cand) {
           if (ci < 0) {
@@ -254,10 +257,13 @@ static void beam_one(const float* x, long long st_t, int Tb, int C, int blank, i
     order[j + 1] = k;
   }
   for (int p = 0; p + 1 < nl && p < P; p++) {
-    const double dm = fabs(s.e[order[p]].newp.total - s.e[order[p + 1]].newp.total);
-    if (dm < mg) mg = dm;
+    NASR_MARGIN(fabs(s.e[order[p]].newp.total - s.e[order[p + 1]].newp.total));
   }
-  if (margin) *margin = mg;
+#undef NASR_MARGIN
+  if (margin) {
+    margin[0] = mg;
+    margin[1] = nzero;
+  }
   for (int p = 0; p < P; p++) {
     long long* out = hyp + (size_t)p * T;
     if (p >= nl) {
@@ -310,14 +316,14 @@ static void* worker(void* p) {
     Tb = Tb < 0 ? 0 : (Tb > j->T ? j->T : Tb);
     beam_one(j->logits + (size_t)b * j->st_b, j->st_t, Tb, j->C, j->blank, j->W, j->P, j->merge,
              j->hyp + (size_t)b * j->P * j->T, j->T, j->hyp_len + (size_t)b * j->P, j->log_prob + (size_t)b * j->P,
-             j->margin ? j->margin + b : NULL);
+             j->margin ? j->margin + 2 * (size_t)b : NULL);
   }
   return NULL;
 }
 
 /* logits float32 [T,B,C] at element strides (st_t, st_b, 1); hyp int64 [B,P,T]; hyp_len int32 [B,P];
  * log_prob float64 [B,P].  Utterances are spread over num_threads threads (<= 0: all cores). */
-/* margin: NULL or float64 [B] (see beam_one). */
+/* margin: NULL or float64 [B][2] (see beam_one). */
 int oracle_beam_search_margin(const float* logits, int T, int B, int C, long long st_t, long long st_b,
                               const int32_t* seq_len, int blank, int W, int P, int merge, long long* hyp,
                               int* hyp_len, double* log_prob, double* margin, int num_threads) {

@@ -99,8 +99,10 @@ def beam_search(logits, seq_len, beam_width=100, top_paths=1, merge_repeated=Tru
                 with_margin=False):
     """oracle/beam_oracle.c (TF's trie + TopN control flow).  Returns (hyp i64[B,P,T], hyp_len i32[B,P],
     log_prob f64[B,P]); logits may be any [T,B,C] float32 view with a dense class axis.  ``with_margin`` adds
-    margin f64[B]: the smallest difference of totals over all decisions the search took for that utterance — a
-    result whose margin is within rounding of zero hangs on the last bit of exp/log."""
+    margin f64[B,2]: [:, 0] the smallest NONZERO difference of totals over all decisions the search took for that
+    utterance — a result whose margin is within rounding of zero hangs on the last bit of exp/log — and [:, 1] the
+    number of decisions between bitwise-equal totals (twins from equal logits in a frame: deterministic everywhere;
+    with quantised logits also accidental equalities that another libm may break)."""
     logits = np.asarray(logits, dtype=np.float32)
     if logits.strides[2] != 4:
         logits = np.ascontiguousarray(logits)
@@ -111,7 +113,7 @@ def beam_search(logits, seq_len, beam_width=100, top_paths=1, merge_repeated=Tru
     hyp = np.zeros((B, P, max(T, 1)), dtype=np.int64)
     hl = np.zeros((B, P), dtype=np.int32)
     lp = np.zeros((B, P), dtype=np.float64)
-    margin = np.full(B, np.inf, dtype=np.float64)
+    margin = np.full((B, 2), np.inf, dtype=np.float64)
     fn = lib().oracle_beam_search_margin
     fn.restype = ctypes.c_int
     fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_longlong,

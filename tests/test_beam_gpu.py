@@ -334,7 +334,8 @@ def test_randomised_shapes_against_the_c_port():
         hyp, hl, want, margin = c_oracle.beam_search(x, seq, W, P, merge, blank=blank, with_margin=True)
         lp = lp.cpu().numpy()
         for b in range(B):
-            if margin[b] < 1e-9:
+            # quantised logits: bitwise-equal totals of different prefixes may be one ulp apart under another libm
+            if margin[b, 0] < 1e-9 or (kind == 2 and margin[b, 1] > 0):
                 skipped += 1
                 continue
             compared += 1
@@ -346,3 +347,24 @@ def test_randomised_shapes_against_the_c_port():
                 else:
                     assert lp[b, p] == want[b, p]
     assert compared >= 350 and skipped <= compared // 2, (compared, skipped)
+
+
+def test_full_size_cfg3_whole_batch_against_the_c_port():
+    """BASELINE cfg3 (B=256, T=1000, C=38, width 100) on the bench's N(0,1)*3 logits: every utterance's top path and
+    log probability against the C port (a second and a half on the box's host threads)."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(1234)
+    T, B, C = 1000, 256, 38
+    x = rng.standard_normal((T, B, C), dtype=np.float32) * np.float32(3.0)
+    seq = np.full(B, T, np.int32)
+    seq[3], seq[200] = 611, 17
+    got, lp = _run(x, seq, 100, 1, True)
+    hyp, hl, want, margin = c_oracle.beam_search(x, seq, 100, 1, True, with_margin=True)
+    # continuous logits: decisions within rounding are rare; bitwise-equal totals (margin[:, 1]) come from twins --
+    # two labels with equal float32 logits in a frame -- which every implementation ties and the hash decides
+    assert (margin[:, 0] > 1e-9).sum() >= B - 8
+    for b in range(B):
+        if margin[b, 0] <= 1e-9:
+            continue
+        assert got[0][b] == hyp[b, 0, : hl[b, 0]].tolist(), b
+        assert abs(lp[b, 0] - want[b, 0]) <= 1e-6 * abs(want[b, 0]), b
