@@ -643,7 +643,7 @@ ctc_fast_kernel(const Params p) {
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int T = p.T, B = p.B, C = p.C, blank = p.blank;
+  const int T = p.T, C = p.C, blank = p.blank;
   constexpr int rowbytes = ROWB;
   constexpr int gstride = NL * 32 + 4;
   constexpr int N = NL * 32;

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(512) ctc_robust_kernel(const Params p) {
   const int b = blockIdx.x;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-  const int T = p.T, B = p.B, C = p.C, K = p.K, Upad = p.Upad, blank = p.blank;
+  const int T = p.T, C = p.C, K = p.K, Upad = p.Upad, blank = p.blank;
   const int Tb = p.seq_len[b];
   const int l0 = p.lab_offs[b];
   const int L = p.lab_offs[b + 1] - l0;
