@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <new>
+#include <thread>
 
 #include "nasr_common.cuh"
 
@@ -127,6 +128,32 @@ int64_t dl_numel(const DLTensor* t) {
 }  // namespace nasr
 
 using namespace nasr;
+
+// Host copy between a caller's pageable buffer and the pinned staging: one thread moves about 20 GB/s on this box,
+// so large copies are split over a few (a per-block, row-by-row staging that overlaps the DMA was measured and is
+// slower: 8000 copies of 4.8 KB cost more than the overlap gains).
+static void host_copy(void* dst, const void* src, size_t bytes) {
+  const size_t kMin = (size_t)4 << 20;
+  unsigned hw = std::thread::hardware_concurrency();
+  int nt = (int)(bytes / kMin);
+  nt = nt > 8 ? 8 : nt;
+  if (hw && nt > (int)hw) nt = (int)hw;
+  if (nt <= 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  std::thread th[8];
+  const size_t chunk = ((bytes / nt) + 4095) & ~(size_t)4095;
+  int started = 0;
+  for (int i = 1; i < nt; i++) {
+    const size_t o = (size_t)i * chunk;
+    if (o >= bytes) break;
+    const size_t n = bytes - o < chunk ? bytes - o : chunk;
+    th[started++] = std::thread([=]() { memcpy((char*)dst + o, (const char*)src + o, n); });
+  }
+  memcpy(dst, src, chunk < bytes ? chunk : bytes);
+  for (int i = 0; i < started; i++) th[i].join();
+}
 
 struct nasr_host_ctx {
   int device;
@@ -504,7 +531,7 @@ int nasr_host_ctc_step(nasr_host_ctx* c, const float* logits, int T, int B, int 
   small_layout(c->max_B, c->max_B * c->max_L, &o_vals, &o_offs, &o_seq, &o_gl, &o_loss, &o_status,
                &o_hl, &o_nsl, &o_dist, &o_ler);
   // stage inputs in pinned memory (skipped for logits when the caller filled the pinned buffer)
-  if (logits != c->h_logits) memcpy(c->h_logits, logits, sizeof(float) * nlog);
+  if (logits != c->h_logits) host_copy(c->h_logits, logits, sizeof(float) * nlog);
   if (N) memcpy(c->h_small + o_vals, label_values, sizeof(int32_t) * N);
   memcpy(c->h_small + o_offs, label_offsets, sizeof(int32_t) * (B + 1));
   memcpy(c->h_small + o_seq, seq_len, sizeof(int32_t) * B);
@@ -587,7 +614,7 @@ int nasr_host_ctc_step(nasr_host_ctx* c, const float* logits, int T, int B, int 
   NASR_CUDA(cudaStreamSynchronize(s));
   memcpy(loss, c->h_small + o_loss, sizeof(float) * B);
   memcpy(status, c->h_small + o_status, sizeof(int32_t) * B);
-  if (grad && grad != c->h_grad) memcpy(grad, c->h_grad, sizeof(float) * nlog);
+  if (grad && grad != c->h_grad) host_copy(grad, c->h_grad, sizeof(float) * nlog);
   if (hyp_len) memcpy(hyp_len, c->h_small + o_hl, sizeof(int32_t) * B);
   if (neg_sum_logits) memcpy(neg_sum_logits, c->h_small + o_nsl, sizeof(float) * B);
   if (hyp) memcpy(hyp, c->h_hyp, sizeof(int64_t) * (size_t)B * T);
