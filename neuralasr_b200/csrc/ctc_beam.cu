@@ -876,7 +876,8 @@ int ctc_beam_search(const float* logits, int T, int B, int C, long long st_t, lo
   NASR_CHECK_ARG(blank >= 0 && blank < C, "ctc_beam_search: blank=%d outside [0,%d)", blank, C);
   NASR_CHECK_ARG(W >= 1 && P >= 1 && P <= W, "ctc_beam_search: need 1 <= top_paths <= beam_width (got %d, %d)", P, W);
   if (B == 0) return NASR_OK;
-  NASR_CHECK_ARG(logits && seq_len && hyp && hyp_len && log_prob && workspace, "ctc_beam_search: NULL argument");
+  NASR_CHECK_ARG((logits || T == 0) && seq_len && (hyp || T == 0) && hyp_len && log_prob && workspace,
+                 "ctc_beam_search: NULL argument");
   size_t need = 0;
   ctc_beam_workspace_bytes(T, B, C, W, &need);
   if (workspace_bytes < need) {

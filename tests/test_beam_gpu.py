@@ -368,3 +368,11 @@ def test_full_size_cfg3_whole_batch_against_the_c_port():
             continue
         assert got[0][b] == hyp[b, 0, : hl[b, 0]].tolist(), b
         assert abs(lp[b, 0] - want[b, 0]) <= 1e-6 * abs(want[b, 0]), b
+
+
+def test_zero_frames():
+    from neuralasr_b200.networks import common
+    x = torch.zeros((0, 3, 7), device="cuda")
+    dec, lp = common.beam_decoding(x, np.zeros(3, np.int32), beam_width=8, top_paths=2)
+    assert dec[0].hyp_len.cpu().tolist() == [0, 0, 0] and dec[1].hyp_len.cpu().tolist() == [0, 0, 0]
+    assert lp[:, 0].cpu().tolist() == [0.0, 0.0, 0.0] and torch.isinf(lp[:, 1]).all()
