@@ -46,6 +46,7 @@ constexpr int kSearchWarps = kSearchThreads / 32;
 constexpr int kBeamThreads = kSearchThreads + 32;   // + one warp that prepares the next frame's log-softmax
 constexpr int kIPT = 4096 / kSearchThreads;         // candidate keys a search thread keeps in registers
 constexpr int kBins = 2048;                         // 11-bit digits
+constexpr int kBitSetMaxC = 4095;                   // widest vocabulary whose active extensions are kept as bit sets
 #ifndef NASR_BEAM_STAGE2_MINC
 #define NASR_BEAM_STAGE2_MINC 64
 #endif
@@ -98,9 +99,10 @@ __host__ __device__ inline int tab_size(int W) {
 // Shared-memory layout, computed once on the host and handed to the kernel as a __grid_constant__ parameter:
 // every array base is then a constant-bank operand instead of arithmetic on W and C redone inside the frame loop.
 struct BeamLayout {
-  int lp2, pb, pl, pt, hash, phash, node, len, last, plast, pslot, ub, ul, ut, liveP, newslot, adm_i, liveL, adm_k,
-      tab_key, tab_slot, mask, hist, redd, redu, redi, c1, c2;
-  int total, TS, CW;
+  int x2, lp2, pb, pl, pt, hash, phash, node, len, last, plast, pslot, ub, ul, ut, liveP, newslot, adm_i, liveL, adm_k,
+      tab_key, tab_slot, mtab, hist, redd, redu, redi, c1, c2;
+  int has_bits, CW;  // bit sets of active extensions ([W][CW] words) while they fit (C <= kBitSetMaxC), else a hash set
+  int total, TS, tshift;  // TS: slots of the two hash tables (a power of two >= 2W); tshift = 32 - log2(TS)
 };
 
 inline BeamLayout beam_layout(int W, int C) {
@@ -111,9 +113,12 @@ inline BeamLayout beam_layout(int W, int C) {
     o += al16(bytes);
     return (int)r;
   };
-  L.CW = (C + 31) / 32;
   L.TS = tab_size(W);
-  L.lp2 = take(sizeof(double) * 2 * C);
+  L.tshift = 32;
+  for (int t = L.TS; t > 1; t >>= 1) L.tshift--;
+  L.has_bits = C <= kBitSetMaxC;
+  L.x2 = take(L.has_bits ? 0 : sizeof(float) * 2 * C);        // BIG: raw rows, lp on demand
+  L.lp2 = take(L.has_bits ? sizeof(double) * 2 * C : 0);      // else: fp64 log-probability rows
   L.pb = take(sizeof(double) * 2 * W);
   L.pl = take(sizeof(double) * 2 * W);
   L.pt = take(sizeof(double) * 2 * W);
@@ -134,7 +139,8 @@ inline BeamLayout beam_layout(int W, int C) {
   L.adm_k = take(sizeof(u64) * W);
   L.tab_key = take(sizeof(u64) * L.TS);
   L.tab_slot = take(sizeof(int) * L.TS);
-  L.mask = take(sizeof(uint32_t) * (size_t)W * L.CW);
+  L.CW = (C + 31) / 32;
+  L.mtab = take(sizeof(uint32_t) * (L.has_bits ? (size_t)W * L.CW : (size_t)L.TS));
   L.hist = take(sizeof(int) * kBins);
   L.redd = take(sizeof(double) * 64);
   L.redu = take(sizeof(u64) * 64);
@@ -154,19 +160,54 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
   return v;
 }
 
+// Extensions that are already active prefixes: a hash set of (parent slot << 16 | label), at most one entry per
+// active prefix, open addressing in a table of TS >= 2W slots (0xffffffff = empty).
+constexpr uint32_t kEmpty = 0xffffffffu;
+__device__ __forceinline__ uint32_t mtab_key(int slot, int label) { return ((uint32_t)slot << 16) | (uint32_t)label; }
+__device__ __forceinline__ unsigned mtab_home(uint32_t key, int tshift) { return (key * 2654435761u) >> tshift; }
+__device__ __forceinline__ bool mtab_has(const uint32_t* tab, int TS, int tshift, int slot, int label) {
+  const uint32_t key = mtab_key(slot, label);
+  unsigned idx = mtab_home(key, tshift);
+  for (;;) {
+    const uint32_t k = tab[idx];
+    if (k == key) return true;
+    if (k == kEmpty) return false;
+    idx = (idx + 1) & (unsigned)(TS - 1);
+  }
+}
+__device__ __forceinline__ void mtab_insert(uint32_t* tab, int TS, int tshift, int slot, int label) {
+  const uint32_t key = mtab_key(slot, label);
+  unsigned idx = mtab_home(key, tshift);
+  for (;;) {
+    const uint32_t old = atomicCAS(&tab[idx], kEmpty, key);
+    if (old == kEmpty || old == key) return;
+    idx = (idx + 1) & (unsigned)(TS - 1);
+  }
+}
+
+template <bool BIG>
+__device__ __forceinline__ bool active_ext(const uint32_t* tab, int CW, int TS, int tshift, int slot, int label) {
+  return BIG ? mtab_has(tab, TS, tshift, slot, label) : (tab[slot * CW + (label >> 5)] >> (label & 31)) & 1u;
+}
+
 struct Ctx {
   // frame constants every candidate evaluation needs
-  const double *lp, *pb, *pt, *ut;
+  const float* x;        // BIG: the frame's logits row, lp[l] = ((double)x[l] - m) - lse
+  const double* lp;      // else: the frame's log-probability row
+  double m, lse;
+  const double *pb, *pt, *ut;
   const u64* hash;
   const int *last, *liveP, *liveL;
-  const uint32_t* mask;
-  int n, nL, CW;
+  const uint32_t* mtab;  // extensions that are already active prefixes: bit sets [W][CW] (CW > 0) or a hash set
+  int n, nL, TS, tshift, CW;
+  bool div32;            // q = j / nL by one 32-bit multiply (exact while W * nL^2 < 2^32)
   unsigned divM;  // floor((2^32-1) / nL) + 1: j / nL == umulhi(j, divM) for j < 2^20 (nL >= 2)
   u64 kkeep, kext;  // smallest key a kept prefix / an extension must have to be a candidate
 };
 
 // Candidate i of the frame: i < n is active prefix i itself (l = -1); otherwise the extension of live prefix
 // liveP[q] by live label liveL[r], i - n = q*nL + r.
+template <bool BIG>
 __device__ __forceinline__ void item_of(const Ctx& c, int i, int& b, int& l) {
   if (i < c.n) {
     b = i;
@@ -174,15 +215,17 @@ __device__ __forceinline__ void item_of(const Ctx& c, int i, int& b, int& l) {
     return;
   }
   const unsigned j = (unsigned)(i - c.n);
-  const unsigned q = c.nL == 1 ? j : __umulhi(j, c.divM);
+  // (beam_width * C < 2^20 and C <= kBitSetMaxC keep the multiply exact; wider vocabularies check per frame)
+  const unsigned q = c.nL == 1 ? j : ((!BIG || c.div32) ? __umulhi(j, c.divM) : j / (unsigned)c.nL);
   b = c.liveP[q];
   l = c.liveL[j - q * (unsigned)c.nL];
 }
 
 // Its key (order-preserving image of its score), 0 if it is not offered to the beam.
+template <bool BIG>
 __device__ __forceinline__ u64 eval_key(const Ctx& c, int i) {
   int b, l;
-  item_of(c, i, b, l);
+  item_of<BIG>(c, i, b, l);
   double v;
   bool ok;
   u64 kmin;
@@ -191,8 +234,8 @@ __device__ __forceinline__ u64 eval_key(const Ctx& c, int i) {
     ok = true;
     kmin = c.kkeep;
   } else {
-    const bool masked = (c.mask[b * c.CW + (l >> 5)] >> (l & 31)) & 1u;
-    v = c.lp[l] + (l == c.last[b] ? c.pb[b] : c.pt[b]);
+    const bool masked = BIG ? mtab_has(c.mtab, c.TS, c.tshift, b, l) : (c.mtab[b * c.CW + (l >> 5)] >> (l & 31)) & 1u;
+    v = (BIG ? ((double)c.x[l] - c.m) - c.lse : c.lp[l]) + (l == c.last[b] ? c.pb[b] : c.pt[b]);
     ok = !masked;
     kmin = c.kext;
   }
@@ -200,11 +243,12 @@ __device__ __forceinline__ u64 eval_key(const Ctx& c, int i) {
   return ok && k >= kmin ? k : 0ull;
 }
 
+template <bool BIG>
 __device__ __forceinline__ u64 item_k2(const Ctx& c, int i) {
   // active prefixes win ties against extensions (TF admits an extension only if it is strictly better than the
   // worst kept entry); then the smaller hash wins
   int b, l;
-  item_of(c, i, b, l);
+  item_of<BIG>(c, i, b, l);
   if (l < 0) return 0x8000000000000000ull | ((~c.hash[b]) >> 1);
   return (~child_hash(c.hash[b], l)) >> 1;
 }
@@ -252,7 +296,10 @@ __device__ __forceinline__ void find_bin(int* hist, int nb, int need, int* wsum,
 
 // STAGE2: second-stage bound on the frame's threshold (phase 2); pays for wide vocabularies, where it shortens the
 // live-label list by one to two orders of magnitude; at C = 38 the lists are short anyway and it costs what it saves.
-template <bool STAGE2>
+// BIG: vocabularies wider than kBitSetMaxC.  Their fp64 log-probability rows (2 x C doubles) and bit sets of active
+// extensions (W x C bits) would not fit shared memory: the rows stay float and lp is computed where it is used, the
+// active extensions become a hash set of (prefix slot, label) pairs.  Narrower ones keep both (6-13 % faster).
+template <bool STAGE2, bool BIG>
 __global__ void __launch_bounds__(kBeamThreads, 2)
 ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long st_t, long long st_b,
                 const int32_t* __restrict__ seq_len, int blank, int W, int P, int merge_repeated,
@@ -261,11 +308,13 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
   extern __shared__ __align__(16) char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b_utt = blockIdx.x;
-  const int CW = L.CW, TS = L.TS;
+  const int TS = L.TS, tshift = L.tshift;
+  const int CW = BIG ? 0 : L.CW;  // 0: the active extensions are a hash set
   const double ninf = neg_inf();
 
 #define BEAM_ARR(T, name, field) T* const name = reinterpret_cast<T*>(smem_raw + L.field)
-  BEAM_ARR(double, s_lp2, lp2);       // log-softmax rows of frame t (t&1) and t+1
+  BEAM_ARR(float, s_x2, x2);          // BIG: logits rows of frame t (t&1) and t+1; their max / log-sum in s_redd
+  BEAM_ARR(double, s_lp2, lp2);       // else: their log-softmax in fp64
   // the two beam buffers are the halves [0,W) and [W,2W) of each array
   BEAM_ARR(double, g_pb, pb);         // log P(prefix, ends in blank)
   BEAM_ARR(double, g_pl, pl);         //                ends in its last label
@@ -287,7 +336,7 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
   BEAM_ARR(u64, s_adm_k, adm_k);
   BEAM_ARR(u64, s_tab_key, tab_key);  // hash -> slot of the prefixes that enter the beam this frame
   BEAM_ARR(int, s_tab_slot, tab_slot);
-  BEAM_ARR(uint32_t, s_mask, mask);   // [W][CW] labels whose extension is already active
+  BEAM_ARR(uint32_t, s_mtab, mtab);   // (prefix slot, label) pairs whose extension is already an active prefix
   BEAM_ARR(int, s_hist, hist);
   BEAM_ARR(double, s_redd, redd);
   BEAM_ARR(u64, s_redu, redu);
@@ -307,7 +356,7 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
   int2* nodes = nodes_all + (size_t)b_utt * ((size_t)T * W + 1);
 
   for (int i = tid; i < kBins; i += kBeamThreads) s_hist[i] = 0;
-  for (int i = tid; i < CW; i += kBeamThreads) s_mask[i] = 0;
+  for (int i = tid; i < (BIG ? TS : CW); i += kBeamThreads) s_mtab[i] = BIG ? kEmpty : 0u;
   if (tid == 0) {
     g_pb[0] = 0.0;
     g_pl[0] = ninf;
@@ -343,8 +392,13 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
       for (int c = lane; c < C; c += 32) sum += exp((double)__ldg(x + c) - m);
       sum = warp_sum(sum);
       const double lse = log(sum);
-      double* lp = s_lp2 + (t & 1) * C;
-      for (int c = lane; c < C; c += 32) lp[c] = ((double)__ldg(x + c) - m) - lse;
+      if (BIG) {
+        float* xs = s_x2 + (t & 1) * C;
+        for (int c = lane; c < C; c += 32) xs[c] = __ldg(x + c);
+      } else {
+        double* lp = s_lp2 + (t & 1) * C;
+        for (int c = lane; c < C; c += 32) lp[c] = ((double)__ldg(x + c) - m) - lse;
+      }
       // the two best labels (blank aside; ties: the smaller index), for the second-stage bound of phase 2
       float v1 = -INFINITY, v2 = -INFINITY;
       int i1 = -1, i2 = -1;
@@ -371,7 +425,9 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
         v2 = bsecond ? b1 : c2v; i2 = bsecond ? bi : c2i;
       }
       if (lane == 0) {
-        s_redd[40 + (t & 1)] = -lse;
+        s_redd[40 + (t & 1)] = -lse;  // the row's best log-probability
+        s_redd[36 + (t & 1)] = m;
+        s_redd[38 + (t & 1)] = lse;
         s_redi[56 + 2 * (t & 1)] = i1;
         s_redi[57 + 2 * (t & 1)] = i2;
       }
@@ -394,7 +450,10 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
   for (int t = 0; t < Tb; t++) {
     if (profiling) tk = clock64();
     const int ao = cur * W, no = (cur ^ 1) * W;  // offsets of the active and of the next beam buffer
-    const double* lp = s_lp2 + (t & 1) * C;
+    const float* xr = s_x2 + (t & 1) * C;
+    const double rm = s_redd[36 + (t & 1)], rlse = s_redd[38 + (t & 1)];
+    const double* lpd = s_lp2 + (t & 1) * C;
+#define BEAM_LP(i) (BIG ? ((double)xr[i] - rm) - rlse : lpd[i])
     const double lpmax = s_redd[40 + (t & 1)];
     const int top1 = s_redi[56 + 2 * (t & 1)], top2 = s_redi[57 + 2 * (t & 1)];
     // ---- 1. active prefixes keep themselves; worst kept score and best old score by warp
@@ -406,12 +465,12 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
         pt_old = g_pt[ao + e];
         double b1 = ninf, b2 = ninf;  // stay on the last label; arrive from the parent prefix
         if (g_len[ao + e] > 0) {
-          const double lpl = lp[last];
+          const double lpl = BEAM_LP(last);
           b1 = g_pl[ao + e] + lpl;
           const int ps = g_pslot[ao + e];
           if (ps >= 0) b2 = (last == g_plast[ao + e] ? g_pb[ao + ps] : g_pt[ao + ps]) + lpl;
         }
-        const double nb = pt_old + lp[blank];
+        const double nb = pt_old + BEAM_LP(blank);
         const double nl = lse2(b1, b2);
         // total' as ONE three-way log-sum-exp, independent of nl's chain (oracle/beam_oracle.py does the same)
         const double mm = fmax(nb, fmax(b1, b2));
@@ -422,10 +481,10 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
         s_newslot[e] = -1;
         // this prefix's extensions by the frame's two best labels: true candidates of the frame (phase 2)
         double c1 = ninf, c2 = ninf;
-        if (STAGE2 && top1 >= 0 && !((s_mask[e * CW + (top1 >> 5)] >> (top1 & 31)) & 1u))
-          c1 = lp[top1] + (top1 == last ? g_pb[ao + e] : pt_old);
-        if (STAGE2 && top2 >= 0 && !((s_mask[e * CW + (top2 >> 5)] >> (top2 & 31)) & 1u))
-          c2 = lp[top2] + (top2 == last ? g_pb[ao + e] : pt_old);
+        if (STAGE2 && top1 >= 0 && !active_ext<BIG>(s_mtab, CW, TS, tshift, e, top1))
+          c1 = BEAM_LP(top1) + (top1 == last ? g_pb[ao + e] : pt_old);
+        if (STAGE2 && top2 >= 0 && !active_ext<BIG>(s_mtab, CW, TS, tshift, e, top2))
+          c2 = BEAM_LP(top2) + (top2 == last ? g_pb[ao + e] : pt_old);
         if (STAGE2) {
           s_c1[e] = c1;
           s_c2[e] = c2;
@@ -512,7 +571,7 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
         }
         for (int c0 = warp * 32; c0 < C; c0 += kSearchThreads) {
           const int cc = c0 + lane;
-          const bool lv = cc < C && cc != blank && lp[cc] + ptmax >= tl;
+          const bool lv = cc < C && cc != blank && BEAM_LP(cc) + ptmax >= tl;
           const unsigned bal = __ballot_sync(0xffffffffu, lv);
           int base = 0;
           if (lane == 0 && bal) base = atomicAdd(&s_redi[23], __popc(bal));
@@ -550,7 +609,7 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
         }
         for (int c0 = warp * 32; c0 < C; c0 += kSearchThreads) {
           const int cc = c0 + lane;
-          const bool lv = cc < C && cc != blank && lp[cc] + ptmax > tau0;
+          const bool lv = cc < C && cc != blank && BEAM_LP(cc) + ptmax > tau0;
           const unsigned bal = __ballot_sync(0xffffffffu, lv);
           int base = 0;
           if (lane == 0 && bal) base = atomicAdd(&s_redi[23], __popc(bal));
@@ -570,8 +629,15 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
     const u64 kkeep = kfloor > kfin ? kfloor : kfin;             // kept prefixes: any finite score, or the bound
     const u64 kext = kfloor > kt0 + 1ull ? kfloor : kt0 + 1ull;  // extensions: strictly above tau0, and the bound
     Ctx c;
-    c.lp = lp; c.pb = g_pb + ao; c.pt = g_pt + ao; c.ut = s_ut; c.hash = g_hash + ao; c.last = g_last + ao;
-    c.liveP = s_liveP; c.liveL = s_liveL; c.mask = s_mask; c.n = n; c.nL = s_redi[23]; c.CW = CW;
+    if (BIG) {
+      c.x = xr; c.m = rm; c.lse = rlse; c.lp = nullptr;
+    } else {
+      c.x = nullptr; c.m = 0.0; c.lse = 0.0; c.lp = lpd;
+    }
+    c.pb = g_pb + ao; c.pt = g_pt + ao; c.ut = s_ut; c.hash = g_hash + ao; c.last = g_last + ao;
+    c.liveP = s_liveP; c.liveL = s_liveL; c.mtab = s_mtab; c.n = n; c.nL = s_redi[23]; c.TS = TS; c.tshift = tshift;
+    c.CW = CW;
+    c.div32 = !BIG || (u64)W * (u64)c.nL * (u64)c.nL < ((u64)1 << 32);
     c.divM = c.nL >= 2 ? 0xffffffffu / (unsigned)c.nL + 1u : 0u;
     c.kkeep = kkeep;
     c.kext = kext;
@@ -586,12 +652,12 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
         key[r] = 0;
         if (r * kSearchThreads < nitems) {
           const int i = tid + r * kSearchThreads;
-          if (i < nitems) key[r] = eval_key(c, i);
+          if (i < nitems) key[r] = eval_key<BIG>(c, i);
           cnt += key[r] != 0;
         }
       }
     } else {
-      for (int i = tid; i < nitems; i += kSearchThreads) cnt += eval_key(c, i) != 0;
+      for (int i = tid; i < nitems; i += kSearchThreads) cnt += eval_key<BIG>(c, i) != 0;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -628,7 +694,7 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
             }
           } else {
             for (int i = tid; i < nitems; i += kSearchThreads) {
-              const u64 k = eval_key(c, i);
+              const u64 k = eval_key<BIG>(c, i);
               if (k && (top >= 64 || ((k ^ prefix) >> top) == 0)) atomicAdd(&s_hist[(int)((k >> shift) & dmask)], 1);
             }
           }
@@ -659,14 +725,14 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
 #pragma unroll
             for (int r = 0; r < kIPT; r++) {
               if (key[r] == F1) {
-                const u64 k = item_k2(c, tid + r * kSearchThreads);
+                const u64 k = item_k2<BIG>(c, tid + r * kSearchThreads);
                 if (top >= 64 || ((k ^ prefix) >> top) == 0) atomicAdd(&s_hist[(int)((k >> shift) & dmask)], 1);
               }
             }
           } else {
             for (int i = tid; i < nitems; i += kSearchThreads) {
-              if (eval_key(c, i) == F1) {
-                const u64 k = item_k2(c, i);
+              if (eval_key<BIG>(c, i) == F1) {
+                const u64 k = item_k2<BIG>(c, i);
                 if (top >= 64 || ((k ^ prefix) >> top) == 0) atomicAdd(&s_hist[(int)((k >> shift) & dmask)], 1);
               }
             }
@@ -692,7 +758,7 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
       for (int r = 0; r < kIPT; r++) {
         const u64 k = key[r];
         if (r * kSearchThreads < nitems && k >= F1 &&
-            !(tie_mode && k == F1 && item_k2(c, tid + r * kSearchThreads) < F2))
+            !(tie_mode && k == F1 && item_k2<BIG>(c, tid + r * kSearchThreads) < F2))
           adm |= 1u << r;
       }
       const int mine = __popc(adm);
@@ -712,8 +778,8 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
       }
     } else {
       for (int i = tid; i < nitems; i += kSearchThreads) {
-        const u64 k = eval_key(c, i);
-        if (k >= F1 && !(tie_mode && k == F1 && item_k2(c, i) < F2)) {
+        const u64 k = eval_key<BIG>(c, i);
+        if (k >= F1 && !(tie_mode && k == F1 && item_k2<BIG>(c, i) < F2)) {
           const int slot = atomicAdd(&s_redi[20], 1);
           if (slot < W) {
             s_adm_i[slot] = i;
@@ -729,7 +795,7 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
     bool orphan = false;
     if (tid < n_new) {
       int b, l;
-      item_of(c, s_adm_i[tid], b, l);
+      item_of<BIG>(c, s_adm_i[tid], b, l);
       const double v = okey_inv(s_adm_k[tid]);
       const int d = no + tid, a = ao + b;
       if (l < 0) {
@@ -771,7 +837,13 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
           idx = (idx + 1) & (unsigned)(TS - 1);
         }
       }
-      for (int w = 0; w < CW; w++) s_mask[tid * CW + w] = 0;
+    }
+    // the set of active extensions is rebuilt in phase 7 for the next frame
+    if (!BIG) {
+      if (tid < n_new)
+        for (int w = 0; w < CW; w++) s_mtab[tid * CW + w] = 0;
+    } else {
+      for (int i = tid; i < TS; i += kSearchThreads) s_mtab[i] = kEmpty;
     }
     bar_search();
     BEAM_TICK(5);
@@ -796,12 +868,18 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
         }
       }
       g_pslot[d] = ps;
-      if (ps >= 0) atomicOr(&s_mask[ps * CW + (g_last[d] >> 5)], 1u << (g_last[d] & 31));
+      if (ps >= 0) {
+        if (!BIG)
+          atomicOr(&s_mtab[ps * CW + (g_last[d] >> 5)], 1u << (g_last[d] & 31));
+        else
+          mtab_insert(s_mtab, TS, tshift, ps, g_last[d]);
+      }
     }
     BEAM_TICK(6);
     __syncthreads();  // frame over; the producer warp has row t+1 ready
     n = n_new;
     cur ^= 1;
+#undef BEAM_LP
   }
   if (profiling)
     for (int k = 0; k < 8; k++) prof[k] = (long long)s_redu[32 + k];
@@ -886,23 +964,17 @@ int ctc_beam_search(const float* logits, int T, int B, int C, long long st_t, lo
   }
   const BeamLayout L = beam_layout(W, C);
   const size_t smem = (size_t)L.total;
-  if (W > kSearchThreads || C > 4095 || (size_t)W * C >= ((size_t)1 << 20) || smem > 200 * 1024) {
-    set_error("ctc_beam_search: beam_width=%d with C=%d is not supported (beam_width <= %d, C <= 4095, %zu bytes of "
+  if (W > kSearchThreads || C > 8192 || (size_t)W * C >= ((size_t)1 << 20) || smem > 200 * 1024) {
+    set_error("ctc_beam_search: beam_width=%d with C=%d is not supported (beam_width <= %d, C <= 8192, %zu bytes of "
               "shared memory needed, 204800 available)", W, C, kSearchThreads, smem);
     return NASR_ERR_UNSUPPORTED;
   }
-  const bool stage2 = C > kStage2MinC;
-  NASR_CUDA(cudaFuncSetAttribute(stage2 ? ctc_beam_kernel<true> : ctc_beam_kernel<false>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const bool stage2 = C > kStage2MinC, big = C > kBitSetMaxC;
+  auto kernel = big ? ctc_beam_kernel<true, true> : (stage2 ? ctc_beam_kernel<true, false> : ctc_beam_kernel<false, false>);
+  NASR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   int2* nodes = reinterpret_cast<int2*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-  if (stage2)
-    ctc_beam_kernel<true><<<B, kBeamThreads, smem, stream>>>(logits, T, B, C, st_t, st_b, seq_len, blank, W, P,
-                                                             merge_repeated, hyp, hyp_len, log_prob, nodes,
-                                                             g_debug_prof, L);
-  else
-    ctc_beam_kernel<false><<<B, kBeamThreads, smem, stream>>>(logits, T, B, C, st_t, st_b, seq_len, blank, W, P,
-                                                              merge_repeated, hyp, hyp_len, log_prob, nodes,
-                                                              g_debug_prof, L);
+  kernel<<<B, kBeamThreads, smem, stream>>>(logits, T, B, C, st_t, st_b, seq_len, blank, W, P, merge_repeated, hyp,
+                                            hyp_len, log_prob, nodes, g_debug_prof, L);
   count_launch();
   NASR_CUDA(cudaGetLastError());
   return NASR_OK;

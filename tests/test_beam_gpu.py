@@ -162,6 +162,15 @@ def test_wide_vocabulary_against_c_port():
     _check_c((rng.normal(size=(40, 2, 1024)) * 3).astype(np.float32), np.array([40, 33], np.int32), W=64, P=2)
 
 
+def test_widest_vocabulary():
+    rng = np.random.default_rng(48)
+    _check_c(_peaky(rng, 40, 2, 8192), np.array([40, 23], np.int32), W=100)
+    _check_c((rng.normal(size=(12, 2, 5000)) * 3).astype(np.float32), np.array([12, 7], np.int32), W=64, P=2)
+    from neuralasr_b200.networks import common
+    with pytest.raises(Exception):
+        common.beam_decoding(torch.zeros((4, 1, 8193), device="cuda"), np.array([4], np.int32))
+
+
 def test_wide_beam():
     rng = np.random.default_rng(45)
     _check_c((rng.normal(size=(60, 2, 38)) * 2).astype(np.float32), np.array([60, 41], np.int32), W=512, P=3)
