@@ -43,7 +43,7 @@ typedef unsigned long long u64;
 #endif
 constexpr int kSearchThreads = NASR_BEAM_SEARCH_THREADS;  // the warps that search (a power of two, 128..512)
 constexpr int kSearchWarps = kSearchThreads / 32;
-constexpr int kBeamThreads = kSearchThreads + 32;   // + one warp that prepares the next frame's log-softmax
+constexpr int kOneProducerMaxC = 1536;              // wider rows get four producer warps
 constexpr int kIPT = 4096 / kSearchThreads;         // candidate keys a search thread keeps in registers
 constexpr int kBins = 2048;                         // 11-bit digits
 constexpr int kBitSetMaxC = 4095;                   // widest vocabulary whose active extensions are kept as bit sets
@@ -299,8 +299,10 @@ __device__ __forceinline__ void find_bin(int* hist, int nb, int need, int* wsum,
 // BIG: vocabularies wider than kBitSetMaxC.  Their fp64 log-probability rows (2 x C doubles) and bit sets of active
 // extensions (W x C bits) would not fit shared memory: the rows stay float and lp is computed where it is used, the
 // active extensions become a hash set of (prefix slot, label) pairs.  Narrower ones keep both (6-13 % faster).
-template <bool STAGE2, bool BIG>
-__global__ void __launch_bounds__(kBeamThreads, 2)
+// NP: producer warps (1, or 4 for rows of more than kOneProducerMaxC classes, whose fp64 softmax one warp cannot
+// finish within a frame's search; then one CTA per SM).
+template <bool STAGE2, bool BIG, int NP>
+__global__ void __launch_bounds__(kSearchThreads + 32 * NP, NP == 1 ? 2 : 1)
 ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long st_t, long long st_b,
                 const int32_t* __restrict__ seq_len, int blank, int W, int P, int merge_repeated,
                 int64_t* hyp, int32_t* __restrict__ hyp_len, float* __restrict__ log_prob,
@@ -355,6 +357,7 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
   const float* xrow = logits + (size_t)b_utt * st_b;
   int2* nodes = nodes_all + (size_t)b_utt * ((size_t)T * W + 1);
 
+  constexpr int kBeamThreads = kSearchThreads + 32 * NP;
   for (int i = tid; i < kBins; i += kBeamThreads) s_hist[i] = 0;
   for (int i = tid; i < (BIG ? TS : CW); i += kBeamThreads) s_mtab[i] = BIG ? kEmpty : 0u;
   if (tid == 0) {
@@ -372,8 +375,14 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
     for (int k = 32; k < 40; k++) s_redu[k] = 0;
   }
 
-  if (warp == kSearchWarps) {
-    // ---- producer warp: log-softmax (fp64) of row t+1 while the others search frame t
+  if (warp >= kSearchWarps) {
+    // ---- producer warps: log-softmax (fp64) of row t+1 while the others search frame t.  Warp pw of NP takes the
+    //      classes pw*32 + lane, pw*32 + lane + 32*NP, ...; with NP > 1 the maxima, sums and best labels of the
+    //      warps meet in shared memory at a named barrier of the producers.
+    const int pw = warp - kSearchWarps, pstep = 32 * NP;
+    auto bar_producers = []() {
+      if (NP > 1) asm volatile("bar.sync 2, %0;" ::"n"(32 * NP) : "memory");
+    };
     for (int t = 0; t <= Tb; t++) {  // Tb + 1 barriers: before frame 0 and after every frame
       if (t == Tb) {
         __syncthreads();
@@ -382,27 +391,26 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
       const float* x = xrow + (size_t)t * st_t;
       if (t + 1 < Tb) {  // pull the row after this one towards L2
         const char* nx = reinterpret_cast<const char*>(x + st_t);
-        for (int o = lane * 128; o < C * 4; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+        for (int o = (pw * 32 + lane) * 128; o < C * 4; o += pstep * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
       }
       float mx = -INFINITY;
-      for (int c = lane; c < C; c += 32) mx = fmaxf(mx, __ldg(x + c));
+      for (int c = pw * 32 + lane; c < C; c += pstep) mx = fmaxf(mx, __ldg(x + c));
       mx = warp_max(mx);
+      if (NP > 1) {
+        if (lane == 0) s_redd[96 + pw] = (double)mx;
+        bar_producers();
+#pragma unroll
+        for (int w = 0; w < NP; w++) mx = fmaxf(mx, (float)s_redd[96 + w]);
+      }
       const double m = (double)mx;
       double sum = 0.0;
-      for (int c = lane; c < C; c += 32) sum += exp((double)__ldg(x + c) - m);
+      for (int c = pw * 32 + lane; c < C; c += pstep) sum += exp((double)__ldg(x + c) - m);
       sum = warp_sum(sum);
-      const double lse = log(sum);
-      if (BIG) {
-        float* xs = s_x2 + (t & 1) * C;
-        for (int c = lane; c < C; c += 32) xs[c] = __ldg(x + c);
-      } else {
-        double* lp = s_lp2 + (t & 1) * C;
-        for (int c = lane; c < C; c += 32) lp[c] = ((double)__ldg(x + c) - m) - lse;
-      }
       // the two best labels (blank aside; ties: the smaller index), for the second-stage bound of phase 2
       float v1 = -INFINITY, v2 = -INFINITY;
       int i1 = -1, i2 = -1;
-      for (int c = lane; STAGE2 && c < C; c += 32) {
+      for (int c = pw * 32 + lane; STAGE2 && c < C; c += pstep) {
         const float v = __ldg(x + c);
         if (c == blank) continue;
         if (v > v1) {
@@ -411,11 +419,8 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
           v2 = v; i2 = c;
         }
       }
-#pragma unroll
-      for (int o = 16; STAGE2 && o > 0; o >>= 1) {
-        const float w1 = __shfl_xor_sync(0xffffffffu, v1, o), w2 = __shfl_xor_sync(0xffffffffu, v2, o);
-        const int j1 = __shfl_xor_sync(0xffffffffu, i1, o), j2 = __shfl_xor_sync(0xffffffffu, i2, o);
-        const bool first = w1 > v1 || (w1 == v1 && (unsigned)j1 < (unsigned)i1);  // the partner's best is the best
+      auto merge2 = [&](float w1, int j1, float w2, int j2) {  // fold another (best, second) pair into ours
+        const bool first = w1 > v1 || (w1 == v1 && (unsigned)j1 < (unsigned)i1);  // the other's best is the best
         const float a1 = first ? w1 : v1, b1 = first ? v1 : w1;  // b1: the loser of the two bests
         const int ai = first ? j1 : i1, bi = first ? i1 : j1;
         const float c2v = first ? w2 : v2;                       // the winner's own second
@@ -423,8 +428,43 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
         const bool bsecond = b1 > c2v || (b1 == c2v && (unsigned)bi < (unsigned)c2i);
         v1 = a1; i1 = ai;
         v2 = bsecond ? b1 : c2v; i2 = bsecond ? bi : c2i;
+      };
+#pragma unroll
+      for (int o = 16; STAGE2 && o > 0; o >>= 1) {
+        const float w1 = __shfl_xor_sync(0xffffffffu, v1, o), w2 = __shfl_xor_sync(0xffffffffu, v2, o);
+        const int j1 = __shfl_xor_sync(0xffffffffu, i1, o), j2 = __shfl_xor_sync(0xffffffffu, i2, o);
+        merge2(w1, j1, w2, j2);
       }
-      if (lane == 0) {
+      if (NP > 1) {
+        if (lane == 0) {
+          s_redd[100 + pw] = sum;
+          s_redd[104 + 4 * pw] = (double)v1;
+          s_redd[105 + 4 * pw] = (double)i1;
+          s_redd[106 + 4 * pw] = (double)v2;
+          s_redd[107 + 4 * pw] = (double)i2;
+        }
+        bar_producers();
+        sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < NP; w++) sum += s_redd[100 + w];  // the same order in every warp
+        if (STAGE2) {
+          v1 = v2 = -INFINITY;
+          i1 = i2 = -1;
+#pragma unroll
+          for (int w = 0; w < NP; w++)
+            merge2((float)s_redd[104 + 4 * w], (int)s_redd[105 + 4 * w], (float)s_redd[106 + 4 * w],
+                   (int)s_redd[107 + 4 * w]);
+        }
+      }
+      const double lse = log(sum);
+      if (BIG) {
+        float* xs = s_x2 + (t & 1) * C;
+        for (int c = pw * 32 + lane; c < C; c += pstep) xs[c] = __ldg(x + c);
+      } else {
+        double* lp = s_lp2 + (t & 1) * C;
+        for (int c = pw * 32 + lane; c < C; c += pstep) lp[c] = ((double)__ldg(x + c) - m) - lse;
+      }
+      if (pw == 0 && lane == 0) {
         s_redd[40 + (t & 1)] = -lse;  // the row's best log-probability
         s_redd[36 + (t & 1)] = m;
         s_redd[38 + (t & 1)] = lse;
@@ -970,10 +1010,21 @@ int ctc_beam_search(const float* logits, int T, int B, int C, long long st_t, lo
     return NASR_ERR_UNSUPPORTED;
   }
   const bool stage2 = C > kStage2MinC, big = C > kBitSetMaxC;
-  auto kernel = big ? ctc_beam_kernel<true, true> : (stage2 ? ctc_beam_kernel<true, false> : ctc_beam_kernel<false, false>);
+  // four producer warps (then one CTA per SM): always for very wide rows; for moderately wide ones while the batch
+  // does not need a second CTA per SM anyway
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    NASR_CUDA(cudaGetDevice(&dev));
+    NASR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const bool four = C > kOneProducerMaxC || (C > kStage2MinC * 4 && B <= num_sms);
+  auto kernel = big ? ctc_beam_kernel<true, true, 4>
+                    : (four ? ctc_beam_kernel<true, false, 4>   /* four implies C > 64: second-stage bound on */
+                            : (stage2 ? ctc_beam_kernel<true, false, 1> : ctc_beam_kernel<false, false, 1>));
   NASR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   int2* nodes = reinterpret_cast<int2*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-  kernel<<<B, kBeamThreads, smem, stream>>>(logits, T, B, C, st_t, st_b, seq_len, blank, W, P, merge_repeated, hyp,
+  kernel<<<B, kSearchThreads + 32 * (four ? 4 : 1), smem, stream>>>(logits, T, B, C, st_t, st_b, seq_len, blank, W, P, merge_repeated, hyp,
                                             hyp_len, log_prob, nodes, g_debug_prof, L);
   count_launch();
   NASR_CUDA(cudaGetLastError());

@@ -12,7 +12,7 @@ from conftest import make_batch  # noqa: E402
 from neuralasr_b200.networks import common  # noqa: E402
 from oracle import c_oracle  # noqa: E402
 
-for (T, B, C, L) in [(500, 32, 3000, 100), (500, 32, 1024, 100), (500, 32, 4000, 60)]:
+for (T, B, C, L) in [(500, 32, 3000, 100), (500, 32, 1024, 100), (500, 32, 4000, 60), (500, 32, 6000, 60), (500, 32, 8192, 60)]:
     g = make_batch(7, T, B, C, L, mode="ragged", peaky=True)
     x = torch.from_numpy(g["logits"]).cuda()
     lab = common.LabelsCSR(torch.from_numpy(g["label_values"]).cuda(), torch.from_numpy(g["label_offsets"]).cuda(),
