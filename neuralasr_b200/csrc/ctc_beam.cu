@@ -295,7 +295,7 @@ __device__ __forceinline__ void find_bin(int* hist, int nb, int need, int* wsum,
 }
 
 // STAGE2: second-stage bound on the frame's threshold (phase 2); pays for wide vocabularies, where it shortens the
-// live-label list by one to two orders of magnitude; at C = 38 the lists are short anyway and it costs what it saves.
+// live-label list by one to two orders of magnitude, and for narrow ones while a CTA has an SM to itself.
 // BIG: vocabularies wider than kBitSetMaxC.  Their fp64 log-probability rows (2 x C doubles) and bit sets of active
 // extensions (W x C bits) would not fit shared memory: the rows stay float and lp is computed where it is used, the
 // active extensions become a hash set of (prefix slot, label) pairs.  Narrower ones keep both (6-13 % faster).
@@ -1009,7 +1009,7 @@ int ctc_beam_search(const float* logits, int T, int B, int C, long long st_t, lo
               "shared memory needed, 204800 available)", W, C, kSearchThreads, smem);
     return NASR_ERR_UNSUPPORTED;
   }
-  const bool stage2 = C > kStage2MinC, big = C > kBitSetMaxC;
+  const bool big = C > kBitSetMaxC;
   // four producer warps (then one CTA per SM): always for very wide rows; for moderately wide ones while the batch
   // does not need a second CTA per SM anyway
   static int num_sms = 0;
@@ -1019,6 +1019,10 @@ int ctc_beam_search(const float* logits, int T, int B, int C, long long st_t, lo
     NASR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const bool four = C > kOneProducerMaxC || (C > kStage2MinC * 4 && B <= num_sms);
+  // second-stage bound: always for wide vocabularies; for narrow ones while there is one CTA per SM (the frame is
+  // then latency bound and the shorter lists pay: B=64, C=38 6.1 -> 5.3 ms on N(0,1)*3, 5.4 -> 5.1 ms on planted
+  // alignments; at B=256 it is -5 % / +5 %, so it stays off there)
+  const bool stage2 = C > kStage2MinC || B <= num_sms;
   auto kernel = big ? ctc_beam_kernel<true, true, 4>
                     : (four ? ctc_beam_kernel<true, false, 4>   /* four implies C > 64: second-stage bound on */
                             : (stage2 ? ctc_beam_kernel<true, false, 1> : ctc_beam_kernel<false, false, 1>));
