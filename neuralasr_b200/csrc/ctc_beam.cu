@@ -301,8 +301,10 @@ __device__ __forceinline__ void find_bin(int* hist, int nb, int need, int* wsum,
 // active extensions become a hash set of (prefix slot, label) pairs.  Narrower ones keep both (6-13 % faster).
 // NP: producer warps (1, or 4 for rows of more than kOneProducerMaxC classes, whose fp64 softmax one warp cannot
 // finish within a frame's search; then one CTA per SM).
-template <bool STAGE2, bool BIG, int NP>
-__global__ void __launch_bounds__(kSearchThreads + 32 * NP, NP == 1 ? 2 : 1)
+// MINB: CTAs per SM the kernel is compiled for: 2 (56 registers, a few spills) when the batch needs two per SM,
+// 1 (96 registers, none) otherwise -- 10 % faster at B=64 in an A/B on one box.
+template <bool STAGE2, bool BIG, int NP, int MINB>
+__global__ void __launch_bounds__(kSearchThreads + 32 * NP, MINB)
 ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long st_t, long long st_b,
                 const int32_t* __restrict__ seq_len, int blank, int W, int P, int merge_repeated,
                 int64_t* hyp, int32_t* __restrict__ hyp_len, float* __restrict__ log_prob,
@@ -1023,9 +1025,12 @@ int ctc_beam_search(const float* logits, int T, int B, int C, long long st_t, lo
   // then latency bound and the shorter lists pay: B=64, C=38 6.1 -> 5.3 ms on N(0,1)*3, 5.4 -> 5.1 ms on planted
   // alignments; at B=256 it is -5 % / +5 %, so it stays off there)
   const bool stage2 = C > kStage2MinC || B <= num_sms;
-  auto kernel = big ? ctc_beam_kernel<true, true, 4>
-                    : (four ? ctc_beam_kernel<true, false, 4>   /* four implies C > 64: second-stage bound on */
-                            : (stage2 ? ctc_beam_kernel<true, false, 1> : ctc_beam_kernel<false, false, 1>));
+  const bool one_cta = B <= num_sms;  // (implies stage2)
+  auto kernel = big ? ctc_beam_kernel<true, true, 4, 1>
+                    : (four ? ctc_beam_kernel<true, false, 4, 1>   /* four implies C > 64: second-stage bound on */
+                            : (one_cta ? ctc_beam_kernel<true, false, 1, 1>
+                                       : (stage2 ? ctc_beam_kernel<true, false, 1, 2>
+                                                 : ctc_beam_kernel<false, false, 1, 2>)));
   NASR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   int2* nodes = reinterpret_cast<int2*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   kernel<<<B, kSearchThreads + 32 * (four ? 4 : 1), smem, stream>>>(logits, T, B, C, st_t, st_b, seq_len, blank, W, P, merge_repeated, hyp,
