@@ -124,3 +124,24 @@ def test_dense_to_sparse_drops_eos():
     idx, vals, shape = dense_to_sparse(np.array([[3, 0, 4], [0, 0, 0], [7, 8, 0]]))
     assert idx.tolist() == [[0, 0], [0, 2], [2, 0], [2, 1]] and vals.tolist() == [3, 4, 7, 8]
     assert shape.tolist() == [3, 3]
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) needs no GPU: one JSON line with the
+    contract's keys, the C port's rate as value."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--workload", "cfg1"], capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "ctc_loss_grad_frames_per_sec" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    for key in ("unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config"):
+        assert key in d
