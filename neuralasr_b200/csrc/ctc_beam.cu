@@ -142,7 +142,7 @@ inline BeamLayout beam_layout(int W, int C) {
   L.CW = (C + 31) / 32;
   L.mtab = take(sizeof(uint32_t) * (L.has_bits ? (size_t)W * L.CW : (size_t)L.TS));
   L.hist = take(sizeof(int) * kBins);
-  L.redd = take(sizeof(double) * 64);
+  L.redd = take(sizeof(double) * 128);  // indices used: 0-59 by the search warps, 96-119 by the producer warps
   L.redu = take(sizeof(u64) * 64);
   L.redi = take(sizeof(int) * 64);
   L.c1 = take(sizeof(double) * W);
@@ -351,7 +351,8 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
   // s_redi: [0..15] warp partials, [16..18] find_bin result, [20] admitted counter,
   //         [22] live prefixes, [23] live labels, [32..47] find_bin warp sums, [56..59] the two best labels of rows t&1
   // s_redd: [0..15] min of the updated totals, [16..31] max of the old totals, [40..41] max of lp rows t&1,
-  //         [44..59] max of the updated totals
+  //         [44..59] max of the updated totals, [36..39] max / log-sum of rows t&1, [96..119] the producer warps' partial maxima,
+  //         sums and best labels
   // s_redu: [32..39] profile accumulators
 
   int Tb = seq_len[b_utt];
