@@ -156,8 +156,8 @@ int nasr_ctc_greedy_decode_strided_i64(const float* logits, int T, int B, int C,
  *   log_prob  float32[B, top_paths]   log P(prefix | logits) under the log-softmax of the logits (-inf when absent)
  * Scores are computed in float64; ties are broken by (kept prefix before new extension, prefix hash).
  * workspace: nasr_ctc_beam_workspace_bytes(T, B, C, beam_width) bytes (the per-utterance prefix trie).
- * Supported: beam_width <= 512, C <= 8192, beam_width * C < 2^20 and a shared-memory footprint under 200 KB
- * (beam_width 100: every C <= 8192); otherwise NASR_ERR_UNSUPPORTED.
+ * Supported: beam_width <= 512, C <= 8192, beam_width * C < 2^20 while C <= 4095, and a shared-memory footprint
+ * under 200 KB (beam_width 100: every C <= 8192); otherwise NASR_ERR_UNSUPPORTED.
  * ---------------------------------------------------------------------------------------------- */
 int nasr_ctc_beam_workspace_bytes(int T, int B, int C, int beam_width, size_t* out_bytes);
 

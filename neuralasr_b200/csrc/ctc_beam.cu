@@ -1007,9 +1007,12 @@ int ctc_beam_search(const float* logits, int T, int B, int C, long long st_t, lo
   }
   const BeamLayout L = beam_layout(W, C);
   const size_t smem = (size_t)L.total;
-  if (W > kSearchThreads || C > 8192 || (size_t)W * C >= ((size_t)1 << 20) || smem > 200 * 1024) {
-    set_error("ctc_beam_search: beam_width=%d with C=%d is not supported (beam_width <= %d, C <= 8192, %zu bytes of "
-              "shared memory needed, 204800 available)", W, C, kSearchThreads, smem);
+  // (beam_width * C < 2^20 keeps the candidate index arithmetic of the narrow-vocabulary build exact; the build for
+  // more than kBitSetMaxC classes checks per frame instead)
+  if (W > kSearchThreads || C > 8192 || (C <= kBitSetMaxC && (size_t)W * C >= ((size_t)1 << 20)) || smem > 200 * 1024) {
+    set_error("ctc_beam_search: beam_width=%d with C=%d is not supported (limits: beam_width <= %d, C <= 8192, "
+              "beam_width * C < 2^20 for C <= %d, shared memory %zu of 204800 bytes)", W, C, kSearchThreads,
+              kBitSetMaxC, smem);
     return NASR_ERR_UNSUPPORTED;
   }
   const bool big = C > kBitSetMaxC;
