@@ -516,3 +516,33 @@ def test_loss_grad_and_decode_capture_into_a_cuda_graph(common):
     hyp, hl, lp = c_oracle.beam_search(g2["logits"], g["seq_len"], 16, 1, True)
     assert np.array_equal(bdec[0].hyp_len.cpu().numpy(), hl[:, 0])
     assert np.allclose(blp.cpu().numpy()[:, 0], lp[:, 0], rtol=1e-6)
+
+
+def test_wide_shapes_sweep(common):
+    """Seeded sweep over wide vocabularies: register-held rows (C <= 1024, C % 4 == 0), streamed rows (wider, odd
+    lengths), batch-major storage and rows offset by one float inside a wider buffer (misaligned)."""
+    rng = np.random.default_rng(777)
+    for case in range(36):
+        C = int(rng.choice([65, 66, 131, 256, 1001, 1024, 1025, 2048, 3187, 6001, 8192]))
+        Lmax = int(rng.integers(1, 120))
+        T = int(rng.integers(max(2 * Lmax + 2, 17), 2 * Lmax + 100))
+        B = int(rng.integers(1, 4))
+        while T * B * C > 12_000_000 and B > 1:
+            B -= 1
+        if T * B * C > 12_000_000:
+            Lmax = max(1, min(Lmax, 12_000_000 // (C * 4)))
+            T = max(2 * Lmax + 2, 17)
+        g = make_batch(5000 + case, T=T, B=B, C=C, Lmax=Lmax, mode=["ragged", "full", "tight"][case % 3],
+                       peaky=bool(case % 2), empty_row=bool(case % 4 == 0))
+        x = torch.from_numpy(g["logits"]).cuda()
+        if case % 3 == 1:
+            x = x.transpose(0, 1).contiguous().transpose(0, 1)
+        elif case % 3 == 2:
+            big = torch.zeros((T, B, C + 3), device="cuda")
+            big[:, :, 1:C + 1] = x
+            x = big[:, :, 1:C + 1]
+        loss, grad, status = common.ctc_loss_and_grad(x, _triple(g), g["seq_len"])
+        want_loss, want_grad, want_status = c_oracle.ctc_loss_grad(
+            g["logits"], g["label_values"], g["label_offsets"], g["seq_len"], precision="f64")
+        _assert_loss_grad(loss.cpu().numpy(), grad.cpu().numpy(), status.cpu().numpy(), want_loss, want_grad,
+                          want_status)
