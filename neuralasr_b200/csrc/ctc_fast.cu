@@ -1254,9 +1254,10 @@ bool is_wide(int C) { return C > 64 && C <= fast::kWideMaxC; }
 // shapes only the streaming producers take; aligned narrower rows are held in registers
 bool stream_only(int C) { return C > fast::kWideRegC || (C & 3) != 0; }
 
-// the wide-vocabulary variant is instantiated for these slot counts only (L <= 126, 158, 222)
+// the wide-vocabulary variant is instantiated for these slot counts only (L <= 126, 158, 222; 318 with streamed
+// rows, whose producers need no row buffers)
 int pick_nl_wide(int Lmax) {
-  static const int kNL[] = {4, 5, 7};
+  static const int kNL[] = {4, 5, 7, 10};
   for (int nl : kNL)
     if (Lmax <= nl * 32 - 2) return nl;
   return 0;
@@ -1305,7 +1306,7 @@ bool ctc_fast_supported(int T, int C, int Lmax) {
   if (T < 2 * fast::KC) return false;
   if (is_wide(C)) {
     const int NL = pick_nl_wide(Lmax);
-    return NL != 0 && fast::smem_layout(NL, 0, C, stream_only(C)).total <= (size_t)kMaxSmem;
+    return NL != 0 && fast::smem_layout(NL, 0, C, stream_only(C) || NL == 10).total <= (size_t)kMaxSmem;
   }
   const int NL = pick_nl(Lmax);
   if (C > 64 || NL == 0) return false;
@@ -1347,6 +1348,7 @@ int ctc_fast_launch(const float* logits, int T, int B, int C, long long st_t, lo
       case 4: return streamed ? launch_fast<4, 0, true>(p, stream) : launch_fast<4, 0>(p, stream);
       case 5: return streamed ? launch_fast<5, 0, true>(p, stream) : launch_fast<5, 0>(p, stream);
       case 7: return streamed ? launch_fast<7, 0, true>(p, stream) : launch_fast<7, 0>(p, stream);
+      case 10: return launch_fast<10, 0, true>(p, stream);  // ten slots per lane leave no room for row buffers
     }
   }
   switch (pick_nl(Lmax)) {

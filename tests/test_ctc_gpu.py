@@ -258,6 +258,8 @@ def _flags(common, B):
     dict(T=100, B=5, C=131, Lmax=25, mode="ragged"),                  # C % 4 != 0: rows at every misalignment, streamed
     dict(T=80, B=3, C=1001, Lmax=20, mode="ragged", peaky=True),
     dict(T=60, B=3, C=3187, Lmax=15, mode="ragged"),
+    dict(T=700, B=2, C=1024, Lmax=300, mode="full", empty_row=False),  # wide with 223..318 labels: ten slots per lane
+    dict(T=680, B=2, C=3000, Lmax=318, mode="ragged", empty_row=False),
 ])
 def test_each_kernel_alone_matches_oracle(common, debug_paths, kw):
     g = make_batch(4242, **kw)
