@@ -303,7 +303,10 @@ __device__ __forceinline__ void find_bin(int* hist, int nb, int need, int* wsum,
 // finish within a frame's search; then one CTA per SM).
 // MINB: CTAs per SM the kernel is compiled for: 2 (56 registers, a few spills) when the batch needs two per SM,
 // 1 (96 registers, none) otherwise -- 10 % faster at B=64 in an A/B on one box.
-template <bool STAGE2, bool BIG, int NP, int MINB>
+// CO ("cached only"): beam_width * (C + 1) candidates always fit the register-cached path, so the passes that
+// recompute candidates are compiled out -- the kernel spends 2.7 cycles per issued instruction waiting for
+// instruction fetch at two CTAs per SM (ncu), and a third of its loop body is those passes.
+template <bool STAGE2, bool BIG, int NP, int MINB, bool CO>
 __global__ void __launch_bounds__(kSearchThreads + 32 * NP, MINB)
 ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long st_t, long long st_b,
                 const int32_t* __restrict__ seq_len, int blank, int W, int P, int merge_repeated,
@@ -685,7 +688,7 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
     c.kkeep = kkeep;
     c.kext = kext;
     const int nitems = n + s_redi[22] * c.nL;
-    const bool cached = nitems <= kIPT * kSearchThreads;  // else: recompute the candidates in every pass
+    const bool cached = CO || nitems <= kIPT * kSearchThreads;  // else: recompute the candidates in every pass
     // ---- 3. the candidates' keys and how many they are
     u64 key[kIPT];
     int cnt = 0;
@@ -719,7 +722,7 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
     if (cnt > W) {
       int need = W;
       const u64 diff = kmin ^ kmax;
-      if (diff == 0) {
+      if (__builtin_expect(diff == 0, 0)) {
         F1 = kmax;
         tie_mode = true;
       } else {
@@ -757,7 +760,7 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
           }
         }
       }
-      if (tie_mode) {
+      if (__builtin_expect(tie_mode, 0)) {  // rare: keep it out of the hot path's instruction stream
         // order the candidates that share the threshold score by (active first, hash)
         u64 prefix = 0;
         int top = 64;
@@ -1030,11 +1033,14 @@ int ctc_beam_search(const float* logits, int T, int B, int C, long long st_t, lo
   // alignments; at B=256 it is -5 % / +5 %, so it stays off there)
   const bool stage2 = C > kStage2MinC || B <= num_sms;
   const bool one_cta = B <= num_sms;  // (implies stage2)
-  auto kernel = big ? ctc_beam_kernel<true, true, 4, 1>
-                    : (four ? ctc_beam_kernel<true, false, 4, 1>   /* four implies C > 64: second-stage bound on */
-                            : (one_cta ? ctc_beam_kernel<true, false, 1, 1>
-                                       : (stage2 ? ctc_beam_kernel<true, false, 1, 2>
-                                                 : ctc_beam_kernel<false, false, 1, 2>)));
+  const bool co = (size_t)W * ((size_t)C + 1) <= (size_t)kIPT * kSearchThreads;  // every frame fits the cached path
+  auto kernel = big ? ctc_beam_kernel<true, true, 4, 1, false>
+                    : (four ? ctc_beam_kernel<true, false, 4, 1, false>   /* four implies C > 64: second-stage bound on */
+                            : (one_cta ? (co ? ctc_beam_kernel<true, false, 1, 1, true>
+                                             : ctc_beam_kernel<true, false, 1, 1, false>)
+                                       : (stage2 ? ctc_beam_kernel<true, false, 1, 2, false>
+                                                 : (co ? ctc_beam_kernel<false, false, 1, 2, true>
+                                                       : ctc_beam_kernel<false, false, 1, 2, false>))));
   NASR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   int2* nodes = reinterpret_cast<int2*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   kernel<<<B, kSearchThreads + 32 * (four ? 4 : 1), smem, stream>>>(logits, T, B, C, st_t, st_b, seq_len, blank, W, P, merge_repeated, hyp,
