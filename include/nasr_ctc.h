@@ -253,7 +253,8 @@ uint64_t nasr_launch_count(void);
  * Change it only between calls, and query nasr_ctc_workspace_bytes again afterwards. */
 int nasr_debug_config(int path, int split_frames);
 
-/* Test/tuning hook: when device_buffer is non-NULL the throughput kernel writes, per utterance and warp,
+/* Tuning hook, active only in a library built with -DNASR_TUNING=1 (NASR_TUNING=1 python -m neuralasr_b200._build;
+ * production builds compile it out: it costs the throughput kernel 14 %): when device_buffer is non-NULL the throughput kernel writes, per utterance and warp,
  * int64[4] = {cycles of work before the meeting, cycles of work after it, total cycles, warp role} to
  * device_buffer[(b*16 + warp)*4 ...] (B*16*4 int64, then a per-iteration trace of the first four utterances:
  * 4*200*8*2 int64).  NULL switches it off (the default). */

@@ -39,7 +39,11 @@ def build_library(force=False, verbose=False):
     if not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + [
+    # NASR_TUNING=1 in the environment compiles the tuning hooks in (per-role / per-phase cycle counters behind
+    # nasr_debug_profile, the ablation bits of nasr_debug_config): tools/gpu_fast_check.py roles, tools/gpu_beam_check.py
+    # phases need them; production builds leave them out (cfg3 loss+grad 0.332 -> 0.285 ms without them).
+    tuning = ["-DNASR_TUNING=1"] if os.environ.get("NASR_TUNING") == "1" else []
+    cmd = [_nvcc()] + NVCC_FLAGS + tuning + [
         "-I" + os.path.join(ROOT, "include"), "-I" + CSRC, "-o", LIB_PATH,
     ] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:

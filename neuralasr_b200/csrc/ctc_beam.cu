@@ -32,6 +32,11 @@
 
 #include "nasr_common.cuh"
 
+// The phase ticks behind nasr_debug_profile are compiled in only with -DNASR_TUNING=1 (see ctc_fast.cu).
+#ifndef NASR_TUNING
+#define NASR_TUNING 0
+#endif
+
 namespace nasr {
 extern long long* g_debug_prof;  // ctc_fast.cu (nasr_debug_profile)
 namespace {
@@ -484,7 +489,7 @@ ctc_beam_kernel(const float* __restrict__ logits, int T, int B, int C, long long
 
   // tuning hook (nasr_debug_profile): thread 0 of CTA 0 accumulates the cycles of each phase of the frame loop
   long long tk = 0;  // the accumulators live in s_redu[32..39]
-  const bool profiling = prof != nullptr && blockIdx.x == 0 && tid == 0;
+  const bool profiling = NASR_TUNING && prof != nullptr && blockIdx.x == 0 && tid == 0;
 #define BEAM_TICK(k)                    \
   if (profiling) {                      \
     const long long now_ = clock64();   \

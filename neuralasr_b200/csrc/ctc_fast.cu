@@ -34,6 +34,14 @@
 
 #include "nasr_common.cuh"
 
+// Tuning hooks (nasr_debug_profile, the ablation bits of nasr_debug_config) are compiled in only with -DNASR_TUNING=1:
+// the kernel is ~130 KB of SASS and waits on instruction fetch, so production builds do not carry them.
+#ifndef NASR_TUNING
+#define NASR_TUNING 0
+#endif
+#define NASR_PROF_PTR(p) (NASR_TUNING ? (p).prof : (long long*)nullptr)
+#define NASR_ABLATE(p) (NASR_TUNING ? (p).ablate : 0)
+
 namespace nasr {
 namespace fast {
 
@@ -832,14 +840,14 @@ ctc_fast_kernel(const Params p) {
   const long long prof_t0 = clock64();
   // Each role runs its own copy of the iteration loop (same trip count, one CTA barrier per iteration) so
   // that a warp keeps only its own role's state in registers.
-#define NASR_PROF_BEGIN() const long long prof_a = p.prof ? clock64() : 0
+#define NASR_PROF_BEGIN() const long long prof_a = NASR_PROF_PTR(p) ? clock64() : 0
 #define NASR_PROF_END()                                    \
-  if (p.prof) {                                            \
+  if (NASR_PROF_PTR(p)) {                                            \
     const long long pe = clock64();                        \
     const long long dt = pe - prof_a;                      \
     if (I < S.P1) prof_w1 += dt; else prof_w2 += dt;       \
     if (b < 4 && lane == 0 && warp < 8 && I - IFIRST < 200) {  \
-      long long* tr = p.prof + (size_t)p.B * 64 + (((size_t)b * 200 + (I - IFIRST)) * 8 + warp) * 2; \
+      long long* tr = NASR_PROF_PTR(p) + (size_t)p.B * 64 + (((size_t)b * 200 + (I - IFIRST)) * 8 + warp) * 2; \
       tr[0] = prof_a - prof_t0;                            \
       tr[1] = pe - prof_t0;                                \
     }                                                      \
@@ -958,7 +966,7 @@ ctc_fast_kernel(const Params p) {
       // this warp computes direction d's rows; they are consumed by the other direction (side d^1)
       const int side = d ^ 1;
       const Chunk ci = chunk_at(S, side, I + 1);
-      if (ci.phase == 2 && want_grad && !(p.ablate & 4)) {
+      if (ci.phase == 2 && want_grad && !(NASR_ABLATE(p) & 4)) {
         const uint32_t* ck = ckpt_ptr<NL>(p, b, d, ci.idx);
 #pragma unroll
         for (int k = 0; k < NL; k++) {
@@ -1081,7 +1089,7 @@ ctc_fast_kernel(const Params p) {
       NASR_PROF_BEGIN();
       {  // raw rows of the chunk of iteration I+2 (complete and visible since the last barrier) -> row records
         const Chunk ci = chunk_at(S, d, I + 2);
-        if (ci.phase != 0 && (ci.phase == 1 || (want_grad && !(p.ablate & 2)))) {
+        if (ci.phase != 0 && (ci.phase == 1 || (want_grad && !(NASR_ABLATE(p) & 2)))) {
           unsigned char* rows = s_rows + (size_t)(d * 4 + ((I + 2) & 3)) * KC * rowbytes;
           const float* raw = s_raw + (size_t)(d * 4 + ((I + 2) & 3)) * KC * CMAX;
           const float l0v = rows_to_smem<EPL, ROWB, YOFF>(raw, rl, ci.len, rows, C, blank, s_scal);
@@ -1095,7 +1103,7 @@ ctc_fast_kernel(const Params p) {
       }
       {  // issue the copies for the chunk of iteration I+5 (one commit group per iteration, empty or not)
         const Chunk ci = chunk_at(S, d, I + 5);
-        if (ci.phase != 0 && (ci.phase == 1 || (want_grad && !(p.ablate & 2)))) {
+        if (ci.phase != 0 && (ci.phase == 1 || (want_grad && !(NASR_ABLATE(p) & 2)))) {
           float* raw = s_raw + (size_t)(d * 4 + ((I + 5) & 3)) * KC * CMAX;
 #pragma unroll
           for (int g = 0; g < KC / 4; g++) {
@@ -1134,7 +1142,7 @@ ctc_fast_kernel(const Params p) {
       // posterior rows are in class-sorted order: an inclusive prefix sum turns "occupancy of class c" into
       // the difference of two prefixes
       const Chunk ci = chunk_at(S, d, I - 1);
-      if (ci.phase == 2 && want_grad && !(p.ablate & 1)) {
+      if (ci.phase == 2 && want_grad && !(NASR_ABLATE(p) & 1)) {
         const int buf = (I - 1) & 1;
         float* G = s_gbuf + (size_t)(d * 2 + buf) * GBUF;
         const unsigned char* rows = s_rows + (size_t)(d * 4 + ((I - 1) & 3)) * KC * rowbytes;
@@ -1221,8 +1229,8 @@ ctc_fast_kernel(const Params p) {
   }
 #undef NASR_PROF_BEGIN
 #undef NASR_PROF_END
-  if (p.prof && lane == 0) {
-    long long* q = p.prof + ((size_t)b * 16 + warp) * 4;
+  if (NASR_PROF_PTR(p) && lane == 0) {
+    long long* q = NASR_PROF_PTR(p) + ((size_t)b * 16 + warp) * 4;
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     q[0] = prof_w1; q[1] = prof_w2; q[2] = clock64() - prof_t0; q[3] = role | ((long long)smid << 8);

@@ -47,7 +47,8 @@ if __name__ == "__main__":
 
 
 def phases(name, x, W=100):
-    """Cycles per frame of each phase of the frame loop (CTA 0), through nasr_debug_profile."""
+    """Cycles per frame of each phase of the frame loop (CTA 0), through nasr_debug_profile.  Needs a library built
+    with the tuning hooks (NASR_TUNING=1 python -m neuralasr_b200._build); a production build reports zeros."""
     import ctypes
     from neuralasr_b200 import _lib
     lib = _lib.load()
