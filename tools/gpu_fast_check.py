@@ -1,5 +1,7 @@
 """Bring-up check of the throughput CTC kernel on a GPU box: per-utterance errors against the C oracle
-with the kernel running alone (debug path 2), the utterances it hands to the robust kernel, and timings."""
+with the kernel running alone (debug path 2), the utterances it hands to the robust kernel, and timings.
+The per-role cycle counts (`roles`, `roles5`, traces) and the ablation runs need a library built with the tuning hooks:
+NASR_TUNING=1 python -m neuralasr_b200._build  (production builds compile them out)."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
