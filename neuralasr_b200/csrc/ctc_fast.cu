@@ -318,14 +318,17 @@ __device__ __forceinline__ void step(Dir<NL>& s, const unsigned char* erow, uint
 
 // Advance one direction over a chunk of `len` frames whose row records start at erows (consumer order).
 // reverse: walk the records backwards (recompute warps run against the consumer's order).
-template <int NL, int MODE, int ROWB>
+// UNR: unroll factor of the eight-frame chunk loop.  The kernel waits on instruction fetch, so the right factor is
+// not the largest: measured (same-box A/B) 8 is best for the narrow kernel at small batches, 2 for the wide variant
+// (cfg5 0.317 -> 0.309 ms) and within 1 % of 8 for the narrow kernel at cfg3.
+template <int NL, int MODE, int ROWB, int UNR = KC>
 __device__ __forceinline__ void run_chunk(Dir<NL>& s, const unsigned char* erows, int len,
                                           bool reverse, uint32_t* obuf, float* gbuf, double fin,
                                           int kshift, const uint32_t (&gphys)[NL], int lane) {
   constexpr int rowbytes = ROWB;
   constexpr int gstride = NL * 32 + 4;
   if (len == KC) {
-#pragma unroll
+#pragma unroll(UNR)
     for (int g = 0; g < KC; g++) {
       const int f = reverse ? KC - 1 - g : g;
       step<NL, MODE>(s, erows + f * rowbytes, obuf + f * (NL * 32), reinterpret_cast<unsigned char*>(gbuf + f * gstride),
@@ -869,7 +872,7 @@ ctc_fast_kernel(const Params p) {
         }
         ck[2 * NL * 32 + lane] = (uint32_t)st.E;
         const double fin = inflow_factor(st.E, lane);
-        run_chunk<NL, PLAIN, ROWB>(st, erows, ci.len, false, s_obuf, s_gbuf, fin, 0, gphys, lane);
+        run_chunk<NL, PLAIN, ROWB, (WIDE ? 2 : KC)>(st, erows, ci.len, false, s_obuf, s_gbuf, fin, 0, gphys, lane);
         if (d == 1 && I == S.P1 - 1) {
           // pre-emission sums of the frame below the meeting point, for the forward warp
           rescale<NL>(st, lane, alarm);
@@ -952,7 +955,7 @@ ctc_fast_kernel(const Params p) {
           if (ks > ZALARM) alarm |= AL_RANGE;
           ks = max(-2047, min(ks, 600));
         }
-        run_chunk<NL, COMBINE, ROWB>(st, erows, ci.len, false, s_obuf + (size_t)(d * 2 + buf) * OBUF,
+        run_chunk<NL, COMBINE, ROWB, (WIDE ? 2 : KC)>(st, erows, ci.len, false, s_obuf + (size_t)(d * 2 + buf) * OBUF,
                                      s_gbuf + (size_t)(d * 2 + buf) * GBUF, fin, ks * (1 << 20), gphys, lane);
       }
       NASR_PROF_END();
@@ -978,7 +981,7 @@ ctc_fast_kernel(const Params p) {
         const int buf = (I + 1) & 1;
         s_oexp[(side * 2 + buf) * 32 + lane] = st.E;
         const unsigned char* erows = s_rows + (size_t)(side * 4 + ((I + 1) & 3)) * KC * rowbytes;
-        run_chunk<NL, STORE_O, ROWB>(st, erows, ci.len, true, s_obuf + (size_t)(side * 2 + buf) * OBUF, s_gbuf, fin, 0,
+        run_chunk<NL, STORE_O, ROWB, (WIDE ? 2 : KC)>(st, erows, ci.len, true, s_obuf + (size_t)(side * 2 + buf) * OBUF, s_gbuf, fin, 0,
                                      gphys, lane);
       }
       NASR_PROF_END();
