@@ -16,6 +16,10 @@ HEADERS = [os.path.join(CSRC, "nasr_common.cuh"), os.path.join(ROOT, "include", 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
+    # the shared CUDA runtime: the process has one runtime (torch's libcudart.so.12 when torch is imported first)
+    # and the library does not embed a private copy of every runtime entry point
+    "--cudart=shared",
+    "-Xlinker", "-rpath=/usr/local/cuda/lib64",
 ]
 
 
