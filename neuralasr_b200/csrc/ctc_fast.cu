@@ -31,6 +31,7 @@
 //   recursion warps  advance alpha / beta over the chunk of iteration I (phase 2: emit posteriors);
 //   gradient warps   reduce the posteriors of iteration I-1 by class and write grad rows.
 #include <math.h>
+#include <stdlib.h>
 
 #include "nasr_common.cuh"
 
@@ -1301,6 +1302,16 @@ int launch_fast_c(const fast::Params& p, cudaStream_t stream) {
 
 }  // namespace
 
+// implemented in ctc_narrow.cu: the float32 kernel for C <= 64 and transcripts up to 254 labels
+bool ctc_narrow_supported(int T, int C, int Lmax);
+bool ctc_narrow_layout_ok(const float* logits, long long st_t, long long st_b);
+size_t ctc_narrow_workspace_bytes(int T, int B, int C, int Lmax);
+int ctc_narrow_launch(const float* logits, int T, int B, int C, long long st_t, long long st_b,
+                      const int32_t* label_values, const int32_t* label_offsets, int Lmax, const int32_t* seq_len,
+                      int blank, float* loss, float* grad, const float* grad_loss, int32_t* status, int32_t* retry,
+                      void* ckpt, cudaStream_t stream);
+int g_debug_old_narrow = 0;  // test hook (nasr_debug_config, environment NASR_OLD_NARROW=1): keep the fp64 kernel for C <= 64
+
 int g_debug_split = 0;  // test hook (nasr_debug_config): frames of the forward half, 0 = automatic
 int g_debug_ablate = 0;
 long long* g_debug_prof = nullptr;  // test hook (nasr_debug_profile): device buffer for per-warp cycle counts
@@ -1325,9 +1336,11 @@ bool ctc_fast_supported(int T, int C, int Lmax) {
 }
 
 size_t ctc_fast_workspace_bytes(int T, int B, int C, int Lmax) {
-  if (!ctc_fast_supported(T, C, Lmax)) return 0;
+  const size_t nw = ctc_narrow_workspace_bytes(T, B, C, Lmax);
+  if (!ctc_fast_supported(T, C, Lmax)) return nw;
   const int NL = is_wide(C) ? pick_nl_wide(Lmax) : pick_nl(Lmax);
-  return (size_t)B * 2 * max_chunks(T) * (2 * NL + 1) * 32 * sizeof(uint32_t);
+  const size_t ow = (size_t)B * 2 * max_chunks(T) * (2 * NL + 1) * 32 * sizeof(uint32_t);
+  return ow > nw ? ow : nw;
 }
 
 int ctc_fast_launch(const float* logits, int T, int B, int C, long long st_t, long long st_b,
@@ -1335,6 +1348,10 @@ int ctc_fast_launch(const float* logits, int T, int B, int C, long long st_t, lo
                     const int32_t* label_offsets, int Lmax, const int32_t* seq_len, int blank, float* loss,
                     float* grad, const float* grad_loss, int32_t* status, int32_t* retry, void* ckpt,
                     cudaStream_t stream) {
+  static const bool env_old = getenv("NASR_OLD_NARROW") != nullptr;
+  if (!env_old && !g_debug_old_narrow && ctc_narrow_supported(T, C, Lmax) && ctc_narrow_layout_ok(logits, st_t, st_b))
+    return ctc_narrow_launch(logits, T, B, C, st_t, st_b, label_values, label_offsets, Lmax, seq_len, blank, loss, grad,
+                             grad_loss, status, retry, ckpt, stream);
   fast::Params p;
   p.logits = logits; p.T = T; p.B = B; p.C = C; p.st_t = st_t; p.st_b = st_b;
   p.lab_vals = label_values; p.lab_offs = label_offsets; p.seq_len = seq_len;

@@ -31,7 +31,7 @@ import numpy as np
 
 SEG = 8           # frames between renormalisations / checkpoints
 TB = 60           # biased exponent the larger state of a slot is brought to (2^-67)
-BIG = np.float32(2.0 ** 96)  # label values saturate here: with F <= 2^GCAP nothing can reach inf, so no NaN can arise
+BIG = np.float32(2.0 ** 90)  # label values saturate here: with F <= 2^GCAP nothing can reach inf, so no NaN can arise
 GCAP = 30         # a slot with mass sits at most this far below the slot with mass beneath it
 PSHIFT = 64       # the posterior buffer holds posterior * 2^-PSHIFT (two values near 2^(TB-127) are multiplied)
 FCLAMP = GCAP     # largest exponent of a transfer factor
@@ -121,8 +121,8 @@ class Dir:
         h = dd // 2
         with np.errstate(over="ignore", under="ignore", invalid="ignore"):
             s1, s2 = _pow2(h), _pow2(dd - h)
-            self.Ab = np.minimum(((self.Ab * s1).astype(np.float32) * s2).astype(np.float32), BIG)
-            self.Al = np.minimum(((self.Al * s1).astype(np.float32) * s2).astype(np.float32), BIG)
+            self.Ab = ((self.Ab * s1).astype(np.float32) * s2).astype(np.float32)
+            self.Al = ((self.Al * s1).astype(np.float32) * s2).astype(np.float32)
         self.E = Enew.copy()
         self._set_F()
 
@@ -133,7 +133,11 @@ class Dir:
         if np.any(ex >= 255) or np.any(np.isnan(self.Ab)) or np.any(np.isnan(self.Al)):
             self.alarm = True
         self.maxexp = max(self.maxexp, int(ex.max()))
-        nz = (ex > 0) & (self.E != ENEG)
+        # a slot whose values have decayed into the denormals still holds mass: exponent from m * 2^64
+        with np.errstate(over="ignore", under="ignore"):
+            exd = ((m * f32(2.0 ** 64)).astype(np.float32).view(np.uint32).astype(np.int64) >> 23) - 64
+        ex = np.where(ex == 0, exd, ex)
+        nz = (m > 0) & (self.E != ENEG)
         own = np.where(nz, self.E + ex - TB, ENEG)
         Enew = np.full(self.N, ENEG, dtype=np.int64)
         NL = self.NL
@@ -188,7 +192,7 @@ def ctc_loss_grad_model(x, lab, blank, NL=8, split=None):
     info = {"alarm": False}
     if not (np.all(np.isfinite(rs)) and R.min() >= f32(1.1754944e-38)):
         return None, None, {"alarm": True, "why": "emission"}
-    M = SEG * int(round(Tb / (2.0 * SEG))) if split is None else int(split)
+    M = SEG * ((Tb + SEG) // (2 * SEG)) if split is None else (int(split) // SEG) * SEG
     M = max(SEG, min(M, SEG * ((Tb - 1) // SEG)))
     info["M"] = M
     fw, bw = Dir(lab, N, False), Dir(lab, N, True)

@@ -22,6 +22,8 @@ gs = [torch.empty_like(xs[0]) for _ in range(5)]
 for i in range(5):
     common.ctc_loss_and_grad(xs[i], lab, seq_d, out_grad=gs[i])
 torch.cuda.synchronize()
+rf = common.retry_flags(dev, B).cpu().numpy()
+print("utterances handed to the robust kernel: %d of %d, reasons %s" % (int((rf != 0).sum()), B, sorted(set(rf[rf != 0].tolist()))), flush=True)
 res = []
 for rep in range(3):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
