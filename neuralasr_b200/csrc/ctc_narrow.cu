@@ -7,16 +7,18 @@
 // The kernel is bound by instruction issue and the shared-memory pipe, not by HBM (12*C bytes per frame are nothing
 // next to ~200 warp instructions per frame), so everything here is arranged to execute few instructions:
 //
-//   * linear-domain recursion in "ratio units", R[t][c] = exp(x[t][c] - x[t][blank]): blank states need no multiply
-//     (and can only grow), log p gets sum_t log y_blank(t) added back;
+//   * linear-domain recursion on emissions in units of u(t) = max(y_blank(t), y_max(t) / 32): R[t][c] = y[t][c] / u(t)
+//     <= 32.  Units of the blank's probability (one multiply per slot cheaper) let the band of a peaked alignment grow
+//     by 2^29 per label and ran into the cap below; units of the largest class cost the band of a flat frame ~9 bits
+//     and ran out of float32 at the other end.  log p gets sum_t log u(t) added back;
 //   * slot i = (blank state 2(i-1), label state 2(i-1)+1); lane l of a recursion warp owns the NL consecutive slots
-//     [l*NL, (l+1)*NL) in registers; a frame is, per slot, one LDS (the label's emission) and four float operations
-//     (two FFMA, FADD, FMUL), plus ONE shuffle for the neighbour lane's last label value;
+//     [l*NL, (l+1)*NL) in registers; a frame is, per slot, one LDS (the label's emission), five float operations
+//     (two FFMA, FADD, two FMUL) and the cap, plus ONE shuffle for the neighbour lane's last label value;
 //   * the backward recursion is the same code on the reversed label string over descending frames;
 //   * float32 values with one integer exponent PER SLOT: true = stored * 2^E[k].  What crosses from slot k-1 into
 //     slot k is multiplied by F[k] = 2^(E[k-1]-E[k]) inside the fused multiply-add that consumes it.  Every KC = 8
 //     frames each slot is renormalised (larger state -> 2^(TB-127)) subject to E[k] >= E[k-1] - GCAP, so F <= 2^GCAP;
-//     label values saturate at 2^90, hence nothing can reach inf and no NaN can arise from 0 * inf;
+//     label values saturate at 2^100, hence nothing can reach inf and no NaN can arise from 0 * inf;
 //   * meet in the middle: the forward warp covers frames [0,M) while the backward warp covers [M,Tb), each leaving a
 //     checkpoint (state + exponents) per chunk; p comes from the two at the meeting point; then each continues through
 //     the other half.  There the SAME warp first regenerates the other direction's eight label rows of the chunk from
@@ -33,9 +35,9 @@
 //     label occupancy may exceed 1 and no state may turn non-finite, else retry[b] hands the utterance to the robust
 //     kernel.
 //
-// Data movement: a frame's logits row (4*C bytes, 8-byte aligned at C = 38) travels global -> shared memory as ONE
-// bulk copy (cp.async.bulk, the TMA's 1-D form) of the 16-byte aligned superset of the row, completing on an mbarrier;
-// the producer warp converts 32 rows at a time, one row per lane, in place.  Warps hand chunks to each other through
+// Data movement: a frame's logits row (4*C bytes, 8-byte aligned at C = 38) travels global -> shared memory as the
+// 16-byte cp.async pieces of its 16-byte aligned superset, 32 rows per instruction; the producer warp converts 32
+// rows at a time, one row per lane, in place.  Warps hand chunks to each other through
 // monotonic counters in shared memory (st.release / ld.acquire): there is no CTA-wide barrier in the main loop.
 //
 //   warp 0,1  recursion forward / backward (phase 2: recompute of the other direction + combine)
@@ -51,8 +53,8 @@ namespace lean {
 constexpr int KC = 8;             // frames per chunk (= renormalisation and checkpoint interval)
 constexpr int NST = 10;           // chunks of row records per side in the ring
 constexpr int NTHREADS = 160;     // 5 warps
-constexpr int TB = 60;            // biased exponent a slot's larger state is brought to (2^-67)
-constexpr int GCAP = 30;          // a slot with mass sits at most this far below the slot with mass beneath it
+constexpr int TB = 107;           // biased exponent a slot's larger state is brought to (2^-20)
+constexpr int GCAP = 20;          // a slot with mass sits at most this far below the slot with mass beneath it
 constexpr int PSHIFT = 64;        // the posterior buffer holds posterior * 2^-PSHIFT
 constexpr int ENEG = -(1 << 28);  // exponent tag of a slot that can never receive mass
 constexpr int ROWW = 76;          // words per row record: odd number of 16-byte vectors (one row per lane, no bank
@@ -63,14 +65,15 @@ constexpr int GSB = GS * 4;
 constexpr int GCELLS = GS - 4;    // cells that may hold posteriors; the last four are dump cells of label-less slots
 constexpr int NGRP = 16;          // class groups of four (63 label classes at most)
 constexpr float kTol = 3e-5f;
-// Label values saturate here (2^90).  Mass that climbs a run of slots each GCAP bits below the one beneath it gains
+constexpr float kUnitGap = 3.4657359f;   // 5 ln 2: see the producer
+// Label values saturate here (2^100).  Mass that climbs a run of slots each GCAP bits below the one beneath it gains
 // 2^GCAP in stored units per slot and can cross eight slots in a chunk: without the cap it reaches inf in slots ahead
-// of the band that carries the posterior (measured: a quarter of the cfg3 utterances).  With F <= 2^30 eight frames of
-// inflow stay below 2^127, so nothing ever reaches inf; what saturation removes the certificate accounts for.
-#define NASR_BIG 1.2379400e27f
+// of the band that carries the posterior (measured: a quarter of the cfg3 utterances).  With F <= 2^20 eight frames of
+// inflow stay below 2^124, so nothing ever reaches inf; what saturation removes the certificate accounts for.
+#define NASR_BIG 1.2676506e30f
 
 enum Role { R_F = 0, R_B = 1, PROD = 2, G_F = 3, G_B = 4 };
-enum Alarm { AL_SHAPE = 1, AL_EMISSION = 2, AL_NONFINITE = 4, AL_P = 32, AL_CERT = 128, AL_OCC = 256 };
+enum Alarm { AL_SHAPE = 1, AL_EMISSION = 2, AL_NONFINITE = 4, AL_SAT = 8, AL_P = 32, AL_CERT = 128, AL_OCC = 256 };
 // counters in shared memory (each written by one warp at a time, only ever increasing)
 enum Flag { FL_READY = 0, FL_FREED = 2, FL_GFULL = 4, FL_GFREE = 6, FL_MEETB = 8, FL_MEETP = 9, NFLAGS = 16 };
 
@@ -222,10 +225,11 @@ __device__ __forceinline__ void sts_f(unsigned char* smem, uint32_t off, float v
 // from the other direction's label values o[] of the same frame.
 template <int NL, bool COMBINE>
 __device__ __forceinline__ void own_frame(float (&A)[NL], float (&B)[NL], const float (&F)[NL], const float (&SF)[NL],
-                                          const uint32_t (&coloff)[NL], unsigned char* smem, uint32_t fo,
+                                          const uint32_t (&coloff)[NL], uint32_t boff, unsigned char* smem, uint32_t fo,
                                           const float (&o)[NL], const float (&c1)[NL], const float (&c2)[NL],
                                           const uint32_t (&gph)[NL], uint32_t go) {
   const float a_in = __shfl_up_sync(0xffffffffu, A[NL - 1], 1);   // lane 0 multiplies it by F = 0
+  const float rb = lds_f(smem, boff + fo);                         // the blank's emission
 #pragma unroll
   for (int k = NL - 1; k >= 0; k--) {
     const float r = lds_f(smem, coloff[k] + fo);
@@ -234,7 +238,7 @@ __device__ __forceinline__ void own_frame(float (&A)[NL], float (&B)[NL], const 
     const float q = fmaf(SF[k], alp, A[k] + B[k]);
     if (COMBINE) sts_f(smem, gph[k] + go, (q * c1[k]) * (o[k] * c2[k]));
     A[k] = fminf(q * r, NASR_BIG);
-    B[k] = nb;
+    B[k] = nb * rb;
   }
 }
 
@@ -242,9 +246,10 @@ __device__ __forceinline__ void own_frame(float (&A)[NL], float (&B)[NL], const 
 // state of label i-1 and the blank AFTER it; mass arrives from position i+1 (slots ascending, in place).
 template <int NL>
 __device__ __forceinline__ void other_frame(float (&A)[NL], float (&B)[NL], const float (&F)[NL], const float (&SF)[NL],
-                                            const uint32_t (&coloff)[NL], const unsigned char* smem, uint32_t fo,
-                                            float (&o)[NL]) {
+                                            const uint32_t (&coloff)[NL], uint32_t boff, const unsigned char* smem,
+                                            uint32_t fo, float (&o)[NL]) {
   const float a_in = __shfl_down_sync(0xffffffffu, A[0], 1);      // lane 31 multiplies it by F = 0
+  const float rb = lds_f(smem, boff + fo);
 #pragma unroll
   for (int k = 0; k < NL; k++) {
     const float r = lds_f(smem, coloff[k] + fo);
@@ -252,7 +257,7 @@ __device__ __forceinline__ void other_frame(float (&A)[NL], float (&B)[NL], cons
     const float nb = fmaf(F[k], alp, B[k]);
     const float q = fmaf(SF[k], alp, A[k] + B[k]);
     A[k] = fminf(q * r, NASR_BIG);
-    B[k] = nb;
+    B[k] = nb * rb;
     o[k] = A[k];
   }
 }
@@ -341,7 +346,7 @@ __device__ __forceinline__ float4* ckpt_ptr(const Params& p, int b, int d, int c
 __device__ __forceinline__ float4 ldcg4(const float4* p) { return __ldcg(p); }
 
 template <int NL>
-__global__ void __maxnreg__(200) ctc_lean_kernel(const Params p) {
+__global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int N = NL * 32;
   constexpr int NV = (NL + 3) / 4;
@@ -505,6 +510,7 @@ __global__ void __maxnreg__(200) ctc_lean_kernel(const Params p) {
     int E[NL];
     uint32_t coloff[NL], gph[NL];
     uint32_t skipmask = 0, skipo = 0;
+    uint32_t boff = (uint32_t)sl.rows + (uint32_t)(d * NST) * KC * ROWB + (uint32_t)(shift + blank) * 4u;
     const uint32_t rows0 = (uint32_t)sl.rows + (uint32_t)(d * NST) * KC * ROWB;   // stage 0 of this side
     const uint32_t gbuf0 = (uint32_t)sl.gbuf + (uint32_t)(d * 2) * KC * GSB;      // buffer 0 of this side
     {
@@ -576,10 +582,10 @@ __global__ void __maxnreg__(200) ctc_lean_kernel(const Params p) {
         flag_wait<20>(FLAG(FL_READY + d), i + 1);
         if (ci.len == KC) {
 #pragma unroll
-          for (int f = 0; f < KC; f++) own_frame<NL, false>(A, B, F, SF, coloff, smem, f * ROWB, c1, c1, c2, gph, 0);
+          for (int f = 0; f < KC; f++) own_frame<NL, false>(A, B, F, SF, coloff, boff, smem, f * ROWB, c1, c1, c2, gph, 0);
         } else {
 #pragma unroll 1
-          for (int f = 0; f < ci.len; f++) own_frame<NL, false>(A, B, F, SF, coloff, smem, f * ROWB, c1, c1, c2, gph, 0);
+          for (int f = 0; f < ci.len; f++) own_frame<NL, false>(A, B, F, SF, coloff, boff, smem, f * ROWB, c1, c1, c2, gph, 0);
         }
         __syncwarp();
         if (lane == 0) flag_set(FLAG(FL_FREED + d), i + 1);
@@ -604,7 +610,7 @@ __global__ void __maxnreg__(200) ctc_lean_kernel(const Params p) {
             flag_wait<100>(FLAG(FL_MEETB), 1);
             // ---- p = sum over states of alpha(M-1) * beta(M-1); label of slot i pairs with mirrored slot N-1-i,
             // the blank of slot i (state 2(i-1)) with the blank of mirrored slot N-i ----
-            const float S64 = 1.8446744e19f;  // 2^64: both factors sit near 2^-67
+            const float S64 = 1.0f;           // both factors sit near 2^0 after the rescale
             const int lm = 31 - lane;
             float term[2 * NL];
             int kt[2 * NL];
@@ -646,7 +652,7 @@ __global__ void __maxnreg__(200) ctc_lean_kernel(const Params p) {
             if (!(tot > 0.f) || !(tot < 3e38f) || kmax < -(1 << 27)) {
               alarm |= AL_P;
               tot = 1.f;
-              kmax = 128;
+              kmax = 0;
             }
             const int et = (int)((__float_as_uint(tot) >> 23) & 255u) - 127;
             const float mp = tot * pow2f(-et);
@@ -654,10 +660,10 @@ __global__ void __maxnreg__(200) ctc_lean_kernel(const Params p) {
 #pragma unroll 1
             for (int q = 0; q < 32; q++) ls += (double)*reinterpret_cast<volatile float*>(&s_lsum[q]);
             if (lane == 0) {
-              s_scal[1] = kmax - 128 + et;
+              s_scal[1] = kmax + et;
               s_scal[3] = __float_as_int(1.0f / mp);
-              // log p = (kmax - 128) ln 2 + ln(tot); sum_t log y_blank(t) = -ln 2 * sum_t log2(sum_c R)
-              p.loss[b] = (float)(-((double)(kmax - 128) * 0.6931471805599453 + log((double)tot) - ls * 0.6931471805599453));
+              // log p = kmax ln 2 + ln(tot) - ln 2 * sum_t log2(sum_c R(t))   (y = R / sum_c R)
+              p.loss[b] = (float)(-((double)kmax * 0.6931471805599453 + log((double)tot) - ls * 0.6931471805599453));
               p.status[b] = 0;
             }
             __syncwarp();
@@ -712,11 +718,11 @@ __global__ void __maxnreg__(200) ctc_lean_kernel(const Params p) {
         const bool full = ci.len == KC;
         if (full) {
 #pragma unroll
-          for (int g = 0; g < KC; g++) other_frame<NL>(Ao, Bo, Fo, SFo, coloff, smem, (KC - 1 - g) * ROWB, O[KC - 1 - g]);
+          for (int g = 0; g < KC; g++) other_frame<NL>(Ao, Bo, Fo, SFo, coloff, boff, smem, (KC - 1 - g) * ROWB, O[KC - 1 - g]);
         } else {
 #pragma unroll
           for (int g = 0; g < KC; g++)
-            if (KC - 1 - g < ci.len) other_frame<NL>(Ao, Bo, Fo, SFo, coloff, smem, (KC - 1 - g) * ROWB, O[KC - 1 - g]);
+            if (KC - 1 - g < ci.len) other_frame<NL>(Ao, Bo, Fo, SFo, coloff, boff, smem, (KC - 1 - g) * ROWB, O[KC - 1 - g]);
         }
         if (i + 1 < S.nch) {
           // the other direction's checkpoint of the next chunk, on its way while this chunk is combined
@@ -744,11 +750,11 @@ __global__ void __maxnreg__(200) ctc_lean_kernel(const Params p) {
         if (full) {
 #pragma unroll
           for (int f = 0; f < KC; f++)
-            own_frame<NL, true>(A, B, F, SF, coloff, smem, f * ROWB, O[f], c1, c2, gph, f * GSB);
+            own_frame<NL, true>(A, B, F, SF, coloff, boff, smem, f * ROWB, O[f], c1, c2, gph, f * GSB);
         } else {
 #pragma unroll
           for (int f = 0; f < KC; f++)
-            if (f < ci.len) own_frame<NL, true>(A, B, F, SF, coloff, smem, f * ROWB, O[f], c1, c2, gph, f * GSB);
+            if (f < ci.len) own_frame<NL, true>(A, B, F, SF, coloff, boff, smem, f * ROWB, O[f], c1, c2, gph, f * GSB);
         }
         __syncwarp();
         if (lane == 0) flag_set(FLAG(FL_GFULL + d), j2 + 1);
@@ -760,6 +766,7 @@ __global__ void __maxnreg__(200) ctc_lean_kernel(const Params p) {
       const uint32_t cd = stg + 1 == NST ? (uint32_t)(-(NST - 1) * KC * ROWB) : (uint32_t)(KC * ROWB);
 #pragma unroll
       for (int k = 0; k < NL; k++) coloff[k] += cd;
+      boff += cd;
       stg = stg + 1 == NST ? 0 : stg + 1;
     }
     if (want_grad) {
@@ -779,83 +786,115 @@ __global__ void __maxnreg__(200) ctc_lean_kernel(const Params p) {
     }
   } else if (role == PROD) {
     // ================================ producer warp =================================
-    // Round r brings chunks 2r and 2r+1 of both sides: 32 rows, one per lane (side, chunk in round, frame).  The
-    // bulk copies of round r+1 are in flight while round r is converted in place: raw logits -> ratio emissions,
-    // y_blank, the zero entry.
+    // A round brings the next two chunks of both sides: 32 rows, one per lane (side, chunk in round, frame), as
+    // 16-byte cp.async pieces of the 16-byte aligned superset of the row (rows are only 8-byte aligned at C = 38, and
+    // 32 scattered 152-byte rows per instruction are exactly what LDGSTS is for; a bulk copy per row would cost an
+    // elected-lane loop of 32 issues).  Three rounds are in flight while the oldest is converted in place: raw logits
+    // -> ratio emissions, y_blank, the zero entry.  The sides advance independently: a side whose ring is full (its
+    // recursion warp waits at the meeting point) sits the round out and must not hold back the other one.
     const int side = lane >> 4, cip = (lane >> 3) & 1, f = lane & 7;
     const size_t rstr = rstride;
     float lsum = 0.f;
-    const int nrounds = (S.nch + 1) / 2;
     const int nvu = (shift + C + 3) >> 2;   // 16-byte vectors that hold the row
-    auto issue = [&](int r) {
-      const int i = 2 * r + cip;
-      const Chunk ci = chunk_at(S, side, i);
-      const uint32_t bar = bar0 + 8u * (uint32_t)(r & 1);
-      // the stage must have been released by its readers of NST chunks ago
-      if (ci.phase != 0) flag_wait<200>(FLAG(FL_FREED + side), i - NST + 1);
-      unsigned char* slot = smem + sl.rows + ((size_t)(side * NST + i % NST) * KC + f) * ROWB;
-      if (ci.phase != 0 && f < ci.len) {
-        const int t = ci.t0 + f * ci.dt;
-        const char* row = reinterpret_cast<const char*>(xbase + (size_t)t * rstr);
-        const char* a0 = reinterpret_cast<const char*>((uintptr_t)row & ~(uintptr_t)15);
-        const char* a1 = reinterpret_cast<const char*>(((uintptr_t)row + 4 * C + 15) & ~(uintptr_t)15);
-        if (a0 >= p.lo && a1 <= p.hi) {
-          const uint32_t bytes = (uint32_t)(a1 - a0);
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_expect_tx(bar, bytes);
-          bulk_g2s(sptr(slot), a0, bytes, bar);
-        } else {
-          // the superset of this row would leave the tensor: element-wise copy
-          float* dst = reinterpret_cast<float*>(slot) + shift;
-          const float* src = reinterpret_cast<const float*>(row);
-          for (int c = 0; c < C; c++) dst[c] = __ldg(src + c);
-          mbar_arrive(bar);
-        }
-      } else {
-        mbar_arrive(bar);
-      }
-    };
-    issue(0);
+    int rs = 0;                             // rounds this lane's side has issued
+    int q0 = -1, q1 = -1, q2 = -1;          // side rounds in flight, oldest first (-1: the side sat that round out)
 #pragma unroll 1
-    for (int r = 0; r < nrounds; r++) {
-      if (r + 1 < nrounds) issue(r + 1);
-      __syncwarp();
-      mbar_wait(bar0 + 8u * (uint32_t)(r & 1), (uint32_t)(r >> 1) & 1u);
-      const int i = 2 * r + cip;
-      const Chunk cc = chunk_at(S, side, i);
-      if (cc.phase != 0 && f < cc.len) {
-        float* slot = reinterpret_cast<float*>(smem + sl.rows + ((size_t)(side * NST + i % NST) * KC + f) * ROWB);
-        const float xb = slot[shift + blank];
-        const float nxb = -xb * 1.4426950408889634f;
-        float rs = 0.f;
+    while (true) {
+      // ---- issue ----
+      int nq = -1;
+      {
+        const int ilast = min(2 * rs + 1, S.nch - 1);
+        // the stages must have been released by their readers of NST chunks ago (the same answer in all lanes of a side)
+        const bool can = 2 * rs < S.nch && flag_get(FLAG(FL_FREED + side)) >= ilast - NST + 1;
+        if (can) {
+          const int i = 2 * rs + cip;
+          const Chunk ci = chunk_at(S, side, i);
+          if (ci.phase != 0 && f < ci.len) {
+            unsigned char* slot = smem + sl.rows + ((size_t)(side * NST + i % NST) * KC + f) * ROWB;
+            const int t = ci.t0 + f * ci.dt;
+            const char* row = reinterpret_cast<const char*>(xbase + (size_t)t * rstr);
+            const char* a0 = reinterpret_cast<const char*>((uintptr_t)row & ~(uintptr_t)15);
+            if (a0 >= p.lo && a0 + 16 * nvu <= p.hi) {
+              const uint32_t dst = sptr(slot);
 #pragma unroll 1
-        for (int v = 0; v < nvu; v++) {
-          const float4 x = *reinterpret_cast<const float4*>(slot + 4 * v);
-          const int w = 4 * v - shift;   // class of x.x
-          float4 rr;
-          rr.x = ex2a(fmaf(x.x, 1.4426950408889634f, nxb));
-          rr.y = ex2a(fmaf(x.y, 1.4426950408889634f, nxb));
-          rr.z = ex2a(fmaf(x.z, 1.4426950408889634f, nxb));
-          rr.w = ex2a(fmaf(x.w, 1.4426950408889634f, nxb));
-          if (w < 0 || w + 3 >= C) {
-            rr.x = (w >= 0 && w < C) ? rr.x : 0.f;
-            rr.y = (w + 1 >= 0 && w + 1 < C) ? rr.y : 0.f;
-            rr.z = (w + 2 >= 0 && w + 2 < C) ? rr.z : 0.f;
-            rr.w = (w + 3 >= 0 && w + 3 < C) ? rr.w : 0.f;
+              for (int v = 0; v < nvu; v++)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (uint32_t)v), "l"(a0 + 16 * v)
+                             : "memory");
+            } else {
+              // the superset of this row would leave the tensor: element-wise copy
+              float* dstf = reinterpret_cast<float*>(slot) + shift;
+              const float* src = reinterpret_cast<const float*>(row);
+              for (int c = 0; c < C; c++) dstf[c] = __ldg(src + c);
+            }
           }
-          rs += (rr.x + rr.y) + (rr.z + rr.w);
-          *reinterpret_cast<float4*>(slot + 4 * v) = rr;
+          nq = rs;
+          rs++;
         }
-        // a class ratio that overflowed (or a non-finite logit) is the robust kernel's business; ratios that
-        // underflow only remove mass and are covered by the certificate
-        if (!(rs < 1e37f) || !(rs > 0.f)) alarm |= AL_EMISSION;
-        slot[ROWW - 2] = __fdividef(1.0f, rs);   // y_blank
-        slot[ROWW - 1] = 0.f;                    // "emission" of slots without a label
-        if (cc.phase == 1) lsum += __log2f(rs);
       }
-      s_lsum[lane] = lsum;
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 3;" ::: "memory");
+      // ---- convert the oldest round in flight ----
+      if (q0 >= 0) {
+        const int i = 2 * q0 + cip;
+        const Chunk cc = chunk_at(S, side, i);
+        if (cc.phase != 0 && f < cc.len) {
+          float* slot = reinterpret_cast<float*>(smem + sl.rows + ((size_t)(side * NST + i % NST) * KC + f) * ROWB);
+          // emissions in units of u = max(blank's, largest class's / 32): R[c] = exp(x[c] - log u).  Flat frames
+          // (the label on the path is a typical class, far below the largest) then cost a state ~4 bits instead of
+          // ~9, peaked frames (the label IS the largest class and the blank is tiny) let it grow by at most 5 bits
+          // instead of by the blank's 11..33: eight frames stay inside float32 either way
+          float m0 = -3.0e38f, m1 = -3.0e38f;
+#pragma unroll 2
+          for (int v = 0; v < nvu; v++) {
+            float4 x = *reinterpret_cast<const float4*>(slot + 4 * v);
+            const int w = 4 * v - shift;   // class of x.x
+            if (w < 0 || w + 3 >= C) {
+              x.x = (w >= 0 && w < C) ? x.x : -3.0e38f;
+              x.y = (w + 1 >= 0 && w + 1 < C) ? x.y : -3.0e38f;
+              x.z = (w + 2 >= 0 && w + 2 < C) ? x.z : -3.0e38f;
+              x.w = (w + 3 >= 0 && w + 3 < C) ? x.w : -3.0e38f;
+            }
+            m0 = fmaxf(m0, fmaxf(x.x, x.y));
+            m1 = fmaxf(m1, fmaxf(x.z, x.w));
+          }
+          const float nxb = -fmaxf(slot[shift + blank], fmaxf(m0, m1) - kUnitGap) * 1.4426950408889634f;
+          float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll 2
+          for (int v = 0; v < nvu; v++) {
+            const float4 x = *reinterpret_cast<const float4*>(slot + 4 * v);
+            const int w = 4 * v - shift;   // class of x.x
+            float4 rr;
+            rr.x = ex2a(fmaf(x.x, 1.4426950408889634f, nxb));
+            rr.y = ex2a(fmaf(x.y, 1.4426950408889634f, nxb));
+            rr.z = ex2a(fmaf(x.z, 1.4426950408889634f, nxb));
+            rr.w = ex2a(fmaf(x.w, 1.4426950408889634f, nxb));
+            if (w < 0 || w + 3 >= C) {
+              rr.x = (w >= 0 && w < C) ? rr.x : 0.f;
+              rr.y = (w + 1 >= 0 && w + 1 < C) ? rr.y : 0.f;
+              rr.z = (w + 2 >= 0 && w + 2 < C) ? rr.z : 0.f;
+              rr.w = (w + 3 >= 0 && w + 3 < C) ? rr.w : 0.f;
+            }
+            rs0 += rr.x + rr.y;
+            rs1 += rr.z + rr.w;
+            *reinterpret_cast<float4*>(slot + 4 * v) = rr;
+          }
+          const float rsum = rs0 + rs1;
+          // a class ratio that overflowed (or a non-finite logit) is the robust kernel's business; ratios that
+          // underflow only remove mass and are covered by the certificate
+          if (!(rsum < 1e37f) || !(rsum > 0.f)) alarm |= AL_EMISSION;
+          slot[ROWW - 2] = __fdividef(1.0f, rsum);   // y[c] = R[c] / sum
+          slot[ROWW - 1] = 0.f;                      // "emission" of slots without a label
+          if (cc.phase == 1) lsum += __log2f(rsum);
+        }
+        s_lsum[lane] = lsum;
+      }
       __syncwarp();
-      if ((lane & 15) == 0) flag_set(FLAG(FL_READY + side), min(2 * r + 2, S.nch));
+      if (q0 >= 0 && (lane & 15) == 0) flag_set(FLAG(FL_READY + side), min(2 * q0 + 2, S.nch));
+      const bool idle = q0 < 0 && nq < 0;
+      q0 = q1; q1 = q2; q2 = nq;
+      const bool more = 2 * rs < S.nch || q0 >= 0 || q1 >= 0 || q2 >= 0;
+      if (!__any_sync(0xffffffffu, more)) break;
+      if (__all_sync(0xffffffffu, idle)) __nanosleep(200);
     }
   } else {
     // ================================ gradient warps =================================
@@ -876,8 +915,8 @@ __global__ void __maxnreg__(200) ctc_lean_kernel(const Params p) {
         flag_wait<100>(FLAG(FL_GFULL + d), j2 + 1);
         const float* G = s_gbuf + (size_t)((d * 2 + (j2 & 1)) * KC + f) * GS;
         float* rec = reinterpret_cast<float*>(smem + sl.rows + ((size_t)(d * NST + stg) * KC + f) * ROWB);
-        const float yb = rec[ROWW - 2];
-        const float gy = gs * yb;
+        const float inv = rec[ROWW - 2];
+        const float gy = gs * inv;
         rec += shift;
         float tot = 0.f;
 #pragma unroll 1
@@ -918,7 +957,7 @@ __global__ void __maxnreg__(200) ctc_lean_kernel(const Params p) {
         tot += __shfl_xor_sync(0xffffffffu, tot, 16);
         tot *= PS;
         if (f < ci.len && !(tot < 1.0f + 1e-4f)) alarm |= AL_OCC;
-        if (cg == 0) rec[blank] = gs * (yb - (1.0f - tot));
+        if (cg == 0) rec[blank] = gs * (rec[blank] * inv - (1.0f - tot));
         __syncwarp();
         if (lane == 0) flag_set(FLAG(FL_GFREE + d), j2 + 1);
         // rows -> global, one row per instruction (152 bytes at C = 38: 19 lanes of 8 bytes where the alignment allows)
@@ -983,6 +1022,9 @@ int launch_lean(const lean::Params& p, cudaStream_t stream) {
   if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
     NASR_CUDA(cudaFuncSetAttribute(lean::ctc_lean_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    kLeanMaxSmem));
+    // two CTAs of ~100 KB per SM: ask for the largest shared-memory carve-out (the default picks one that fits one)
+    NASR_CUDA(cudaFuncSetAttribute(lean::ctc_lean_kernel<NL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
     if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
   }
   lean::ctc_lean_kernel<NL><<<p.B, lean::NTHREADS, sl.total, stream>>>(p);

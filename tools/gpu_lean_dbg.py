@@ -10,6 +10,12 @@ from oracle import c_oracle
 
 kw = dict(T=500, B=16, C=38, Lmax=100, mode="ragged")
 seed = 4242
+if len(sys.argv) > 1 and sys.argv[1] == "peaky":
+    kw = dict(T=400, B=12, C=38, Lmax=60, mode="ragged", peaky=True)
+if len(sys.argv) > 1 and sys.argv[1] == "peaky4":
+    kw = dict(T=400, B=12, C=38, Lmax=100, mode="ragged", peaky=True)
+if len(sys.argv) > 1 and sys.argv[1] == "rand2":
+    kw = dict(T=400, B=12, C=38, Lmax=60, mode="ragged")
 if len(sys.argv) > 1 and sys.argv[1] == "cfg3":
     kw = dict(T=1000, B=32, C=38, Lmax=200, mode="full"); seed = 7
 g = make_batch(seed, **kw)
