@@ -1,5 +1,5 @@
 // CTC loss + d(loss)/d(logits) for narrow vocabularies (C <= 64, transcripts up to 254 labels) on sm_100a:
-// one CTA of five specialised warps per utterance, one launch per batch, float32 arithmetic.
+// one CTA of four specialised warps per utterance, one launch per batch, float32 arithmetic.
 //
 // Replaces tf.nn.ctc_loss + _CTCLossGrad behind create_loss (reference networks/tfnetwork.py:58-59); semantics per
 // SURVEY.md Appendix A.1.  ctc_loss.cu holds the robust kernel that redoes any utterance flagged in retry[].
@@ -41,18 +41,24 @@
 // monotonic counters in shared memory (st.release / ld.acquire): there is no CTA-wide barrier in the main loop.
 //
 //   warp 0,1  recursion forward / backward (phase 2: recompute of the other direction + combine)
-//   warp 2    producer (bulk copies, softmax pieces)        warp 3,4  gradient (class sums, coalesced row stores)
+//   warp 2    producer (cp.async rows, softmax pieces)      warp 3    gradient of both sides (class sums, row stores)
 #include <limits.h>
 #include <math.h>
 
+#include <type_traits>
+
 #include "nasr_common.cuh"
+
+#ifndef NASR_TUNING
+#define NASR_TUNING 0
+#endif
 
 namespace nasr {
 namespace lean {
 
 constexpr int KC = 8;             // frames per chunk (= renormalisation and checkpoint interval)
 constexpr int NST = 10;           // chunks of row records per side in the ring
-constexpr int NTHREADS = 160;     // 5 warps
+constexpr int NTHREADS = 128;     // 4 warps: two CTAs per SM leave every thread 255 registers
 constexpr int TB = 107;           // biased exponent a slot's larger state is brought to (2^-20)
 constexpr int GCAP = 20;          // a slot with mass sits at most this far below the slot with mass beneath it
 constexpr int PSHIFT = 64;        // the posterior buffer holds posterior * 2^-PSHIFT
@@ -62,7 +68,8 @@ constexpr int ROWW = 76;          // words per row record: odd number of 16-byte
 constexpr int ROWB = ROWW * 4;
 constexpr int GS = 356;           // words per posterior row: = 4 (mod 32), so that 16 bytes of 8 frames hit 32 banks
 constexpr int GSB = GS * 4;
-constexpr int GCELLS = GS - 4;    // cells that may hold posteriors; the last four are dump cells of label-less slots
+constexpr int GCELLS = GS - 8;    // cells that may hold posteriors; then four cells nobody writes (zeros), then the
+                                  // four dump cells of label-less slots
 constexpr int NGRP = 16;          // class groups of four (63 label classes at most)
 constexpr float kTol = 3e-5f;
 constexpr float kUnitGap = 3.4657359f;   // 5 ln 2: see the producer
@@ -72,7 +79,7 @@ constexpr float kUnitGap = 3.4657359f;   // 5 ln 2: see the producer
 // inflow stay below 2^124, so nothing ever reaches inf; what saturation removes the certificate accounts for.
 #define NASR_BIG 1.2676506e30f
 
-enum Role { R_F = 0, R_B = 1, PROD = 2, G_F = 3, G_B = 4 };
+enum Role { R_F = 0, R_B = 1, PROD = 2, GRAD = 3 };
 enum Alarm { AL_SHAPE = 1, AL_EMISSION = 2, AL_NONFINITE = 4, AL_SAT = 8, AL_P = 32, AL_CERT = 128, AL_OCC = 256 };
 // counters in shared memory (each written by one warp at a time, only ever increasing)
 enum Flag { FL_READY = 0, FL_FREED = 2, FL_GFULL = 4, FL_GFREE = 6, FL_MEETB = 8, FL_MEETP = 9, NFLAGS = 16 };
@@ -97,6 +104,7 @@ struct Params {
   int split;               // debug: frames of the forward half (multiple of KC), 0 = automatic
   const char* lo;          // lowest byte of the logits view
   const char* hi;          // one past its highest byte
+  long long* prof;         // tuning builds: time stamps [role 5][chunk 160][4] of CTA 0
 };
 
 // ---- shared-memory accessors, counters, mbarrier, bulk copy ----------------------------------------------------
@@ -166,7 +174,7 @@ __host__ __device__ inline Smem smem_layout(int NL) {
   s.cell = o;    o = al16(o + (size_t)N * 2);
   s.cnt = o;     o = al16(o + 64 * 4);
   s.clsoff = o;  o = al16(o + 64 * 4);
-  s.gtab = o;    o = al16(o + NGRP * 4 * 16);
+  s.gtab = o;    o = al16(o + (NGRP + 1) * 4 * 16);
   s.lsum = o;    o = al16(o + 32 * 4);
   s.scal = o;    o = al16(o + 64);
   s.total = o;
@@ -176,8 +184,10 @@ __host__ __device__ inline Smem smem_layout(int NL) {
 // ---- schedule -----------------------------------------------------------------------------------------------------
 struct Sched {
   int Tb;
-  int n1[2];    // frames each direction covers in phase 1
-  int nc1[2];   // chunks of phase 1
+  int n10, n11;    // frames each direction covers in phase 1 (scalars: arrays indexed by the direction would live
+  int nc10, nc11;  // in local memory)            ... chunks of phase 1
+  __device__ __forceinline__ int n1(int d) const { return d ? n11 : n10; }
+  __device__ __forceinline__ int nc1(int d) const { return d ? nc11 : nc10; }
   int nch;      // chunks per side (phase 1 + phase 2)
   int grad;     // 0: loss only, no phase 2
 };
@@ -192,17 +202,17 @@ __device__ __forceinline__ Chunk chunk_at(const Sched& S, int d, int i) {
   Chunk c;
   c.phase = 0; c.len = 0; c.jo = 0; c.t0 = 0; c.dt = 1;
   if (i < 0 || i >= S.nch) return c;
-  if (i < S.nc1[d]) {
+  if (i < S.nc1(d)) {
     const int tau0 = i * KC;
     c.phase = 1;
     c.jo = i;
-    c.len = min(KC, S.n1[d] - tau0);
+    c.len = min(KC, S.n1(d) - tau0);
     c.t0 = d ? S.Tb - 1 - tau0 : tau0;
     c.dt = d ? -1 : 1;
   } else if (S.grad) {
     const int o = d ^ 1;
-    const int jo = S.nc1[o] - 1 - (i - S.nc1[d]);
-    const int hi_tau = min(jo * KC + KC, S.n1[o]);
+    const int jo = S.nc1(o) - 1 - (i - S.nc1(d));
+    const int hi_tau = min(jo * KC + KC, S.n1(o));
     c.phase = 2;
     c.jo = jo;
     c.len = hi_tau - jo * KC;
@@ -221,24 +231,40 @@ __device__ __forceinline__ void sts_f(unsigned char* smem, uint32_t off, float v
   *reinterpret_cast<float*>(smem + off) = v;
 }
 
-// One frame of this warp's own recursion (slots descending, in place).  COMBINE: also the posteriors of the frame,
-// from the other direction's label values o[] of the same frame.
+// The emissions of a frame for this lane's slots (r[NL] = the blank's).  They are loaded a frame ahead of their use:
+// a single warp carries the recursion, so nothing else hides the latency of shared memory.
+template <int NL>
+__device__ __forceinline__ void load_em(float (&r)[NL + 1], const uint32_t (&coloff)[NL], uint32_t boff,
+                                        const unsigned char* smem, uint32_t fo) {
+#pragma unroll
+  for (int k = 0; k < NL; k++) r[k] = lds_f(smem, coloff[k] + fo);
+  r[NL] = lds_f(smem, boff + fo);
+}
+
+// One frame of this warp's own recursion (slots descending, in place).  r: the frame's emissions on entry, those of
+// the frame at fnext on exit (pref).  COMBINE: also the posteriors of the frame, from the other direction's label
+// values o[] of the same frame.
 template <int NL, bool COMBINE>
 __device__ __forceinline__ void own_frame(float (&A)[NL], float (&B)[NL], const float (&F)[NL], const float (&SF)[NL],
-                                          const uint32_t (&coloff)[NL], uint32_t boff, unsigned char* smem, uint32_t fo,
-                                          const float (&o)[NL], const float (&c1)[NL], const float (&c2)[NL],
-                                          const uint32_t (&gph)[NL], uint32_t go) {
+                                          float (&r)[NL + 1], const uint32_t (&coloff)[NL], uint32_t boff,
+                                          unsigned char* smem, bool pref, uint32_t fnext, const float (&o)[NL],
+                                          const float (&c1)[NL], const float (&c2)[NL], const uint32_t (&gph)[NL],
+                                          uint32_t go) {
   const float a_in = __shfl_up_sync(0xffffffffu, A[NL - 1], 1);   // lane 0 multiplies it by F = 0
-  const float rb = lds_f(smem, boff + fo);                         // the blank's emission
+  float rn[NL + 1];
+  if (pref) load_em<NL>(rn, coloff, boff, smem, fnext);
 #pragma unroll
   for (int k = NL - 1; k >= 0; k--) {
-    const float r = lds_f(smem, coloff[k] + fo);
     const float alp = k ? A[k - 1] : a_in;
     const float nb = fmaf(F[k], alp, B[k]);
     const float q = fmaf(SF[k], alp, A[k] + B[k]);
     if (COMBINE) sts_f(smem, gph[k] + go, (q * c1[k]) * (o[k] * c2[k]));
-    A[k] = fminf(q * r, NASR_BIG);
-    B[k] = nb * rb;
+    A[k] = fminf(q * r[k], NASR_BIG);
+    B[k] = nb * r[NL];
+  }
+  if (pref) {
+#pragma unroll
+    for (int k = 0; k <= NL; k++) r[k] = rn[k];
   }
 }
 
@@ -246,24 +272,28 @@ __device__ __forceinline__ void own_frame(float (&A)[NL], float (&B)[NL], const 
 // state of label i-1 and the blank AFTER it; mass arrives from position i+1 (slots ascending, in place).
 template <int NL>
 __device__ __forceinline__ void other_frame(float (&A)[NL], float (&B)[NL], const float (&F)[NL], const float (&SF)[NL],
-                                            const uint32_t (&coloff)[NL], uint32_t boff, const unsigned char* smem,
-                                            uint32_t fo, float (&o)[NL]) {
+                                            float (&r)[NL + 1], const uint32_t (&coloff)[NL], uint32_t boff,
+                                            const unsigned char* smem, bool pref, uint32_t fnext, float (&o)[NL]) {
   const float a_in = __shfl_down_sync(0xffffffffu, A[0], 1);      // lane 31 multiplies it by F = 0
-  const float rb = lds_f(smem, boff + fo);
+  float rn[NL + 1];
+  if (pref) load_em<NL>(rn, coloff, boff, smem, fnext);
 #pragma unroll
   for (int k = 0; k < NL; k++) {
-    const float r = lds_f(smem, coloff[k] + fo);
     const float alp = (k < NL - 1) ? A[k + 1] : a_in;
     const float nb = fmaf(F[k], alp, B[k]);
     const float q = fmaf(SF[k], alp, A[k] + B[k]);
-    A[k] = fminf(q * r, NASR_BIG);
-    B[k] = nb * rb;
+    A[k] = fminf(q * r[k], NASR_BIG);
+    B[k] = nb * r[NL];
     o[k] = A[k];
+  }
+  if (pref) {
+#pragma unroll
+    for (int k = 0; k <= NL; k++) r[k] = rn[k];
   }
 }
 
-// Transfer factors of the own recursion from the slot exponents: F[k] = 2^(E[k-1]-E[k]) (<= 2^GCAP), 0 where either
-// slot is dead.
+// Transfer factors of the own recursion from the slot exponents: F[k] = 2^(E[k-1]-E[k]) (<= 2^GCAP).  A dead slot
+// (exponent ENEG) only ever sits below a live one, so 2^(ENEG - E) = 0 switches its outflow off by itself.
 template <int NL>
 __device__ __forceinline__ void set_F(float (&F)[NL], float (&SF)[NL], const int (&E)[NL], uint32_t skipmask, int lane) {
   int Ep = __shfl_up_sync(0xffffffffu, E[NL - 1], 1);
@@ -271,12 +301,11 @@ __device__ __forceinline__ void set_F(float (&F)[NL], float (&SF)[NL], const int
 #pragma unroll
   for (int k = 0; k < NL; k++) {
     const int lower = k ? E[k - 1] : Ep;
-    const bool dead = lower <= ENEG / 2 || E[k] <= ENEG / 2;
-    F[k] = dead ? 0.f : pow2f(min(lower - E[k], GCAP));
+    F[k] = pow2f(min(lower - E[k], GCAP));
     SF[k] = ((skipmask >> k) & 1u) ? F[k] : 0.f;
   }
 }
-// ... of the other direction in this warp's layout: F[k] = 2^(E[k+1]-E[k])
+// ... of the other direction in this warp's layout: F[k] = 2^(E[k+1]-E[k]); there the dead slots sit above
 template <int NL>
 __device__ __forceinline__ void set_F_other(float (&F)[NL], float (&SF)[NL], const int (&E)[NL], uint32_t skipmask,
                                             int lane) {
@@ -285,55 +314,50 @@ __device__ __forceinline__ void set_F_other(float (&F)[NL], float (&SF)[NL], con
 #pragma unroll
   for (int k = 0; k < NL; k++) {
     const int upper = (k < NL - 1) ? E[k + 1] : En;
-    const bool dead = upper <= ENEG / 2 || E[k] <= ENEG / 2;
-    F[k] = dead ? 0.f : pow2f(min(upper - E[k], GCAP));
+    F[k] = pow2f(min(upper - E[k], GCAP));
     SF[k] = ((skipmask >> k) & 1u) ? F[k] : 0.f;
   }
 }
 
 // Renormalise every slot (larger state -> biased exponent TB), keeping E[k] >= E[k-1] - GCAP over slots with mass;
-// empty slots adopt the exponent below.
+// empty slots adopt the exponent below.  The chain through a lane is x -> max(a, x - b) (a: what the lane yields on its
+// own, b: GCAP per slot with mass); it is followed through the two lanes below -- up to 3 NL slots and 3 NL GCAP bits,
+// beyond which a raise could only move what is flushed anyway.  A single warp runs this between two chunks of its
+// recursion, so the dependent chain is kept short: one pass over the slots, the lanes below folded in with two
+// shuffles, every slot then finished independently of the others.
 template <int NL>
 __device__ __forceinline__ void rescale(float (&A)[NL], float (&B)[NL], float (&F)[NL], float (&SF)[NL], int (&E)[NL],
                                         uint32_t skipmask, int lane, int& alarm) {
-  int En[NL];
-  uint32_t nzmask = 0;
+  int En[NL], loc[NL], cnt[NL];
   uint32_t mall = 0;
+  int prev = ENEG, c = 0;
 #pragma unroll
   for (int k = 0; k < NL; k++) {
     const uint32_t m = max(__float_as_uint(A[k]), __float_as_uint(B[k]));
     mall = max(mall, m);
-    const int ex = (int)(m >> 23);
-    const bool nz = m != 0u && E[k] > ENEG / 2;
-    nzmask |= nz ? (1u << k) : 0u;
-    En[k] = E[k] + ex - TB;
+    const bool nz = m != 0u;                    // dead slots hold zeros
+    En[k] = E[k] + (int)(m >> 23) - TB;
+    prev = nz ? max(En[k], prev - GCAP) : prev;
+    c += nz ? GCAP : 0;
+    loc[k] = prev;
+    cnt[k] = c;
   }
   if (mall >= 0x7f800000u) alarm |= AL_NONFINITE;   // inf or nan (sign bit set or exponent 255)
-  // the chain through a lane is x -> max(a, x - b): a = what the lane yields on its own, b = GCAP per slot with mass;
-  // an inclusive scan of these maps over the lanes gives every lane the exact exponent below its first slot
-  int prev = ENEG;
-#pragma unroll
-  for (int k = 0; k < NL; k++) prev = ((nzmask >> k) & 1u) ? max(En[k], prev - GCAP) : prev;
-  int ca = prev, cb = GCAP * __popc(nzmask);
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int la = __shfl_up_sync(0xffffffffu, ca, o);
-    const int lb = __shfl_up_sync(0xffffffffu, cb, o);
-    if (lane >= o) {
-      ca = max(ca, la - cb);
-      cb += lb;
-    }
-  }
-  prev = __shfl_up_sync(0xffffffffu, ca, 1);
-  if (lane == 0) prev = ENEG;
+  // exponent below this lane's first slot: the lane below on its own, raised by what the lane below that sends up
+  int pin = __shfl_up_sync(0xffffffffu, prev, 1);
+  const int cb = __shfl_up_sync(0xffffffffu, c, 1);
+  if (lane == 0) pin = ENEG;
+  int pin2 = __shfl_up_sync(0xffffffffu, pin, 1);   // (lane 1 receives ENEG)
+  if (lane == 0) pin2 = ENEG;
+  pin = max(pin, max(pin2, ENEG + (1 << 20)) - cb);
 #pragma unroll
   for (int k = 0; k < NL; k++) {
-    prev = ((nzmask >> k) & 1u) ? max(En[k], prev - GCAP) : prev;
-    const int d = min(max(E[k] - prev, -127), 100);   // slots without mass hold zeros: any finite factor will do
-    const float s = __int_as_float((d + 127) << 23);
-    A[k] *= s;
-    B[k] *= s;
-    E[k] = prev > ENEG / 2 ? prev : ENEG;
+    const int e = max(loc[k], max(pin, ENEG + (1 << 20)) - cnt[k]);
+    const int d = min(max(E[k] - e, -127), 100);   // slots without mass hold zeros: any finite factor will do
+    const float sc = __int_as_float((d + 127) << 23);
+    A[k] *= sc;
+    B[k] *= sc;
+    E[k] = e > ENEG / 2 ? e : ENEG;
   }
   set_F<NL>(F, SF, E, skipmask, lane);
 }
@@ -372,7 +396,23 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
   const uint32_t bar0 = sptr(smem + sl.bars);
   const uint32_t flag0 = sptr(s_flag);
 #define FLAG(i) (flag0 + 4u * (uint32_t)(i))
+#if NASR_TUNING
+#define TS(role_, chunk_, slot_)                                                                    \
+  do {                                                                                              \
+    if (p.prof && b == 0 && lane == 0 && (chunk_) < 160)                                            \
+      p.prof[((role_) * 160 + (chunk_)) * 4 + (slot_)] = clock64();                                 \
+  } while (0)
+#else
+#define TS(role_, chunk_, slot_) do {} while (0)
+#endif
 
+#if NASR_TUNING
+  if (p.prof && tid == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.prof[3700 + 2 * b] = (long long)gt;
+  }
+#endif
   const int Tb = p.seq_len[b];
   const int l0 = p.lab_offs[b];
   const int L = p.lab_offs[b + 1] - l0;
@@ -407,7 +447,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
   // cells of a group's classes are four runs of the group's run length (a multiple of four cells: a lane (class,
   // frame) reads its run in 16-byte pieces, and the eight frames of a class cover all 32 banks)
   if (!bad && warp == 0) {
-    for (int i = lane; i < NGRP * 4; i += 32) s_gtab[i] = make_int4(-1, GCELLS, 0, 0);
+    for (int i = lane; i < (NGRP + 1) * 4; i += 32) s_gtab[i] = make_int4(-1, GCELLS, 0, 0);
     __syncwarp();
     for (int c = lane; c < C; c += 32)
       if (c != blank) {
@@ -482,11 +522,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
     int nf = KC * ((Tb + KC) / (2 * KC));
     if (p.split > 0) nf = (p.split / KC) * KC;
     nf = max(KC, min(nf, ((Tb - 1) / KC) * KC));
-    S.n1[0] = nf;
-    S.n1[1] = Tb - nf;
-    S.nc1[0] = (S.n1[0] + KC - 1) / KC;
-    S.nc1[1] = (S.n1[1] + KC - 1) / KC;
-    S.nch = want_grad ? S.nc1[0] + S.nc1[1] : max(S.nc1[0], S.nc1[1]);
+    S.n10 = nf;
+    S.n11 = Tb - nf;
+    S.nc10 = (S.n10 + KC - 1) / KC;
+    S.nc11 = (S.n11 + KC - 1) / KC;
+    S.nch = want_grad ? S.nc10 + S.nc11 : max(S.nc10, S.nc11);
     S.grad = want_grad ? 1 : 0;
   }
   // every row of this utterance starts at the same offset inside its 16-byte aligned superset (the launcher checked)
@@ -494,14 +534,29 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
   const int shift = (int)(((uintptr_t)xbase & 15) >> 2);
   __syncthreads();
 
-  // the second CTA that lands on an SM deals its roles so that the four recursion warps of an SM sit on four
-  // different schedulers (warp w issues from scheduler w mod 4)
+  // Roles go by the scheduler a warp issues from (hardware warp slot mod 4; measured: the second CTA of an SM gets
+  // slots 5, 6, 7, 4 for its warps 0..3), and the second CTA that lands on an SM deals them the other way round, so
+  // that the four recursion warps of an SM sit on four different schedulers, each beside one of the helper warps.
+  unsigned hwid;
+  asm volatile("mov.u32 %0, %%warpid;" : "=r"(hwid));
+  hwid = __shfl_sync(0xffffffffu, hwid, 0);
+  if (lane == 0) s_flag[NFLAGS - 4 + warp] = (int)(hwid & 3u);
+  __syncthreads();
   int role = warp;
-  if (s_scal[4] & 1) {
-    const int rot[5] = {G_B, G_F, R_F, R_B, PROD};
-    role = rot[warp];
+  {
+    // (fall back to the warp's index if the four slots do not cover the four schedulers)
+    const int m = (1 << s_flag[NFLAGS - 4]) | (1 << s_flag[NFLAGS - 3]) | (1 << s_flag[NFLAGS - 2]) | (1 << s_flag[NFLAGS - 1]);
+    const int q = m == 15 ? (int)(hwid & 3u) : warp;
+    role = (s_scal[4] & 1) ? (q ^ 2) : q;
   }
-  const int d = (role == R_B || role == G_B) ? 1 : 0;   // direction / side this warp works for (producer: unused)
+  const int d = role == R_B ? 1 : 0;   // direction / side of a recursion warp
+#if NASR_TUNING
+  if (p.prof && lane == 0 && b >= 148 && b < 212) {
+    unsigned hwid;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(hwid));
+    p.prof[3400 + (b - 148) * 4 + warp] = ((long long)smid << 32) | (hwid << 8) | (unsigned)role;
+  }
+#endif
   int alarm = 0;
 
   if (role == R_F || role == R_B) {
@@ -526,7 +581,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
         } else {
           if (i - pad >= 0 && i - pad < L) j = i - pad;
         }
-        int col = -1, cell = GCELLS + (k & 3);
+        int col = -1, cell = GCELLS + 4 + (k & 3);
         bool skip = false, skipn = false;
         if (j >= 0) {
           const int jj = d == 0 ? j : L - 1 - j;          // index into the transcript
@@ -547,7 +602,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
       }
       set_F<NL>(F, SF, E, skipmask, lane);
     }
-    float c1[NL], c2[NL], Ao[NL], Bo[NL], Fo[NL], SFo[NL];
+    float c1[NL], c2[NL], Ao[NL], Bo[NL], Fo[NL], SFo[NL], r[NL + 1];
     int Eo[NL];
 #pragma unroll
     for (int k = 0; k < NL; k++) {
@@ -579,17 +634,24 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
             reinterpret_cast<int4*>(ck)[(2 * NV + v) * 32 + lane] = make_int4(e[4 * v], e[4 * v + 1], e[4 * v + 2], e[4 * v + 3]);
           }
         }
+        TS(role, i, 0);
         flag_wait<20>(FLAG(FL_READY + d), i + 1);
+        TS(role, i, 1);
+        load_em<NL>(r, coloff, boff, smem, 0);
         if (ci.len == KC) {
 #pragma unroll
-          for (int f = 0; f < KC; f++) own_frame<NL, false>(A, B, F, SF, coloff, boff, smem, f * ROWB, c1, c1, c2, gph, 0);
+          for (int f = 0; f < KC; f++)
+            own_frame<NL, false>(A, B, F, SF, r, coloff, boff, smem, f < KC - 1, (f + 1) * ROWB, c1, c1, c2, gph, 0);
         } else {
 #pragma unroll 1
-          for (int f = 0; f < ci.len; f++) own_frame<NL, false>(A, B, F, SF, coloff, boff, smem, f * ROWB, c1, c1, c2, gph, 0);
+          for (int f = 0; f < ci.len; f++)
+            own_frame<NL, false>(A, B, F, SF, r, coloff, boff, smem, true, (f + 1) * ROWB, c1, c1, c2, gph, 0);
         }
         __syncwarp();
+        TS(role, i, 2);
         if (lane == 0) flag_set(FLAG(FL_FREED + d), i + 1);
-        if (i == S.nc1[d] - 1) {
+        TS(role, i, 3);
+        if (i == S.nc1(d) - 1) {
           // ---- end of phase 1: checkpoints visible to the other recursion warp, then the meeting ----
           __threadfence_block();
           rescale<NL>(A, B, F, SF, E, skipmask, lane, alarm);
@@ -677,7 +739,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
             A[k] *= im;
             B[k] *= im;
           }
-          if (want_grad && S.nch > S.nc1[d]) {
+          if (want_grad && S.nch > S.nc1(d)) {
             // the other direction's checkpoint of the first chunk of phase 2
             const Chunk cn = chunk_at(S, d, i + 1);
             const float4* ck = ckpt_ptr<NL>(p, b, d ^ 1, cn.jo);
@@ -702,7 +764,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
         }
       } else {
         // ---- phase 2: continue through the other half against the other direction's values, regenerated here ----
-        const int j2 = i - S.nc1[d];
+        const int j2 = i - S.nc1(d);
         rescale<NL>(A, B, F, SF, E, skipmask, lane, alarm);
         set_F_other<NL>(Fo, SFo, Eo, skipo, lane);
 #pragma unroll
@@ -713,17 +775,26 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
           c1[k] = __int_as_float((h + 127) << 23);
           c2[k] = __int_as_float((kk - h + 127) << 23);
         }
+        TS(role, i, 0);
         flag_wait<20>(FLAG(FL_READY + d), i + 1);
+        TS(role, i, 1);
         float O[KC][NL];
         const bool full = ci.len == KC;
+        load_em<NL>(r, coloff, boff, smem, (uint32_t)(ci.len - 1) * ROWB);
         if (full) {
 #pragma unroll
-          for (int g = 0; g < KC; g++) other_frame<NL>(Ao, Bo, Fo, SFo, coloff, boff, smem, (KC - 1 - g) * ROWB, O[KC - 1 - g]);
+          for (int g = 0; g < KC; g++)
+            other_frame<NL>(Ao, Bo, Fo, SFo, r, coloff, boff, smem, g < KC - 1, (KC - 2 - g) * ROWB, O[KC - 1 - g]);
         } else {
 #pragma unroll
           for (int g = 0; g < KC; g++)
-            if (KC - 1 - g < ci.len) other_frame<NL>(Ao, Bo, Fo, SFo, coloff, boff, smem, (KC - 1 - g) * ROWB, O[KC - 1 - g]);
+            if (KC - 1 - g < ci.len)
+              other_frame<NL>(Ao, Bo, Fo, SFo, r, coloff, boff, smem, g < KC - 1, (KC - 2 - g) * ROWB, O[KC - 1 - g]);
         }
+        // r now holds the emissions of the chunk's first frame again: where the own recursion starts
+        TS(role, i, 2);
+        flag_wait<20>(FLAG(FL_GFREE + d), j2 - 1);
+        TS(role, i, 3);
         if (i + 1 < S.nch) {
           // the other direction's checkpoint of the next chunk, on its way while this chunk is combined
           const Chunk cn = chunk_at(S, d, i + 1);
@@ -746,27 +817,34 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
             Eo[k] = e[NL - 1 - k];
           }
         }
-        flag_wait<20>(FLAG(FL_GFREE + d), j2 - 1);
         if (full) {
 #pragma unroll
           for (int f = 0; f < KC; f++)
-            own_frame<NL, true>(A, B, F, SF, coloff, boff, smem, f * ROWB, O[f], c1, c2, gph, f * GSB);
+            own_frame<NL, true>(A, B, F, SF, r, coloff, boff, smem, f < KC - 1, (f + 1) * ROWB, O[f], c1, c2, gph, f * GSB);
         } else {
 #pragma unroll
           for (int f = 0; f < KC; f++)
-            if (f < ci.len) own_frame<NL, true>(A, B, F, SF, coloff, boff, smem, f * ROWB, O[f], c1, c2, gph, f * GSB);
+            if (f < ci.len)
+              own_frame<NL, true>(A, B, F, SF, r, coloff, boff, smem, f < KC - 1, (f + 1) * ROWB, O[f], c1, c2, gph, f * GSB);
         }
         __syncwarp();
         if (lane == 0) flag_set(FLAG(FL_GFULL + d), j2 + 1);
         const uint32_t gd = (j2 & 1) ? (uint32_t)(-KC * GSB) : (uint32_t)(KC * GSB);
 #pragma unroll
-        for (int k = 0; k < NL; k++) gph[k] += gd;
+        for (int k = 0; k < NL; k++) {
+          gph[k] += gd;
+          asm volatile("" : "+r"(gph[k]));   // keep the updated address in its register: the stores take [reg + imm]
+        }
       }
       // the row records of the next chunk are in the next ring stage
       const uint32_t cd = stg + 1 == NST ? (uint32_t)(-(NST - 1) * KC * ROWB) : (uint32_t)(KC * ROWB);
 #pragma unroll
-      for (int k = 0; k < NL; k++) coloff[k] += cd;
+      for (int k = 0; k < NL; k++) {
+        coloff[k] += cd;
+        asm volatile("" : "+r"(coloff[k]));
+      }
       boff += cd;
+      asm volatile("" : "+r"(boff));
       stg = stg + 1 == NST ? 0 : stg + 1;
     }
     if (want_grad) {
@@ -798,8 +876,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
     const int nvu = (shift + C + 3) >> 2;   // 16-byte vectors that hold the row
     int rs = 0;                             // rounds this lane's side has issued
     int q0 = -1, q1 = -1, q2 = -1;          // side rounds in flight, oldest first (-1: the side sat that round out)
+    int it = 0;
 #pragma unroll 1
     while (true) {
+      TS(role, it, 0);
       // ---- issue ----
       int nq = -1;
       {
@@ -832,7 +912,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
+      TS(role, it, 1);
       asm volatile("cp.async.wait_group 3;" ::: "memory");
+      TS(role, it, 2);
       // ---- convert the oldest round in flight ----
       if (q0 >= 0) {
         const int i = 2 * q0 + cip;
@@ -842,43 +924,60 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
           // emissions in units of u = max(blank's, largest class's / 32): R[c] = exp(x[c] - log u).  Flat frames
           // (the label on the path is a typical class, far below the largest) then cost a state ~4 bits instead of
           // ~9, peaked frames (the label IS the largest class and the blank is tiny) let it grow by at most 5 bits
-          // instead of by the blank's 11..33: eight frames stay inside float32 either way
-          float m0 = -3.0e38f, m1 = -3.0e38f;
-#pragma unroll 2
-          for (int v = 0; v < nvu; v++) {
-            float4 x = *reinterpret_cast<const float4*>(slot + 4 * v);
-            const int w = 4 * v - shift;   // class of x.x
-            if (w < 0 || w + 3 >= C) {
-              x.x = (w >= 0 && w < C) ? x.x : -3.0e38f;
-              x.y = (w + 1 >= 0 && w + 1 < C) ? x.y : -3.0e38f;
-              x.z = (w + 2 >= 0 && w + 2 < C) ? x.z : -3.0e38f;
-              x.w = (w + 3 >= 0 && w + 3 < C) ? x.w : -3.0e38f;
+          // instead of by the blank's 11..33: eight frames stay inside float32 either way.
+          // The words of the 16-byte pieces that are not this row's become -3e38 first (exp -> 0, no part in the
+          // maximum), so that the pieces are processed whole; a row of up to 41 classes (11 pieces) is held in
+          // registers: one warp converts all rows, the loads must not wait for each other.
+          for (int c = 0; c < shift; c++) slot[c] = -3.0e38f;
+          for (int c = shift + C; c < 4 * nvu; c++) slot[c] = -3.0e38f;
+          const float xbl = slot[shift + blank];
+          float rsum;
+          if (nvu <= 11) {
+            float4 x[11];
+#pragma unroll
+            for (int v = 0; v < 11; v++) x[v] = *reinterpret_cast<const float4*>(slot + 4 * v);
+            float m[11];
+#pragma unroll
+            for (int v = 0; v < 11; v++) m[v] = v < nvu ? fmaxf(fmaxf(x[v].x, x[v].y), fmaxf(x[v].z, x[v].w)) : -3.0e38f;
+            const float mx = fmaxf(fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7]))),
+                                   fmaxf(fmaxf(m[8], m[9]), m[10]));
+            const float nxb = -fmaxf(xbl, mx - kUnitGap) * 1.4426950408889634f;
+            float sv[11];
+#pragma unroll
+            for (int v = 0; v < 11; v++) {
+              float4 rr;
+              rr.x = ex2a(fmaf(x[v].x, 1.4426950408889634f, nxb));
+              rr.y = ex2a(fmaf(x[v].y, 1.4426950408889634f, nxb));
+              rr.z = ex2a(fmaf(x[v].z, 1.4426950408889634f, nxb));
+              rr.w = ex2a(fmaf(x[v].w, 1.4426950408889634f, nxb));
+              sv[v] = v < nvu ? (rr.x + rr.y) + (rr.z + rr.w) : 0.f;
+              if (v < nvu) *reinterpret_cast<float4*>(slot + 4 * v) = rr;
             }
-            m0 = fmaxf(m0, fmaxf(x.x, x.y));
-            m1 = fmaxf(m1, fmaxf(x.z, x.w));
-          }
-          const float nxb = -fmaxf(slot[shift + blank], fmaxf(m0, m1) - kUnitGap) * 1.4426950408889634f;
-          float rs0 = 0.f, rs1 = 0.f;
+            rsum = (((sv[0] + sv[1]) + (sv[2] + sv[3])) + ((sv[4] + sv[5]) + (sv[6] + sv[7]))) + ((sv[8] + sv[9]) + sv[10]);
+          } else {
+            float m0 = -3.0e38f, m1 = -3.0e38f;
 #pragma unroll 2
-          for (int v = 0; v < nvu; v++) {
-            const float4 x = *reinterpret_cast<const float4*>(slot + 4 * v);
-            const int w = 4 * v - shift;   // class of x.x
-            float4 rr;
-            rr.x = ex2a(fmaf(x.x, 1.4426950408889634f, nxb));
-            rr.y = ex2a(fmaf(x.y, 1.4426950408889634f, nxb));
-            rr.z = ex2a(fmaf(x.z, 1.4426950408889634f, nxb));
-            rr.w = ex2a(fmaf(x.w, 1.4426950408889634f, nxb));
-            if (w < 0 || w + 3 >= C) {
-              rr.x = (w >= 0 && w < C) ? rr.x : 0.f;
-              rr.y = (w + 1 >= 0 && w + 1 < C) ? rr.y : 0.f;
-              rr.z = (w + 2 >= 0 && w + 2 < C) ? rr.z : 0.f;
-              rr.w = (w + 3 >= 0 && w + 3 < C) ? rr.w : 0.f;
+            for (int v = 0; v < nvu; v++) {
+              const float4 x = *reinterpret_cast<const float4*>(slot + 4 * v);
+              m0 = fmaxf(m0, fmaxf(x.x, x.y));
+              m1 = fmaxf(m1, fmaxf(x.z, x.w));
             }
-            rs0 += rr.x + rr.y;
-            rs1 += rr.z + rr.w;
-            *reinterpret_cast<float4*>(slot + 4 * v) = rr;
+            const float nxb = -fmaxf(xbl, fmaxf(m0, m1) - kUnitGap) * 1.4426950408889634f;
+            float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll 2
+            for (int v = 0; v < nvu; v++) {
+              const float4 x = *reinterpret_cast<const float4*>(slot + 4 * v);
+              float4 rr;
+              rr.x = ex2a(fmaf(x.x, 1.4426950408889634f, nxb));
+              rr.y = ex2a(fmaf(x.y, 1.4426950408889634f, nxb));
+              rr.z = ex2a(fmaf(x.z, 1.4426950408889634f, nxb));
+              rr.w = ex2a(fmaf(x.w, 1.4426950408889634f, nxb));
+              rs0 += rr.x + rr.y;
+              rs1 += rr.z + rr.w;
+              *reinterpret_cast<float4*>(slot + 4 * v) = rr;
+            }
+            rsum = rs0 + rs1;
           }
-          const float rsum = rs0 + rs1;
           // a class ratio that overflowed (or a non-finite logit) is the robust kernel's business; ratios that
           // underflow only remove mass and are covered by the certificate
           if (!(rsum < 1e37f) || !(rsum > 0.f)) alarm |= AL_EMISSION;
@@ -890,6 +989,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
       }
       __syncwarp();
       if (q0 >= 0 && (lane & 15) == 0) flag_set(FLAG(FL_READY + side), min(2 * q0 + 2, S.nch));
+      TS(role, it, 3);
+      if (NASR_TUNING && p.prof && b == 0 && lane == 0 && it < 160) p.prof[3200 + it] = ((long long)q0 << 32) | (unsigned)nq;
+      it++;
       const bool idle = q0 < 0 && nq < 0;
       q0 = q1; q1 = q2; q2 = nq;
       const bool more = 2 * rs < S.nch || q0 >= 0 || q1 >= 0 || q2 >= 0;
@@ -897,81 +999,104 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
       if (__all_sync(0xffffffffu, idle)) __nanosleep(200);
     }
   } else {
-    // ================================ gradient warps =================================
-    // lane = (class of the round's group, frame): sums the run of cells of its class in 16-byte pieces, finishes the
-    // class in place in the frame's row record (ratio emission -> gradient); the warp then stores the rows to global
-    // memory, a row per instruction
+    // ================================ gradient warp =================================
+    // Serves both sides, whichever has a chunk of posteriors ready.  lane = (class of the group, frame): sums the
+    // run of cells of its class in 16-byte pieces, finishes the class in place in the frame's row record (emission ->
+    // gradient); the warp then stores the rows to global memory, a row per instruction.  One warp does this for the
+    // whole CTA, so the code is laid out for latency: the class table lives in registers, the first two pieces of
+    // EVERY run are loaded before the first add (a run shorter than that reads cells that hold zeros), only what a
+    // run has beyond eight cells goes through a loop, and the rows leave as eight loads followed by eight stores.
     if (want_grad) {
       const int f = lane & 7, cg = lane >> 3;
       const float PS = 1.8446744e19f;  // 2^PSHIFT
       const float gps = gs * PS;
       const int ngrp = (C - 1 + 3) / 4;
       const bool vec2 = ((shift | C) & 1) == 0 && ((((uintptr_t)gbase) | (rstride * 4)) & 7) == 0;
+      constexpr int NG = NGRP;
+      int cls[NG], o0[NG], o1[NG];
+      int nlong = 0;   // groups whose runs are longer than eight cells (falling counts: the first nlong)
+#pragma unroll
+      for (int g = 0; g < NG; g++) {
+        const int4 e = s_gtab[4 * g + cg];
+        cls[g] = e.x;
+        o0[g] = e.z > 0 ? e.y : GCELLS;
+        o1[g] = e.z > 4 ? e.y + 4 : GCELLS;
+        nlong += (e.z > 8) ? 1 : 0;
+      }
+      int done0 = 0, done1 = 0;
+      const int todo0 = S.nch - S.nc10, todo1 = S.nch - S.nc11;
 #pragma unroll 1
-      for (int i = S.nc1[d]; i < S.nch; i++) {
-        const Chunk ci = chunk_at(S, d, i);
-        const int j2 = i - S.nc1[d];
+      while (done0 < todo0 || done1 < todo1) {
+        int d2 = -1;
+        if (done0 < todo0 && flag_get(FLAG(FL_GFULL + 0)) > done0) d2 = 0;
+        else if (done1 < todo1 && flag_get(FLAG(FL_GFULL + 1)) > done1) d2 = 1;
+        d2 = __shfl_sync(0xffffffffu, d2, 0);
+        if (d2 < 0) {
+          __nanosleep(100);
+          continue;
+        }
+        const int j2 = d2 ? done1 : done0;
+        const int i = S.nc1(d2) + j2;
+        const Chunk ci = chunk_at(S, d2, i);
         const int stg = i % NST;
-        flag_wait<100>(FLAG(FL_GFULL + d), j2 + 1);
-        const float* G = s_gbuf + (size_t)((d * 2 + (j2 & 1)) * KC + f) * GS;
-        float* rec = reinterpret_cast<float*>(smem + sl.rows + ((size_t)(d * NST + stg) * KC + f) * ROWB);
+        TS(3 + d2, i, 1);
+        const float* G = s_gbuf + (size_t)((d2 * 2 + (j2 & 1)) * KC + f) * GS;
+        float* rec = reinterpret_cast<float*>(smem + sl.rows + ((size_t)(d2 * NST + stg) * KC + f) * ROWB);
         const float inv = rec[ROWW - 2];
         const float gy = gs * inv;
         rec += shift;
-        float tot = 0.f;
-#pragma unroll 1
-        for (int g = 0; g < ngrp; g++) {
-          const int4 e = s_gtab[4 * g + cg];
-          const float4* q = reinterpret_cast<const float4*>(G + e.y);
-          int n4 = e.z >> 2;
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#define NASR_ACC(i_)            \
-  {                             \
-    const float4 v = q[i_];     \
-    s0 += v.x;                  \
-    s1 += v.y;                  \
-    s2 += v.z;                  \
-    s3 += v.w;                  \
-  }
-          while (n4 > 8) {
-            n4--;
-            NASR_ACC(n4)
+        auto sums = [&](auto ngc) {
+          constexpr int N = decltype(ngc)::value;
+          float4 u[N], w[N];
+          float y[N], acc[N];
+#pragma unroll
+          for (int g = 0; g < N; g++) {
+            u[g] = *reinterpret_cast<const float4*>(G + o0[g]);
+            w[g] = *reinterpret_cast<const float4*>(G + o1[g]);
+            y[g] = rec[max(cls[g], 0)];
           }
-          switch (n4) {
-            case 8: NASR_ACC(7)
-            case 7: NASR_ACC(6)
-            case 6: NASR_ACC(5)
-            case 5: NASR_ACC(4)
-            case 4: NASR_ACC(3)
-            case 3: NASR_ACC(2)
-            case 2: NASR_ACC(1)
-            case 1: NASR_ACC(0)
-            default: break;
+#pragma unroll
+          for (int g = 0; g < N; g++) acc[g] = ((u[g].x + w[g].x) + (u[g].y + w[g].y)) + ((u[g].z + w[g].z) + (u[g].w + w[g].w));
+          for (int g = 0; g < nlong; g++) {   // the same in all lanes
+            const int4 e = s_gtab[4 * g + cg];
+            const float4* q = reinterpret_cast<const float4*>(G + e.y);
+            float x = 0.f;
+            for (int n = 2; n < (e.z >> 2); n++) {
+              const float4 v = q[n];
+              x += (v.x + v.y) + (v.z + v.w);
+            }
+#pragma unroll
+            for (int h = 0; h < N; h++) acc[h] += (h == g) ? x : 0.f;
           }
-#undef NASR_ACC
-          const float acc = (s0 + s1) + (s2 + s3);
-          tot += acc;
-          if (e.x >= 0) rec[e.x] = fmaf(rec[e.x], gy, -gps * acc);
-        }
+          float t = 0.f;
+#pragma unroll
+          for (int g = 0; g < N; g++) {
+            t += acc[g];
+            if (cls[g] >= 0) rec[cls[g]] = fmaf(y[g], gy, -gps * acc[g]);
+          }
+          return t;
+        };
+        float tot = ngrp <= 10 ? sums(std::integral_constant<int, 10>()) : sums(std::integral_constant<int, NG>());
         tot += __shfl_xor_sync(0xffffffffu, tot, 8);
         tot += __shfl_xor_sync(0xffffffffu, tot, 16);
         tot *= PS;
         if (f < ci.len && !(tot < 1.0f + 1e-4f)) alarm |= AL_OCC;
         if (cg == 0) rec[blank] = gs * (rec[blank] * inv - (1.0f - tot));
         __syncwarp();
-        if (lane == 0) flag_set(FLAG(FL_GFREE + d), j2 + 1);
+        TS(3 + d2, i, 2);
+        if (lane == 0) flag_set(FLAG(FL_GFREE + d2), j2 + 1);
         // rows -> global, one row per instruction (152 bytes at C = 38: 19 lanes of 8 bytes where the alignment allows)
-        const float* src = reinterpret_cast<const float*>(smem + sl.rows + (size_t)(d * NST + stg) * KC * ROWB) + shift;
+        const float* src = reinterpret_cast<const float*>(smem + sl.rows + (size_t)(d2 * NST + stg) * KC * ROWB) + shift;
         float* dst = gbase + (size_t)ci.t0 * rstride;
         const long long dstep = (long long)ci.dt * (long long)rstride;
         if (vec2) {
           if (2 * lane < C) {
-#pragma unroll 1
-            for (int ff = 0; ff < ci.len; ff++) {
-              *reinterpret_cast<float2*>(dst + 2 * lane) = *reinterpret_cast<const float2*>(src + 2 * lane);
-              src += ROWW;
-              dst += dstep;
-            }
+            float2 v[KC];
+#pragma unroll
+            for (int ff = 0; ff < KC; ff++) v[ff] = *reinterpret_cast<const float2*>(src + ff * ROWW + 2 * lane);
+#pragma unroll
+            for (int ff = 0; ff < KC; ff++)
+              if (ff < ci.len) *reinterpret_cast<float2*>(dst + ff * dstep + 2 * lane) = v[ff];
           }
         } else {
 #pragma unroll 1
@@ -983,12 +1108,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
           }
         }
         __syncwarp();
-        if (lane == 0) flag_set(FLAG(FL_FREED + d), i + 1);
+        if (lane == 0) flag_set(FLAG(FL_FREED + d2), i + 1);
+        TS(3 + d2, i, 3);
+        if (d2) done1++; else done0++;
       }
     }
   }
   if (alarm) atomicOr(&s_scal[0], alarm);
   __syncthreads();
+#if NASR_TUNING
+  if (p.prof && tid == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.prof[3700 + 2 * b + 1] = (long long)gt | ((long long)(s_scal[4] & 1) << 62);
+  }
+#endif
   if (tid == 0) {
     p.retry[b] = s_scal[0];
     atomicSub(&g_sm_arrivals[smid & 1023], 1);
@@ -1036,6 +1170,7 @@ int launch_lean(const lean::Params& p, cudaStream_t stream) {
 }  // namespace
 
 extern int g_debug_split;
+extern long long* g_debug_prof;
 
 bool ctc_narrow_supported(int T, int C, int Lmax) {
   if (T < 2 * lean::KC || C > 64 || C < 2) return false;
@@ -1067,6 +1202,7 @@ int ctc_narrow_launch(const float* logits, int T, int B, int C, long long st_t, 
   p.lo = reinterpret_cast<const char*>(logits);
   p.hi = reinterpret_cast<const char*>(logits) +
          4 * ((size_t)(T - 1) * st_t + (size_t)(B - 1) * st_b + (size_t)C);
+  p.prof = g_debug_prof;
   switch (lean_nl(Lmax)) {
     case 2: return launch_lean<2>(p, stream);
     case 4: return launch_lean<4>(p, stream);

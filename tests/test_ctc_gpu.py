@@ -299,13 +299,18 @@ def test_out_of_range_inputs_go_to_the_robust_kernel(common, debug_paths):
     x[30, 1, 3] += 60.0                  # one class dominates a frame by e^60
     x[:, 2, :] *= 5.0                    # large dynamic range everywhere (gaps up to ~e^80)
     g["seq_len"][3] = 9                  # shorter than two chunks
-    debug_paths(2, 0)
-    _run_loss(common, g)
-    flags = _flags(common, 8)
-    assert flags[0] and flags[3]
-    debug_paths(0, 0)
     want_loss, want_grad, want_status = c_oracle.ctc_loss_grad(
         x, g["label_values"], g["label_offsets"], g["seq_len"], precision="f64")
+    debug_paths(2, 0)
+    loss, grad, status = _run_loss(common, g)
+    flags = _flags(common, 8)
+    assert flags[3]
+    # whatever the throughput kernel keeps for itself must be right (the float32 kernel's emissions are in units of
+    # max(blank, largest class / 32), so a vanishing blank no longer forces a hand-over; the fp64 kernel flags it)
+    ok = flags == 0
+    np.testing.assert_allclose(loss[ok], want_loss[ok], rtol=LOSS_RTOL, atol=1e-5)
+    assert np.abs(grad[:, ok] - want_grad[:, ok]).max() <= GRAD_ATOL
+    debug_paths(0, 0)
     loss, grad, status = _run_loss(common, g)
     _assert_loss_grad(loss, grad, status, want_loss, want_grad, want_status)
 
