@@ -1026,12 +1026,8 @@ int ctc_beam_search(const float* logits, int T, int B, int C, long long st_t, lo
   const bool big = C > kBitSetMaxC;
   // four producer warps (then one CTA per SM): always for very wide rows; for moderately wide ones while the batch
   // does not need a second CTA per SM anyway
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    NASR_CUDA(cudaGetDevice(&dev));
-    NASR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int num_sms = 0;
+  NASR_CUDA(device_sm_count(&num_sms));
   const bool four = C > kOneProducerMaxC || (C > kStage2MinC * 4 && B <= num_sms);
   // second-stage bound: always for wide vocabularies; for narrow ones while there is one CTA per SM (the frame is
   // then latency bound and the shorter lists pay: B=64, C=38 6.1 -> 5.3 ms on N(0,1)*3, 5.4 -> 5.1 ms on planted

@@ -403,12 +403,8 @@ int launch_edit_distance(const HypT* hyp, long hyp_stride, const int32_t* hyp_le
               max_hyp_len);
     return NASR_ERR_UNSUPPORTED;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    NASR_CUDA(cudaFuncSetAttribute(edit_distance_kernel<HypT>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  // (set at every launch: the attribute is per device, and a process may drive several; the call is cheap)
+  NASR_CUDA(cudaFuncSetAttribute(edit_distance_kernel<HypT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   edit_distance_kernel<HypT><<<B, 32, smem, stream>>>(hyp, hyp_stride, hyp_len, hyp_offsets,
                                                      truth_values, truth_offsets, max_truth_len,
                                                      max_hyp_len, (int)(table / 4), normalize, dist, ler);

@@ -1278,12 +1278,9 @@ int pick_nl_wide(int Lmax) {
 template <int NL, int EPL, bool STREAM = false>
 int launch_fast(const fast::Params& p, cudaStream_t stream) {
   const fast::Smem sl = fast::smem_layout(NL, 8 * EPL, EPL ? 0 : p.C, STREAM);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NASR_CUDA(cudaFuncSetAttribute(fast::ctc_fast_kernel<NL, EPL, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   kMaxSmem));
-    attr_set = true;
-  }
+  // (set at every launch: the attribute is per device, and a process may drive several; the call is cheap)
+  NASR_CUDA(cudaFuncSetAttribute(fast::ctc_fast_kernel<NL, EPL, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kMaxSmem));
   if (sl.total > (size_t)kMaxSmem) {
     set_error("nasr_ctc: fast kernel shared memory %zu too large", sl.total);
     return NASR_ERR_UNSUPPORTED;
@@ -1310,7 +1307,13 @@ int ctc_narrow_launch(const float* logits, int T, int B, int C, long long st_t, 
                       const int32_t* label_values, const int32_t* label_offsets, int Lmax, const int32_t* seq_len,
                       int blank, float* loss, float* grad, const float* grad_loss, int32_t* status, int32_t* retry,
                       void* ckpt, cudaStream_t stream);
-int g_debug_old_narrow = 0;  // test hook (nasr_debug_config, environment NASR_OLD_NARROW=1): keep the fp64 kernel for C <= 64
+// Which kernel takes narrow vocabularies (C <= 64): the fp64 kernel of this file by default; the float32 kernel of
+// ctc_narrow.cu where NASR_NARROW_F32=1 is set in the environment (read at every call, so tests can switch).  Measured on
+// B200 (profiles/r2_*): 0.282 ms against 0.298 ms at cfg3, 0.137 against 0.154 at cfg2, 0.089 against 0.095 at cfg1.
+static bool use_narrow_f32() {
+  const char* e = getenv("NASR_NARROW_F32");
+  return e && e[0] == '1';
+}
 
 int g_debug_split = 0;  // test hook (nasr_debug_config): frames of the forward half, 0 = automatic
 int g_debug_ablate = 0;
@@ -1348,8 +1351,7 @@ int ctc_fast_launch(const float* logits, int T, int B, int C, long long st_t, lo
                     const int32_t* label_offsets, int Lmax, const int32_t* seq_len, int blank, float* loss,
                     float* grad, const float* grad_loss, int32_t* status, int32_t* retry, void* ckpt,
                     cudaStream_t stream) {
-  static const bool env_old = getenv("NASR_OLD_NARROW") != nullptr;
-  if (!env_old && !g_debug_old_narrow && ctc_narrow_supported(T, C, Lmax) && ctc_narrow_layout_ok(logits, st_t, st_b))
+  if (use_narrow_f32() && ctc_narrow_supported(T, C, Lmax) && ctc_narrow_layout_ok(logits, st_t, st_b))
     return ctc_narrow_launch(logits, T, B, C, st_t, st_b, label_values, label_offsets, Lmax, seq_len, blank, loss, grad,
                              grad_loss, status, retry, ckpt, stream);
   fast::Params p;
@@ -1362,12 +1364,8 @@ int ctc_fast_launch(const float* logits, int T, int B, int C, long long st_t, lo
   p.split = g_debug_split;
   p.prof = g_debug_prof;
   p.ablate = g_debug_ablate;
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    NASR_CUDA(cudaGetDevice(&dev));
-    NASR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int num_sms = 0;
+  NASR_CUDA(device_sm_count(&num_sms));
   p.num_sms = num_sms;
   if (is_wide(C)) {
     // rows the register-held path cannot take (too wide, not a multiple of four, not 16-byte aligned) are streamed

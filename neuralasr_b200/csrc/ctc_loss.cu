@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(512) ctc_robust_kernel(const Params p) {
   for (int i = tid; i < L; i += nt) {
     const int v = p.lab_vals[l0 + i];
     lab[i] = v;
-    bad |= (v < 0 || v >= blank);
+    bad |= (v < 0 || v >= C || v == blank);   // any class but the blank, wherever the blank sits (as the fast kernels)
   }
   if (L > p.Lmax) bad = 1;  // caller lied about max_label_len: shared memory is not sized for it
   if (__syncthreads_or(bad)) st |= NASR_ST_LABEL_OUT_OF_RANGE;
@@ -552,12 +552,8 @@ int ctc_loss_grad(const float* logits, int T, int B, int C, long long st_t, long
   p.ckpt = reinterpret_cast<double*>(base + pl.ws_scale);  // ws_scale is a multiple of 16
   p.K = pl.K; p.nseg = pl.nseg; p.Upad = pl.Upad; p.Cpad = pl.Cpad;
   p.only_if = use_fast ? retry : nullptr;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NASR_CUDA(cudaFuncSetAttribute(ctc_robust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)kSmemBudget));
-    attr_set = true;
-  }
+  // (set at every launch: the attribute is per device, and a process may drive several; the call is cheap)
+  NASR_CUDA(cudaFuncSetAttribute(ctc_robust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
   ctc_robust_kernel<<<B, pl.threads, pl.smem, stream>>>(p);
   count_launch();
   NASR_CUDA(cudaGetLastError());

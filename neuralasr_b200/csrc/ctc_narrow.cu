@@ -321,10 +321,9 @@ __device__ __forceinline__ void set_F_other(float (&F)[NL], float (&SF)[NL], con
 
 // Renormalise every slot (larger state -> biased exponent TB), keeping E[k] >= E[k-1] - GCAP over slots with mass;
 // empty slots adopt the exponent below.  The chain through a lane is x -> max(a, x - b) (a: what the lane yields on its
-// own, b: GCAP per slot with mass); it is followed through the two lanes below -- up to 3 NL slots and 3 NL GCAP bits,
-// beyond which a raise could only move what is flushed anyway.  A single warp runs this between two chunks of its
-// recursion, so the dependent chain is kept short: one pass over the slots, the lanes below folded in with two
-// shuffles, every slot then finished independently of the others.
+// own, b: GCAP per slot with mass), composed over the lanes by a scan.  A single warp runs this between two chunks of
+// its recursion, so the dependent chain is kept short: one pass over the slots, the scan, every slot then finished
+// independently of the others.
 template <int NL>
 __device__ __forceinline__ void rescale(float (&A)[NL], float (&B)[NL], float (&F)[NL], float (&SF)[NL], int (&E)[NL],
                                         uint32_t skipmask, int lane, int& alarm) {
@@ -343,13 +342,20 @@ __device__ __forceinline__ void rescale(float (&A)[NL], float (&B)[NL], float (&
     cnt[k] = c;
   }
   if (mall >= 0x7f800000u) alarm |= AL_NONFINITE;   // inf or nan (sign bit set or exponent 255)
-  // exponent below this lane's first slot: the lane below on its own, raised by what the lane below that sends up
-  int pin = __shfl_up_sync(0xffffffffu, prev, 1);
-  const int cb = __shfl_up_sync(0xffffffffu, c, 1);
+  // exponent below this lane's first slot: an inclusive scan of the lanes' maps x -> max(a, x - b), shifted by one lane
+  // (exact; following only the two lanes below was measured to lose mass at steep fronts with two slots per lane)
+  int ca = prev, cb = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int la = __shfl_up_sync(0xffffffffu, ca, o);
+    const int lb = __shfl_up_sync(0xffffffffu, cb, o);
+    if (lane >= o) {
+      ca = max(ca, max(la, ENEG + (1 << 20)) - cb);
+      cb += lb;
+    }
+  }
+  int pin = __shfl_up_sync(0xffffffffu, ca, 1);
   if (lane == 0) pin = ENEG;
-  int pin2 = __shfl_up_sync(0xffffffffu, pin, 1);   // (lane 1 receives ENEG)
-  if (lane == 0) pin2 = ENEG;
-  pin = max(pin, max(pin2, ENEG + (1 << 20)) - cb);
 #pragma unroll
   for (int k = 0; k < NL; k++) {
     const int e = max(loc[k], max(pin, ENEG + (1 << 20)) - cnt[k]);
@@ -996,16 +1002,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
       q0 = q1; q1 = q2; q2 = nq;
       const bool more = 2 * rs < S.nch || q0 >= 0 || q1 >= 0 || q2 >= 0;
       if (!__any_sync(0xffffffffu, more)) break;
-      if (__all_sync(0xffffffffu, idle)) __nanosleep(200);
+      // nothing to request and nothing to convert: the producer is up to NST chunks (tens of microseconds) ahead of
+      // its readers and shares a scheduler with a recursion warp -- sleep, do not poll
+      if (__all_sync(0xffffffffu, idle)) __nanosleep(2000);
     }
   } else {
     // ================================ gradient warp =================================
     // Serves both sides, whichever has a chunk of posteriors ready.  lane = (class of the group, frame): sums the
     // run of cells of its class in 16-byte pieces, finishes the class in place in the frame's row record (emission ->
     // gradient); the warp then stores the rows to global memory, a row per instruction.  One warp does this for the
-    // whole CTA, so the code is laid out for latency: the class table lives in registers, the first two pieces of
+    // whole CTA, so the code is laid out for latency: the class table lives in registers, the first three pieces of
     // EVERY run are loaded before the first add (a run shorter than that reads cells that hold zeros), only what a
-    // run has beyond eight cells goes through a loop, and the rows leave as eight loads followed by eight stores.
+    // run has beyond twelve cells goes through a loop, and the rows leave as eight loads followed by eight stores.
     if (want_grad) {
       const int f = lane & 7, cg = lane >> 3;
       const float PS = 1.8446744e19f;  // 2^PSHIFT
@@ -1013,15 +1021,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
       const int ngrp = (C - 1 + 3) / 4;
       const bool vec2 = ((shift | C) & 1) == 0 && ((((uintptr_t)gbase) | (rstride * 4)) & 7) == 0;
       constexpr int NG = NGRP;
-      int cls[NG], o0[NG], o1[NG];
-      int nlong = 0;   // groups whose runs are longer than eight cells (falling counts: the first nlong)
+      int cls[NG], o0[NG], o1[NG], o2[NG];
+      int nlong = 0;   // groups whose runs are longer than twelve cells (falling counts: the first nlong)
 #pragma unroll
       for (int g = 0; g < NG; g++) {
         const int4 e = s_gtab[4 * g + cg];
         cls[g] = e.x;
         o0[g] = e.z > 0 ? e.y : GCELLS;
         o1[g] = e.z > 4 ? e.y + 4 : GCELLS;
-        nlong += (e.z > 8) ? 1 : 0;
+        o2[g] = e.z > 8 ? e.y + 8 : GCELLS;
+        nlong += (e.z > 12) ? 1 : 0;
       }
       int done0 = 0, done1 = 0;
       const int todo0 = S.nch - S.nc10, todo1 = S.nch - S.nc11;
@@ -1047,21 +1056,24 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
         rec += shift;
         auto sums = [&](auto ngc) {
           constexpr int N = decltype(ngc)::value;
-          float4 u[N], w[N];
+          float4 u[N], w[N], x3[N];
           float y[N], acc[N];
 #pragma unroll
           for (int g = 0; g < N; g++) {
             u[g] = *reinterpret_cast<const float4*>(G + o0[g]);
             w[g] = *reinterpret_cast<const float4*>(G + o1[g]);
+            x3[g] = *reinterpret_cast<const float4*>(G + o2[g]);
             y[g] = rec[max(cls[g], 0)];
           }
 #pragma unroll
-          for (int g = 0; g < N; g++) acc[g] = ((u[g].x + w[g].x) + (u[g].y + w[g].y)) + ((u[g].z + w[g].z) + (u[g].w + w[g].w));
+          for (int g = 0; g < N; g++)
+            acc[g] = (((u[g].x + w[g].x) + (u[g].y + w[g].y)) + ((u[g].z + w[g].z) + (u[g].w + w[g].w))) +
+                     ((x3[g].x + x3[g].y) + (x3[g].z + x3[g].w));
           for (int g = 0; g < nlong; g++) {   // the same in all lanes
             const int4 e = s_gtab[4 * g + cg];
             const float4* q = reinterpret_cast<const float4*>(G + e.y);
             float x = 0.f;
-            for (int n = 2; n < (e.z >> 2); n++) {
+            for (int n = 3; n < (e.z >> 2); n++) {
               const float4 v = q[n];
               x += (v.x + v.y) + (v.z + v.w);
             }
@@ -1090,10 +1102,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
         float* dst = gbase + (size_t)ci.t0 * rstride;
         const long long dstep = (long long)ci.dt * (long long)rstride;
         if (vec2) {
+          // the rows go into registers, the stage is released, then the stores drain on their own (the release is a
+          // fence: after the stores it would wait for every one of them to be acknowledged)
+          float2 v[KC];
           if (2 * lane < C) {
-            float2 v[KC];
 #pragma unroll
             for (int ff = 0; ff < KC; ff++) v[ff] = *reinterpret_cast<const float2*>(src + ff * ROWW + 2 * lane);
+          }
+          __syncwarp();
+          if (lane == 0) flag_set(FLAG(FL_FREED + d2), i + 1);
+          if (2 * lane < C) {
 #pragma unroll
             for (int ff = 0; ff < KC; ff++)
               if (ff < ci.len) *reinterpret_cast<float2*>(dst + ff * dstep + 2 * lane) = v[ff];
@@ -1106,9 +1124,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
             src += ROWW;
             dst += dstep;
           }
+          __syncwarp();
+          if (lane == 0) flag_set(FLAG(FL_FREED + d2), i + 1);
         }
-        __syncwarp();
-        if (lane == 0) flag_set(FLAG(FL_FREED + d2), i + 1);
         TS(3 + d2, i, 3);
         if (d2) done1++; else done0++;
       }

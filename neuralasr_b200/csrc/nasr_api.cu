@@ -500,6 +500,17 @@ int nasr_host_ctx_set_decoder(nasr_host_ctx* c, int decoder, int beam_width) {
   return NASR_OK;
 }
 
+// An error return from the middle of a step: wait for the copies and kernels already queued on the context's streams,
+// so that the caller may reuse or free its buffers (the status of the waits is ignored: rc is what is reported).
+static int host_drain(nasr_host_ctx* c, int rc) {
+  if (c->s_in) cudaStreamSynchronize(c->s_in);
+  for (int i = 0; i < 4; i++)
+    if (c->s_k[i]) cudaStreamSynchronize(c->s_k[i]);
+  if (c->s_beam) cudaStreamSynchronize(c->s_beam);
+  if (c->s_out) cudaStreamSynchronize(c->s_out);
+  return rc;
+}
+
 float* nasr_host_ctx_pinned_logits(nasr_host_ctx* c) { return c ? c->h_logits : nullptr; }
 float* nasr_host_ctx_pinned_grad(nasr_host_ctx* c) { return c ? c->h_grad : nullptr; }
 
@@ -567,15 +578,15 @@ int nasr_host_ctc_step(nasr_host_ctx* c, const float* logits, int T, int B, int 
     int rc = ctc_loss_grad(c->d_logits + off, T, Bk, C, (long long)B * C, C, c->d_lab_vals, c->d_lab_offs + b0, Lmax,
                            c->d_seq + b0, blank, c->d_loss + b0, grad ? c->d_grad + off : nullptr,
                            grad_loss ? c->d_grad_loss + b0 : nullptr, c->d_status + b0, ws, ws_bytes, s);
-    if (rc != NASR_OK) return rc;
+    if (rc != NASR_OK) return host_drain(c, rc);
     if (want_decode && c->decoder == 0) {
       rc = greedy_decode(c->d_logits + off, T, Bk, C, (long long)B * C, C, c->d_seq + b0, blank, 1,
                          c->d_hyp + (size_t)b0 * T, c->d_hyp_len + b0, c->d_nsl + b0, s);
-      if (rc != NASR_OK) return rc;
+      if (rc != NASR_OK) return host_drain(c, rc);
       if (dist || ler) {
         rc = edit_distance_dense(c->d_hyp + (size_t)b0 * T, T, c->d_hyp_len + b0, c->d_lab_vals, c->d_lab_offs + b0,
                                  Lmax, Bk, 1, c->d_dist + b0, c->d_ler + b0, s);
-        if (rc != NASR_OK) return rc;
+        if (rc != NASR_OK) return host_drain(c, rc);
       }
     }
     NASR_CUDA(cudaEventRecord(c->ev_done[k], s));
@@ -590,11 +601,11 @@ int nasr_host_ctc_step(nasr_host_ctx* c, const float* logits, int T, int B, int 
     NASR_CUDA(cudaStreamWaitEvent(c->s_beam, c->ev_in[nblk - 1], 0));
     int rc = ctc_beam_search(c->d_logits, T, B, C, (long long)B * C, C, c->d_seq, blank, c->beam_width, 1, 1, c->d_hyp,
                              c->d_hyp_len, c->d_nsl, c->d_ws_beam, c->ws_beam_bytes, c->s_beam);
-    if (rc != NASR_OK) return rc;
+    if (rc != NASR_OK) return host_drain(c, rc);
     if (dist || ler) {
       rc = edit_distance_dense(c->d_hyp, T, c->d_hyp_len, c->d_lab_vals, c->d_lab_offs, Lmax, B, 1, c->d_dist,
                                c->d_ler, c->s_beam);
-      if (rc != NASR_OK) return rc;
+      if (rc != NASR_OK) return host_drain(c, rc);
     }
     NASR_CUDA(cudaEventRecord(c->ev_beam, c->s_beam));
     NASR_CUDA(cudaStreamWaitEvent(sout, c->ev_beam, 0));

@@ -32,6 +32,22 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
     }                                                                                     \
   } while (0)
 
+// SM count of the current device (cached per device: a process may drive several)
+inline cudaError_t device_sm_count(int* out) {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  int n = (dev >= 0 && dev < 64) ? cache[dev].load(std::memory_order_relaxed) : 0;
+  if (!n) {
+    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) cache[dev].store(n, std::memory_order_relaxed);
+  }
+  *out = n;
+  return cudaSuccess;
+}
+
 constexpr int kWarp = 32;
 
 __device__ __forceinline__ float warp_max(float v) {

@@ -90,8 +90,14 @@ def _seq_len_tensor(seq_len, device, B):
     return t
 
 
+def _ws_key(device):
+    """One workspace per (device, stream): calls queued on different streams must not share retry flags,
+    checkpoints or the beam trie, and a buffer that is regrown is only ever in use by the stream that owns it."""
+    return (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
+
+
 def _workspace(device, nbytes):
-    key = (device.type, device.index)
+    key = _ws_key(device)
     ws = _WORKSPACES.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
@@ -108,7 +114,7 @@ def debug_config(path=0, split_frames=0):
 def retry_flags(device, B):
     """Test hook: which utterances of the last loss call the throughput kernel handed to the robust one
     (the first B int32 of the workspace; undefined if the throughput kernel did not run)."""
-    ws = _WORKSPACES[(device.type, device.index)]
+    ws = _WORKSPACES[_ws_key(device)]
     off = (-ws.data_ptr()) % 256
     return ws[off:off + 4 * B].view(torch.int32).clone()
 
@@ -361,7 +367,7 @@ def beam_decoding(logits, seq_len, beam_width=100, top_paths=1, merge_repeated=T
     log_prob = torch.empty((B, P), dtype=torch.float32, device=dev)
     need = ctypes.c_size_t(0)
     _lib.check(lib.nasr_ctc_beam_workspace_bytes(T, B, C, W, ctypes.byref(need)), "beam workspace")
-    key = (dev.type, dev.index)
+    key = _ws_key(dev)
     ws = _BEAM_WORKSPACES.get(key)
     if ws is None or ws.numel() < need.value:
         ws = torch.empty(max(need.value, 1), dtype=torch.uint8, device=dev)

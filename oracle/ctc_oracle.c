@@ -89,7 +89,7 @@ static void parallel_for(int n, item_fn fn, void* ctx, int num_threads) {
                               real grad_scale) {                                           \
     int status = 0;                                                                        \
     for (int i = 0; i < L; i++)                                                            \
-      if (lab[i] < 0 || lab[i] >= blank) {                                                 \
+      if (lab[i] < 0 || lab[i] >= C || lab[i] == blank) {                                              \
         *loss_out = INFINITY;                                                              \
         return NASR_ST_LABEL_OUT_OF_RANGE;                                                 \
       }                                                                                    \

@@ -43,7 +43,7 @@ import numpy as np
 
 # Per-utterance status bit flags, shared with include/nasr_ctc.h.
 STATUS_OK = 0
-STATUS_LABEL_OUT_OF_RANGE = 1   # label < 0 or label >= blank
+STATUS_LABEL_OUT_OF_RANGE = 1   # label < 0, label >= C or label == blank
 STATUS_SEQ_LEN_OUT_OF_RANGE = 2  # seq_len < 0 or seq_len > T
 STATUS_NOT_ENOUGH_TIME = 4      # seq_len < L + repeats
 STATUS_NO_VALID_PATH = 8        # log p == -inf (underflow / bypassed checks)
@@ -101,7 +101,7 @@ def ctc_loss_grad_one(x, lab, blank, dtype=np.float64):
     lab = np.asarray(lab, dtype=np.int64)
     L = lab.size
     status = STATUS_OK
-    if L and (lab.min() < 0 or lab.max() >= blank):
+    if L and (lab.min() < 0 or lab.max() >= C or (lab == blank).any()):
         return np.inf, np.zeros_like(x), STATUS_LABEL_OUT_OF_RANGE
     if Tb == 0:
         # (definition) zero-length utterance: skipped, loss 0, gradient 0.
@@ -173,7 +173,7 @@ def ctc_loss_grad_one_vec(x, lab, blank, dtype=np.float64):
     lab = np.asarray(lab, dtype=np.int64)
     L = lab.size
     status = STATUS_OK
-    if L and (lab.min() < 0 or lab.max() >= blank):
+    if L and (lab.min() < 0 or lab.max() >= C or (lab == blank).any()):
         return np.inf, np.zeros_like(x), STATUS_LABEL_OUT_OF_RANGE
     if Tb == 0:
         return 0.0, np.zeros_like(x), status

@@ -26,6 +26,18 @@ def common():
     return c
 
 
+@pytest.fixture(autouse=True, params=["f64", "f32"])
+def narrow_kernel(request, monkeypatch):
+    """Every test of this module runs with both kernels for narrow vocabularies: the fp64 kernel (csrc/ctc_fast.cu,
+    the default) and the float32 one (csrc/ctc_narrow.cu, NASR_NARROW_F32=1: the library reads the variable at
+    every call)."""
+    if request.param == "f32":
+        monkeypatch.setenv("NASR_NARROW_F32", "1")
+    else:
+        monkeypatch.delenv("NASR_NARROW_F32", raising=False)
+    return request.param
+
+
 def _triple(g):
     from neuralasr_b200.utils import sparse_to_csr  # noqa: F401
     offs = g["label_offsets"]
@@ -553,3 +565,52 @@ def test_wide_shapes_sweep(common):
             g["logits"], g["label_values"], g["label_offsets"], g["seq_len"], precision="f64")
         _assert_loss_grad(loss.cpu().numpy(), grad.cpu().numpy(), status.cpu().numpy(), want_loss, want_grad,
                           want_status)
+
+
+def test_tf_published_basic_case_through_the_c_abi(common):
+    """TensorFlow's ctc_loss_op_test.py basic case (tests/golden/tf_ctc_loss_op_test_basic.json): losses to the six
+    published digits, the published gradient entries."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "tf_ctc_loss_op_test_basic.json")) as f:
+        d = json.load(f)
+    probs = np.stack([np.asarray(c["probs"], np.float64) for c in d["cases"]], axis=1)     # [T=5, B=2, C=6]
+    labs = [np.asarray(c["labels"], np.int32) for c in d["cases"]]
+    g = dict(logits=np.log(probs).astype(np.float32), label_values=np.concatenate(labs),
+             label_offsets=np.asarray([0, labs[0].size, labs[0].size + labs[1].size], np.int32),
+             seq_len=np.asarray([5, 5], np.int32))
+    loss, grad, status = _run_loss(common, g)
+    assert not status.any()
+    for b, c in enumerate(d["cases"]):
+        assert abs(loss[b] - c["loss"]) < 2e-5
+        for t, k, want in c["grad_entries"]:
+            assert abs(grad[t, b, k] - want) < 2e-6 + 1e-6
+
+
+@pytest.mark.parametrize("blank", [0, 7])
+def test_blank_anywhere_on_both_paths(common, debug_paths, blank):
+    """The blank may be any class (the C-ABI takes it explicitly): same answers from the throughput kernel and from
+    the robust one, labels may be every class but the blank."""
+    g = make_batch(31, T=96, B=6, C=12, Lmax=14, mode="ragged")
+    # make_batch draws labels from [0, C-2] with the blank last: move the classes around so that `blank` is the blank
+    vals = g["label_values"].copy()
+    vals[vals == blank] = 11
+    g["label_values"] = vals
+    want_loss, want_grad, want_status = c_oracle.ctc_loss_grad(
+        g["logits"], g["label_values"], g["label_offsets"], g["seq_len"], precision="f64", blank=blank)
+    assert not want_status.any()
+    for path in (0, 1):
+        debug_paths(path, 0)
+        x = torch.from_numpy(g["logits"]).cuda()
+        loss, grad, status = common.ctc_loss_and_grad(x, _triple(g), g["seq_len"], blank=blank)
+        torch.cuda.synchronize()
+        _assert_loss_grad(loss.cpu().numpy(), grad.cpu().numpy(), status.cpu().numpy(), want_loss, want_grad, want_status)
+
+
+def test_full_size_cfg4_whole_batch_against_oracle(common):
+    """BASELINE cfg4 at its own size (B=32, T=3000, L<=600): every utterance against the C oracle."""
+    g = make_batch(404, T=3000, B=32, C=38, Lmax=600, mode="full", empty_row=False)
+    want_loss, want_grad, want_status = c_oracle.ctc_loss_grad(
+        g["logits"], g["label_values"], g["label_offsets"], g["seq_len"], precision="f64")
+    loss, grad, status = _run_loss(common, g)
+    _assert_loss_grad(loss, grad, status, want_loss, want_grad, want_status)

@@ -185,3 +185,33 @@ def test_sparse_csr_roundtrip():
     assert np.array_equal(i2, idx) and s2.tolist() == [3, 2]
     with pytest.raises(ValueError):
         o.sparse_to_csr((idx[::-1], vals, np.array([3, 2], np.int64)))
+
+
+def _tf_basic_case():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "tf_ctc_loss_op_test_basic.json")) as f:
+        return json.load(f)
+
+
+def test_tf_published_ctc_loss_basic_case():
+    """TensorFlow's own ctc_loss_op_test.py basic case (tests/golden/tf_ctc_loss_op_test_basic.json): the oracle, numpy
+    and C, gives the published losses to their six printed digits, the published gradient entries, and otherwise the
+    softmax itself (TF's tables equal the input matrix wherever the class is not on the target's path at that frame)."""
+    from oracle import c_oracle
+    d = _tf_basic_case()
+    blank = d["blank"]
+    for case in d["cases"]:
+        p = np.asarray(case["probs"], np.float64)
+        lab = np.asarray(case["labels"], np.int32)
+        loss, grad, st = o.ctc_loss_grad_one(np.log(p), lab, blank)
+        assert st == 0
+        assert abs(loss - case["loss"]) < 5e-6
+        for t, c, g in case["grad_entries"]:
+            assert abs(grad[t, c] - g) < 2e-6
+        x = np.log(p).astype(np.float32)[:, None, :]
+        closs, cgrad, cst = c_oracle.ctc_loss_grad(x, lab, np.asarray([0, lab.size], np.int32),
+                                                   np.asarray([5], np.int32), precision="f64")
+        assert cst[0] == 0 and abs(closs[0] - case["loss"]) < 5e-6
+        for t, c, g in case["grad_entries"]:
+            assert abs(cgrad[t, 0, c] - g) < 2e-6

@@ -4,6 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import torch
+os.environ.setdefault('NASR_NARROW_F32', '1')
 from conftest import make_batch
 from neuralasr_b200.networks import common
 from oracle import c_oracle
@@ -16,6 +17,9 @@ if len(sys.argv) > 1 and sys.argv[1] == "peaky4":
     kw = dict(T=400, B=12, C=38, Lmax=100, mode="ragged", peaky=True)
 if len(sys.argv) > 1 and sys.argv[1] == "rand2":
     kw = dict(T=400, B=12, C=38, Lmax=60, mode="ragged")
+split = 0
+if len(sys.argv) > 1 and sys.argv[1] == "uneven":
+    kw = dict(T=120, B=6, C=38, Lmax=30, mode="ragged"); seed = 99; split = 104
 if len(sys.argv) > 1 and sys.argv[1] == "cfg3":
     kw = dict(T=1000, B=32, C=38, Lmax=200, mode="full"); seed = 7
 g = make_batch(seed, **kw)
@@ -27,7 +31,7 @@ rows = np.repeat(np.arange(B), lens)
 cols = np.arange(g["label_offsets"][-1]) - np.repeat(g["label_offsets"][:-1], lens)
 lab = (np.stack([rows, cols], 1).astype(np.int64), g["label_values"], np.asarray([B, int(max(lens.max(), 1))]))
 x = torch.from_numpy(g["logits"]).to(dev)
-common.debug_config(2, 0)
+common.debug_config(2, split)
 loss, grad, st = common.ctc_loss_and_grad(x, lab, g["seq_len"], out_grad=torch.zeros_like(x))
 torch.cuda.synchronize()
 fl = common.retry_flags(dev, B).cpu().numpy()
