@@ -202,6 +202,11 @@ def run_ours(args, w, rank, world, local_rank):
         sys.stdout.flush()
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
+        # the one collective is 32 bytes: one channel (one CTA) is all it needs, and every further NCCL CTA is a CTA
+        # slot the loss kernel of the next step does not get (NASR_NCCL_TUNE=0 leaves NCCL's defaults)
+        if os.environ.get("NASR_NCCL_TUNE", "1") != "0":
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", "1")
+            os.environ.setdefault("NCCL_MIN_NCHANNELS", "1")
         dist.init_process_group("nccl", device_id=dev)
     from neuralasr_b200 import _build
     if not os.path.exists(_build.LIB_PATH) and world == 1:
@@ -236,9 +241,10 @@ def run_ours(args, w, rank, world, local_rank):
         sums = common.batch_sums(loss_b=loss_b)
         # the path's one collective: 4 float64 scalars over NCCL, asynchronous like the logging it feeds
         # (the next step's kernels do not wait for it; every reduction is waited for before the clock stops)
-        _, work = towers.all_reduce_sums(sums, async_op=True)
-        if work is not None:
-            pending.append(work)
+        if args.reduce == "step":
+            _, work = towers.all_reduce_sums(sums, async_op=True)
+            if work is not None:
+                pending.append(work)
         return sums
 
     for i in range(args.warmup):
@@ -493,6 +499,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reduce", default="step", choices=["step", "none"],
+                    help="experiment: 'none' leaves the per-step scalar all-reduce out (upper bound of weak scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -206,6 +206,12 @@ int nasr_edit_distance_csr_i64(const int64_t* hyp_values, const int32_t* hyp_off
 int nasr_batch_sums_f64(const float* loss, const float* ler, const int32_t* dist, int B,
                         double* sums, void* stream);
 
+/* The one collective of the path: the tower means of tfnetwork.py:135-136 are an all-reduce(sum) of the float64
+ * vector nasr_batch_sums_f64 builds (n = 4), 32 bytes over NCCL / NVLink.  `nccl_comm` is the caller's ncclComm_t;
+ * the library resolves ncclAllReduce from the NCCL the process has loaded (libnccl.so.2), it does not link NCCL.
+ * Asynchronous on `stream`, in place.  A caller that lives in torch.distributed uses towers.all_reduce_sums instead. */
+int nasr_allreduce_scalars(void* nccl_comm, double* vec, int n, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * HOST-buffer path: what a caller that holds numpy arrays (the reference's feed_dict world,
  * tfnetwork.py:183-190) uses.  The context owns device buffers, pinned staging and one stream, sized

@@ -77,7 +77,7 @@ def build_library(force=False, verbose=False):
         if verbose:
             print(out)
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "--cudart=shared",
-           "-Xlinker", "-rpath=/usr/local/cuda/lib64", "-o", LIB_PATH] + objs
+           "-Xlinker", "-rpath=/usr/local/cuda/lib64", "-ldl", "-o", LIB_PATH] + objs
     res = subprocess.run(cmd, capture_output=True, text=True, env=env)
     if res.returncode != 0:
         raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)

@@ -21,6 +21,7 @@ SIGNATURES = {
     "nasr_launch_count": (ctypes.c_uint64, []),
     "nasr_debug_config": (_i, [_i, _i]),
     "nasr_debug_profile": (_i, [_vp]),
+    "nasr_allreduce_scalars": (_i, [_vp, _vp, _i, _vp]),
     "nasr_ctc_workspace_bytes": (_i, [_i, _i, _i, _i, ctypes.POINTER(_sz)]),
     "nasr_ctc_loss_grad_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp,
                                     _sz, _vp]),

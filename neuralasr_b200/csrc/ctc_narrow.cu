@@ -57,7 +57,7 @@ namespace nasr {
 namespace lean {
 
 constexpr int KC = 8;             // frames per chunk (= renormalisation and checkpoint interval)
-constexpr int NST = 10;           // chunks of row records per side in the ring
+constexpr int NST = 8;            // chunks of row records per side in the ring
 constexpr int NTHREADS = 128;     // 4 warps: two CTAs per SM leave every thread 255 registers
 constexpr int TB = 107;           // biased exponent a slot's larger state is brought to (2^-20)
 constexpr int GCAP = 20;          // a slot with mass sits at most this far below the slot with mass beneath it
@@ -159,7 +159,7 @@ __device__ __forceinline__ float pow2f(int e) { return __int_as_float(max(e + 12
 // ---- shared memory layout -----------------------------------------------------------------------------------------
 __host__ __device__ constexpr size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 struct Smem {
-  size_t bars, flags, rows, gbuf, meet, lab, cell, cnt, clsoff, gtab, lsum, scal, total;
+  size_t bars, flags, rows, gbuf, obuf, meet, lab, cell, cnt, clsoff, gtab, lsum, scal, total;
 };
 __host__ __device__ inline Smem smem_layout(int NL) {
   Smem s;
@@ -169,6 +169,7 @@ __host__ __device__ inline Smem smem_layout(int NL) {
   s.flags = o;   o = al16(o + NFLAGS * 4);
   s.rows = o;    o = al16(o + (size_t)2 * NST * KC * ROWB);
   s.gbuf = o;    o = al16(o + (size_t)2 * 2 * KC * GSB);
+  s.obuf = o;    o = al16(o + (size_t)2 * KC * 32 * 32);          // [side][frame][lane][8]: the other direction's rows
   s.meet = o;    o = al16(o + (size_t)3 * N * 4);
   s.lab = o;     o = al16(o + (size_t)N * 4);
   s.cell = o;    o = al16(o + (size_t)N * 2);
@@ -784,18 +785,45 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
         TS(role, i, 0);
         flag_wait<20>(FLAG(FL_READY + d), i + 1);
         TS(role, i, 1);
-        float O[KC][NL];
-        const bool full = ci.len == KC;
-        load_em<NL>(r, coloff, boff, smem, (uint32_t)(ci.len - 1) * ROWB);
-        if (full) {
+        // The chunk's frames run through two-frame loop bodies (a chunk fully unrolled is ~27 KB of code per warp: the
+        // profile of that version had "no instruction" -- instruction-cache misses -- as its first stall reason), and
+        // the other direction's rows go through shared memory in between: [frame][lane][8], two 16-byte stores per frame.
+        const uint32_t obase = (uint32_t)sl.obuf + (uint32_t)d * KC * 32 * 32 + (uint32_t)lane * 32;
+        {
+          uint32_t wc[NL], wb;
+          const uint32_t top = (uint32_t)(ci.len - 1) * ROWB;
 #pragma unroll
-          for (int g = 0; g < KC; g++)
-            other_frame<NL>(Ao, Bo, Fo, SFo, r, coloff, boff, smem, g < KC - 1, (KC - 2 - g) * ROWB, O[KC - 1 - g]);
-        } else {
+          for (int k = 0; k < NL; k++) wc[k] = coloff[k] + top;
+          wb = boff + top;
+          load_em<NL>(r, wc, wb, smem, 0);
+          auto put = [&](int f, const float (&o)[NL]) {
+            float v[8];
 #pragma unroll
-          for (int g = 0; g < KC; g++)
-            if (KC - 1 - g < ci.len)
-              other_frame<NL>(Ao, Bo, Fo, SFo, r, coloff, boff, smem, g < KC - 1, (KC - 2 - g) * ROWB, O[KC - 1 - g]);
+            for (int k = 0; k < 8; k++) v[k] = k < NL ? o[k] : 0.f;
+            float4* q = reinterpret_cast<float4*>(smem + obase + (uint32_t)f * (32 * 32));
+            q[0] = make_float4(v[0], v[1], v[2], v[3]);
+            if (NL > 4) q[1] = make_float4(v[4], v[5], v[6], v[7]);
+          };
+          int f = ci.len - 1;
+          float o[NL];
+          if (ci.len & 1) {
+            other_frame<NL>(Ao, Bo, Fo, SFo, r, wc, wb, smem, f > 0, (uint32_t)(-ROWB), o);
+            put(f, o);
+            f--;
+#pragma unroll
+            for (int k = 0; k < NL; k++) wc[k] -= ROWB;
+            wb -= ROWB;
+          }
+#pragma unroll 1
+          for (; f >= 1; f -= 2) {
+            other_frame<NL>(Ao, Bo, Fo, SFo, r, wc, wb, smem, true, (uint32_t)(-ROWB), o);
+            put(f, o);
+            other_frame<NL>(Ao, Bo, Fo, SFo, r, wc, wb, smem, f > 1, (uint32_t)(-2 * ROWB), o);
+            put(f - 1, o);
+#pragma unroll
+            for (int k = 0; k < NL; k++) wc[k] -= 2 * ROWB;
+            wb -= 2 * ROWB;
+          }
         }
         // r now holds the emissions of the chunk's first frame again: where the own recursion starts
         TS(role, i, 2);
@@ -823,15 +851,42 @@ __global__ void __launch_bounds__(NTHREADS, 2) ctc_lean_kernel(const Params p) {
             Eo[k] = e[NL - 1 - k];
           }
         }
-        if (full) {
+        {
+          uint32_t wc[NL], wg[NL], wb = boff;
 #pragma unroll
-          for (int f = 0; f < KC; f++)
-            own_frame<NL, true>(A, B, F, SF, r, coloff, boff, smem, f < KC - 1, (f + 1) * ROWB, O[f], c1, c2, gph, f * GSB);
-        } else {
+          for (int k = 0; k < NL; k++) {
+            wc[k] = coloff[k];
+            wg[k] = gph[k];
+          }
+          auto get = [&](int f, float (&o)[NL]) {
+            const float4* q = reinterpret_cast<const float4*>(smem + obase + (uint32_t)f * (32 * 32));
+            const float4 a = q[0];
+            float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (NL > 4) bq = q[1];
+            const float v[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
-          for (int f = 0; f < KC; f++)
-            if (f < ci.len)
-              own_frame<NL, true>(A, B, F, SF, r, coloff, boff, smem, f < KC - 1, (f + 1) * ROWB, O[f], c1, c2, gph, f * GSB);
+            for (int k = 0; k < NL; k++) o[k] = v[k];
+          };
+          __syncwarp();
+          float o[NL];
+          int f = 0;
+#pragma unroll 1
+          for (; f + 1 < ci.len; f += 2) {
+            get(f, o);
+            own_frame<NL, true>(A, B, F, SF, r, wc, wb, smem, true, ROWB, o, c1, c2, wg, 0);
+            get(f + 1, o);
+            own_frame<NL, true>(A, B, F, SF, r, wc, wb, smem, f + 2 < ci.len, 2 * ROWB, o, c1, c2, wg, GSB);
+#pragma unroll
+            for (int k = 0; k < NL; k++) {
+              wc[k] += 2 * ROWB;
+              wg[k] += 2 * GSB;
+            }
+            wb += 2 * ROWB;
+          }
+          if (f < ci.len) {
+            get(f, o);
+            own_frame<NL, true>(A, B, F, SF, r, wc, wb, smem, false, 0, o, c1, c2, wg, 0);
+          }
         }
         __syncwarp();
         if (lane == 0) flag_set(FLAG(FL_GFULL + d), j2 + 1);

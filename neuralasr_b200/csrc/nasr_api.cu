@@ -8,6 +8,8 @@
 #include <new>
 #include <thread>
 
+#include <dlfcn.h>
+
 #include "nasr_common.cuh"
 
 namespace nasr {
@@ -198,6 +200,31 @@ int nasr_debug_config(int path, int split_frames) {
   path &= 0xff;
   g_debug_path = path;
   g_debug_split = split_frames;
+  return NASR_OK;
+}
+
+int nasr_allreduce_scalars(void* nccl_comm, double* vec, int n, void* stream) {
+  NASR_CHECK_ARG(nccl_comm && vec && n > 0, "nasr_allreduce_scalars: bad arguments");
+  typedef int (*allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  static std::atomic<allreduce_fn> fn{nullptr};
+  allreduce_fn f = fn.load(std::memory_order_acquire);
+  if (!f) {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    f = h ? reinterpret_cast<allreduce_fn>(dlsym(h, "ncclAllReduce")) : nullptr;
+    if (!f) {
+      set_error("nasr_allreduce_scalars: NCCL (libnccl.so.2) is not available in this process");
+      return NASR_ERR_UNSUPPORTED;
+    }
+    fn.store(f, std::memory_order_release);
+  }
+  // ncclFloat64 = 8, ncclSum = 0 (nccl.h)
+  const int rc = f(vec, vec, (size_t)n, 8, 0, nccl_comm, static_cast<cudaStream_t>(stream));
+  if (rc != 0) {
+    set_error("nasr_allreduce_scalars: ncclAllReduce failed with code %d", rc);
+    return NASR_ERR_CUDA;
+  }
   return NASR_OK;
 }
 

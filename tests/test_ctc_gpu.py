@@ -614,3 +614,28 @@ def test_full_size_cfg4_whole_batch_against_oracle(common):
         g["logits"], g["label_values"], g["label_offsets"], g["seq_len"], precision="f64")
     loss, grad, status = _run_loss(common, g)
     _assert_loss_grad(loss, grad, status, want_loss, want_grad, want_status)
+
+
+def test_allreduce_scalars_through_the_c_abi(common, narrow_kernel):
+    """nasr_allreduce_scalars on a one-rank NCCL communicator (the call a non-torch caller makes for the tower means,
+    tfnetwork.py:135-136): the 4-vector comes back unchanged; NCCL is resolved from the process, not linked."""
+    if narrow_kernel != "f64":
+        pytest.skip("kernel-independent")
+    import ctypes
+    from neuralasr_b200 import _lib
+    try:
+        nccl = ctypes.CDLL("libnccl.so.2")
+    except OSError:
+        pytest.skip("libnccl.so.2 not loadable")
+    comm = ctypes.c_void_p()
+    devs = (ctypes.c_int * 1)(0)
+    assert nccl.ncclCommInitAll(ctypes.byref(comm), 1, devs) == 0
+    try:
+        v = torch.tensor([1.5, 2.5, 3.0, 4.0], dtype=torch.float64, device="cuda:0")
+        rc = _lib.load().nasr_allreduce_scalars(comm, ctypes.c_void_p(v.data_ptr()), 4,
+                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert v.cpu().tolist() == [1.5, 2.5, 3.0, 4.0]
+    finally:
+        nccl.ncclCommDestroy(comm)
