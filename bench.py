@@ -204,9 +204,7 @@ def run_ours(args, w, rank, world, local_rank):
         os.dup2(2, 1)
         # the one collective is 32 bytes: one channel (one CTA) is all it needs, and every further NCCL CTA is a CTA
         # slot the loss kernel of the next step does not get (NASR_NCCL_TUNE=0 leaves NCCL's defaults)
-        if os.environ.get("NASR_NCCL_TUNE", "1") != "0":
-            os.environ.setdefault("NCCL_MAX_NCHANNELS", "1")
-            os.environ.setdefault("NCCL_MIN_NCHANNELS", "1")
+        towers.tune_nccl_for_scalars()
         dist.init_process_group("nccl", device_id=dev)
     from neuralasr_b200 import _build
     if not os.path.exists(_build.LIB_PATH) and world == 1:

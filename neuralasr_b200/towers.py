@@ -20,6 +20,17 @@ import torch.distributed as dist
 from .utils import split_labels
 
 
+def tune_nccl_for_scalars():
+    """Call before the NCCL communicator is created: the path's one collective is 32 bytes, one channel (one CTA) is
+    all it needs, and every further NCCL CTA is a CTA slot the next step's loss kernel does not get (measured on
+    8 B200: 0.317 -> 0.314 ms per step at cfg3, 97 % of linear).  Respects values already in the environment;
+    ``NASR_NCCL_TUNE=0`` leaves NCCL's defaults."""
+    import os
+    if os.environ.get("NASR_NCCL_TUNE", "1") != "0":
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "1")
+        os.environ.setdefault("NCCL_MIN_NCHANNELS", "1")
+
+
 def shard_range(batch, rank, world):
     """Rows ``[lo, hi)`` of a global batch that tower ``rank`` owns (``tf.split`` semantics: equal blocks;
     the reference guarantees divisibility, ``config.py:35-36``)."""
