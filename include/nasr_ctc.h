@@ -172,6 +172,17 @@ int nasr_ctc_beam_search_strided_i64(const float* logits, int T, int B, int C, l
                                      int top_paths, int merge_repeated, int64_t* hyp, int32_t* hyp_len,
                                      float* log_prob, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Device-side label ingest: the COO triple sparse_tuple_from builds (reference utils.py:44-58: indices int64 [N,2]
+ * row-major with rows in order, values int32 [N]) -> the CSR the loss / edit-distance entries take, without touching
+ * the host.  Rows [row0, row0 + B) are taken and re-based: a tower's block under tf.sparse_split(axis=0)
+ * (tfnetwork.py:97-99) is a row window.  offsets int32 [B+1]; values_out int32 [>= entries of the window] or NULL
+ * (with row0 = 0 the input values ARE the CSR values); info int32 [3] on the device: [0] = 1 if the rows are not in
+ * order or a position is not the running index of its row (TF would reject the SparseTensor), [1] = longest row,
+ * [2] = first entry of the window.  max_label_len of the loss call can be the triple's dense_shape[1], known on the
+ * host without a sync. */
+int nasr_labels_coo_to_csr_i32(const int64_t* indices, const int32_t* values, int N, int row0, int B,
+                               int32_t* offsets, int32_t* values_out, int32_t* info, void* stream);
+
 /* Dense hypotheses -> the SparseTensor triple TF returns as decoded[0] (tfnetwork.py:64):
  * hyp_offsets int32[B+1] must hold the exclusive prefix sum of hyp_len (M = hyp_offsets[B]);
  * indices int64[M,2] row-major (b, position), values int64[M], dense_shape int64[2] = [B, max len]. */

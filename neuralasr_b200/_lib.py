@@ -22,6 +22,7 @@ SIGNATURES = {
     "nasr_debug_config": (_i, [_i, _i]),
     "nasr_debug_profile": (_i, [_vp]),
     "nasr_allreduce_scalars": (_i, [_vp, _vp, _i, _vp]),
+    "nasr_labels_coo_to_csr_i32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "nasr_ctc_workspace_bytes": (_i, [_i, _i, _i, _i, ctypes.POINTER(_sz)]),
     "nasr_ctc_loss_grad_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp,
                                     _sz, _vp]),

@@ -461,6 +461,82 @@ int edit_distance_csr(const int64_t* hyp_values, const int32_t* hyp_offsets, int
                                        max_truth_len, max_hyp_len, B, normalize, dist, ler, stream);
 }
 
+// ---- device-side label ingest: the COO triple of sparse_tuple_from (reference utils.py:44-58) -> CSR ------------
+// One block.  indices int64 [N,2] row-major (row, position), rows non-decreasing (tf.SparseTensor's canonical order,
+// which sparse_tuple_from produces).  Rows [row0, row0 + B) are taken -- tf.sparse_split(axis=0)'s block of a tower
+// (tfnetwork.py:97-99) is a row window -- and re-based to 0.  offsets[B+1] = prefix sum of the row lengths,
+// values_out[n - first] = values[n] for the window's entries, info[0] = 1 if the rows are not ordered or a position is
+// not the running index within its row, info[1] = longest row, info[2] = first entry of the window.
+__global__ void coo_to_csr_kernel(const int64_t* __restrict__ indices, const int32_t* __restrict__ values, int N,
+                                  int row0, int B, int32_t* __restrict__ offsets, int32_t* __restrict__ values_out,
+                                  int32_t* __restrict__ info) {
+  extern __shared__ int s_cnt[];   // [B + 1]
+  __shared__ int s_bad, s_max, s_first;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i <= B; i += nt) s_cnt[i] = 0;
+  if (tid == 0) {
+    s_bad = 0;
+    s_max = 0;
+    s_first = N;
+  }
+  __syncthreads();
+  for (int n = tid; n < N; n += nt) {
+    const long long r = indices[2 * n], c = indices[2 * n + 1];
+    if (n > 0) {
+      const long long rp = indices[2 * n - 2], cp = indices[2 * n - 1];
+      if (r < rp || (r == rp && c != cp + 1) || (r > rp && c != 0)) s_bad = 1;
+    } else if (c != 0) {
+      s_bad = 1;
+    }
+    if (r >= row0 && r < (long long)row0 + B) {
+      atomicAdd(&s_cnt[(int)(r - row0) + 1], 1);
+      atomicMin(&s_first, n);
+    }
+  }
+  __syncthreads();
+  // inclusive scan of the B row counts by one warp (B is a batch size: a few hundred)
+  if (tid < 32) {
+    int run = 0;
+    for (int base = 1; base <= B; base += 32) {
+      const int i = base + tid;
+      const int v = i <= B ? s_cnt[i] : 0;
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (tid >= o) inc += t;
+      }
+      if (i <= B) {
+        s_cnt[i] = run + inc;
+        atomicMax(&s_max, v);
+      }
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i <= B; i += nt) offsets[i] = s_cnt[i];
+  const int first = s_first == N ? 0 : s_first, total = s_cnt[B];
+  if (values_out)
+    for (int n = tid; n < total; n += nt) values_out[n] = values[first + n];
+  if (tid == 0) {
+    info[0] = s_bad;
+    info[1] = s_max;
+    info[2] = first;
+  }
+}
+
+int labels_coo_to_csr(const int64_t* indices, const int32_t* values, int N, int row0, int B, int32_t* offsets,
+                      int32_t* values_out, int32_t* info, cudaStream_t stream) {
+  NASR_CHECK_ARG(N >= 0 && B >= 0 && row0 >= 0 && offsets && info && (N == 0 || indices),
+                 "nasr_labels_coo_to_csr: bad arguments");
+  NASR_CHECK_ARG((size_t)(B + 1) * 4 <= 160 * 1024, "nasr_labels_coo_to_csr: batch %d too large", B);
+  NASR_CUDA(cudaFuncSetAttribute(coo_to_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  coo_to_csr_kernel<<<1, 1024, (size_t)(B + 1) * 4, stream>>>(indices, values, N, row0, B, offsets, values_out, info);
+  count_launch();
+  NASR_CUDA(cudaGetLastError());
+  return NASR_OK;
+}
+
 int hyp_to_sparse(const int64_t* hyp, int hyp_stride, const int32_t* hyp_offsets, int B,
                   int64_t* indices, int64_t* values, int64_t* dense_shape, cudaStream_t stream) {
   NASR_CHECK_ARG(B >= 0, "nasr_hyp_to_sparse: bad B");

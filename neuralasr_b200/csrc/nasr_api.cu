@@ -39,6 +39,8 @@ int edit_distance_dense(const int64_t* hyp, int hyp_stride, const int32_t* hyp_l
 int edit_distance_csr(const int64_t* hyp_values, const int32_t* hyp_offsets, int max_hyp_len,
                       const int32_t* truth_values, const int32_t* truth_offsets, int max_truth_len,
                       int B, int normalize, int32_t* dist, float* ler, cudaStream_t stream);
+int labels_coo_to_csr(const int64_t* indices, const int32_t* values, int N, int row0, int B, int32_t* offsets,
+                      int32_t* values_out, int32_t* info, cudaStream_t stream);
 int hyp_to_sparse(const int64_t* hyp, int hyp_stride, const int32_t* hyp_offsets, int B,
                   int64_t* indices, int64_t* values, int64_t* dense_shape, cudaStream_t stream);
 int batch_sums(const float* loss, const float* ler, const int32_t* dist, int B, double* sums,
@@ -342,6 +344,11 @@ int nasr_ctc_beam_search_strided_i64(const float* logits, int T, int B, int C, l
   return ctc_beam_search(logits, T, B, C, stride_t, stride_b, seq_len, blank, beam_width, top_paths,
                          merge_repeated, hyp, hyp_len, log_prob, workspace, workspace_bytes,
                          static_cast<cudaStream_t>(stream));
+}
+
+int nasr_labels_coo_to_csr_i32(const int64_t* indices, const int32_t* values, int N, int row0, int B,
+                               int32_t* offsets, int32_t* values_out, int32_t* info, void* stream) {
+  return labels_coo_to_csr(indices, values, N, row0, B, offsets, values_out, info, static_cast<cudaStream_t>(stream));
 }
 
 int nasr_hyp_to_sparse_i64(const int64_t* hyp, int hyp_stride, const int32_t* hyp_offsets, int B,

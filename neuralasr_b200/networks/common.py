@@ -55,10 +55,44 @@ def prepare_labels(labels, device):
     if hasattr(labels, "indices") and hasattr(labels, "values") and hasattr(labels, "dense_shape"):
         labels = (labels.indices, labels.values, labels.dense_shape)     # SparseTensorValue-like
     indices, values, shape = labels
+    if isinstance(indices, torch.Tensor) and indices.is_cuda and isinstance(values, torch.Tensor) and values.is_cuda:
+        return prepare_labels_device(indices, values, shape)
     vals, offs, max_len = sparse_to_csr((_to_numpy(indices), _to_numpy(values), _to_numpy(shape)))
     dvals = torch.from_numpy(vals if vals.size else np.zeros(1, np.int32)).to(device, non_blocking=True)
     doffs = torch.from_numpy(offs).to(device, non_blocking=True)
     return LabelsCSR(dvals, doffs, max_len, offs.size - 1, vals, offs)
+
+
+def prepare_labels_device(indices, values, shape, row0=0, rows=None, check=False):
+    """A label triple that already lives on the GPU -> :class:`LabelsCSR` without touching the host
+    (``nasr_labels_coo_to_csr_i32``): ``indices`` int64 ``[N,2]`` and ``values`` int32 ``[N]`` CUDA tensors in
+    ``sparse_tuple_from``'s order (reference ``utils.py:44-58``), ``shape`` the host pair ``[B, max_len]``.
+    ``row0`` / ``rows`` take a tower's block of rows, re-based (``tf.sparse_split(axis=0)``,
+    ``tfnetwork.py:97-99``).  ``check=True`` reads the order flag back (one sync) and raises like TF would."""
+    lib = _lib.load()
+    dev = indices.device
+    shape = [int(v) for v in (shape.tolist() if hasattr(shape, "tolist") else shape)]
+    B = shape[0] - int(row0) if rows is None else int(rows)
+    N = int(values.numel())
+    if indices.dtype != torch.int64 or tuple(indices.shape) != (N, 2):
+        raise ValueError("indices must be int64 [N, 2]")
+    indices = indices.contiguous()
+    values = values.to(torch.int32).contiguous()
+    offs = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    info = torch.empty(3, dtype=torch.int32, device=dev)
+    out = values if int(row0) == 0 and B == shape[0] else torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nasr_labels_coo_to_csr_i32(_ptr(indices), _ptr(values), N, int(row0), B, _ptr(offs),
+                                                  None if out is values else _ptr(out), _ptr(info),
+                                                  _stream_ptr(dev)), "nasr_labels_coo_to_csr")
+    if check and int(info[0].item()):
+        raise ValueError("labels: indices are not in row-major order (tf.SparseTensor canonical ordering)")
+    if N == 0:
+        out = torch.zeros(1, dtype=torch.int32, device=dev)
+    lab = LabelsCSR(out, offs, shape[1], B)
+    lab_info = info
+    lab.host_values = lab_info       # (kept alive; the host copies do not exist on this path)
+    return lab
 
 
 def _check_logits(logits):
@@ -456,8 +490,11 @@ def label_error_rate(model, labels):
     return mean
 
 
-# reference-era aliases (the snapshot's method names, networks/tfnetwork.py:58,61,66)
+# reference-era aliases (the snapshot's method names, networks/tfnetwork.py:58,61,66).  ``create_model`` is what the
+# snapshot's method of that name runs -- the beam search decoder, width 100, returning (decoded[0], log_prob)
+# (tfnetwork.py:62,64); ``decoding`` / ``model`` keep the README-era name for the greedy decoder the north star asks for
+# (the commented alternative on tfnetwork.py:63).
 create_loss = loss
-create_model = decoding
+create_model = create_model_beam
 create_metric = label_error_rate
 model = decoding

@@ -639,3 +639,53 @@ def test_allreduce_scalars_through_the_c_abi(common, narrow_kernel):
         assert v.cpu().tolist() == [1.5, 2.5, 3.0, 4.0]
     finally:
         nccl.ncclCommDestroy(comm)
+
+
+def test_device_side_label_ingest(common, narrow_kernel):
+    """COO triple on the GPU -> CSR on the GPU: same offsets / values / longest row as the host
+    conversion, a tower's row window re-based like tf.sparse_split, disorder flagged; and the loss takes it."""
+    if narrow_kernel != "f64":
+        pytest.skip("kernel-independent")
+    import ctypes
+    from neuralasr_b200 import _lib
+    from neuralasr_b200.utils import sparse_to_csr, sparse_tuple_from, split_labels
+    rng = np.random.default_rng(5)
+    B, Lmax = 12, 9
+    lens = rng.integers(0, Lmax + 1, size=B)
+    lens[3] = 0
+    lens[7] = Lmax
+    dense = rng.integers(0, 30, size=(B, Lmax))
+    idx, vals, shape = sparse_tuple_from(dense, lens)
+    want_vals, want_offs, want_max = sparse_to_csr((idx, vals, shape))
+    di, dv = torch.from_numpy(idx).cuda(), torch.from_numpy(vals.astype(np.int32)).cuda()
+    lab = common.prepare_labels((di, dv, shape), torch.device("cuda", 0))
+    torch.cuda.synchronize()
+    assert np.array_equal(lab.offsets.cpu().numpy(), want_offs)
+    assert np.array_equal(lab.values.cpu().numpy()[: want_vals.size], want_vals)
+    info = lab.host_values.cpu().numpy()
+    assert info[0] == 0 and info[1] == want_max == Lmax
+    # a tower's block: rows [4, 8) of the same triple
+    part = split_labels((idx, vals, shape), 3)[1]
+    pv, po, _ = sparse_to_csr(part)
+    lab2 = common.prepare_labels_device(di, dv, shape, row0=4, rows=4)
+    torch.cuda.synchronize()
+    assert np.array_equal(lab2.offsets.cpu().numpy(), po)
+    assert np.array_equal(lab2.values.cpu().numpy()[: pv.size], pv)
+    # rows out of order are flagged
+    bad = idx.copy()
+    bad[[0, -1]] = bad[[-1, 0]]
+    with pytest.raises(ValueError):
+        common.prepare_labels_device(torch.from_numpy(bad).cuda(), dv, shape, check=True)
+    # and the loss accepts the device-resident triple
+    g = make_batch(77, T=64, B=B, C=38, Lmax=Lmax, mode="full", empty_row=False)
+    offs = g["label_offsets"]
+    l2 = np.diff(offs)
+    d2 = np.zeros((B, max(int(l2.max()), 1)), np.int32)
+    for b in range(B):
+        d2[b, : l2[b]] = g["label_values"][offs[b]:offs[b + 1]]
+    i3, v3, s3 = sparse_tuple_from(d2, l2)
+    x = torch.from_numpy(g["logits"]).cuda()
+    loss_d, grad_d, _ = common.ctc_loss_and_grad(x, (torch.from_numpy(i3).cuda(), torch.from_numpy(v3.astype(np.int32)).cuda(), s3), g["seq_len"])
+    loss_h, grad_h, _ = common.ctc_loss_and_grad(x, (i3, v3, s3), g["seq_len"])
+    torch.cuda.synchronize()
+    assert torch.equal(loss_d, loss_h) and torch.equal(grad_d, grad_h)
