@@ -785,7 +785,27 @@ ctc_fast_kernel(const Params p) {
   const int perm = WIDE ? 0 : (s_scal[3] & 1);
   // wide: warps 0-3 recursion / recompute, 4-7 gradient (4,5 frames 0-3 of a chunk, 6,7 frames 4-7),
   // 8-15 producers; side = parity of the warp index
-  const int role = WIDE ? (warp < 4 ? warp : (warp < 8 ? G_F + (warp & 1) : P_F + (warp & 1))) : (warp ^ (perm << 1));
+  int role = WIDE ? (warp < 4 ? warp : (warp < 8 ? G_F + (warp & 1) : P_F + (warp & 1))) : (warp ^ (perm << 1));
+  if (!WIDE) {
+    // A warp issues from scheduler (hardware warp slot mod 4), and the slots of an SM's second CTA need not start at
+    // a multiple of four (measured with four-warp CTAs: 5, 6, 7, 4).  Deal the roles by the scheduler actually got:
+    // the first warp of the CTA on a scheduler takes recursion / recompute, the second producer / gradient, the second
+    // CTA the other way round, so that every scheduler of the SM carries one warp of each kind.
+    __shared__ int s_hw[8];
+    unsigned hwid;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(hwid));
+    hwid = __shfl_sync(0xffffffffu, hwid, 0);
+    if (lane == 0) s_hw[warp] = (int)(hwid & 3u);
+    __syncthreads();
+    int cnt = 0, mine = 0;   // four 4-bit counters: warps of this CTA per scheduler
+#pragma unroll
+    for (int v = 0; v < 8; v++) {
+      const int q = s_hw[v];
+      if (v == warp) mine = (cnt >> (4 * q)) & 15;
+      cnt += 1 << (4 * q);
+    }
+    if (cnt == 0x2222) role = ((int)(hwid & 3u) ^ (perm << 1)) + 4 * mine;
+  }
   const int d = role & 1;  // direction / side this warp works for
   __syncthreads();
 
