@@ -1329,7 +1329,7 @@ int ctc_narrow_launch(const float* logits, int T, int B, int C, long long st_t, 
                       void* ckpt, cudaStream_t stream);
 // Which kernel takes narrow vocabularies (C <= 64): the fp64 kernel of this file by default; the float32 kernel of
 // ctc_narrow.cu where NASR_NARROW_F32=1 is set in the environment (read at every call, so tests can switch).  Measured on
-// B200 (profiles/r2_*): 0.282 ms against 0.298 ms at cfg3, 0.137 against 0.154 at cfg2, 0.089 against 0.095 at cfg1.
+// B200 (profiles/r2_*): 0.256 ms against 0.298 ms at cfg3, 0.137 against 0.143 at cfg2, 0.089 against 0.095 at cfg1.
 static bool use_narrow_f32() {
   const char* e = getenv("NASR_NARROW_F32");
   return e && e[0] == '1';
