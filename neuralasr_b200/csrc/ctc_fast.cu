@@ -804,6 +804,7 @@ ctc_fast_kernel(const Params p) {
       if (v == warp) mine = (cnt >> (4 * q)) & 15;
       cnt += 1 << (4 * q);
     }
+    // (which of a scheduler's two warps takes the heavy role makes no difference: measured 0.2546 / 0.2536 ms)
     if (cnt == 0x2222) role = ((int)(hwid & 3u) ^ (perm << 1)) + 4 * mine;
   }
   const int d = role & 1;  // direction / side this warp works for

@@ -8,6 +8,9 @@ sys.path.insert(0, ".")
 import bench  # noqa: E402
 from neuralasr_b200.networks import common  # noqa: E402
 
+import os
+if os.environ.get('NASR_DBG'):
+    common.debug_config(int(os.environ['NASR_DBG'], 0), 0)
 w = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cfg3"]
 T, B, C = w["T"], w["B"], w["C"]
 x, vals, offs, seq = bench.synth(w, 1234)
