@@ -403,8 +403,7 @@ int launch_edit_distance(const HypT* hyp, long hyp_stride, const int32_t* hyp_le
               max_hyp_len);
     return NASR_ERR_UNSUPPORTED;
   }
-  // (set at every launch: the attribute is per device, and a process may drive several; the call is cheap)
-  NASR_CUDA(cudaFuncSetAttribute(edit_distance_kernel<HypT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  NASR_CUDA((ensure_max_dynamic_smem<edit_distance_kernel<HypT>>(200 * 1024)));
   edit_distance_kernel<HypT><<<B, 32, smem, stream>>>(hyp, hyp_stride, hyp_len, hyp_offsets,
                                                      truth_values, truth_offsets, max_truth_len,
                                                      max_hyp_len, (int)(table / 4), normalize, dist, ler);
@@ -530,7 +529,7 @@ int labels_coo_to_csr(const int64_t* indices, const int32_t* values, int N, int 
   NASR_CHECK_ARG(N >= 0 && B >= 0 && row0 >= 0 && offsets && info && (N == 0 || indices),
                  "nasr_labels_coo_to_csr: bad arguments");
   NASR_CHECK_ARG((size_t)(B + 1) * 4 <= 160 * 1024, "nasr_labels_coo_to_csr: batch %d too large", B);
-  NASR_CUDA(cudaFuncSetAttribute(coo_to_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  NASR_CUDA((ensure_max_dynamic_smem<coo_to_csr_kernel>(160 * 1024)));
   coo_to_csr_kernel<<<1, 1024, (size_t)(B + 1) * 4, stream>>>(indices, values, N, row0, B, offsets, values_out, info);
   count_launch();
   NASR_CUDA(cudaGetLastError());

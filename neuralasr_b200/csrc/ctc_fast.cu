@@ -1299,9 +1299,7 @@ int pick_nl_wide(int Lmax) {
 template <int NL, int EPL, bool STREAM = false>
 int launch_fast(const fast::Params& p, cudaStream_t stream) {
   const fast::Smem sl = fast::smem_layout(NL, 8 * EPL, EPL ? 0 : p.C, STREAM);
-  // (set at every launch: the attribute is per device, and a process may drive several; the call is cheap)
-  NASR_CUDA(cudaFuncSetAttribute(fast::ctc_fast_kernel<NL, EPL, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kMaxSmem));
+  NASR_CUDA((ensure_max_dynamic_smem<fast::ctc_fast_kernel<NL, EPL, STREAM>>(kMaxSmem)));
   if (sl.total > (size_t)kMaxSmem) {
     set_error("nasr_ctc: fast kernel shared memory %zu too large", sl.total);
     return NASR_ERR_UNSUPPORTED;

@@ -552,8 +552,7 @@ int ctc_loss_grad(const float* logits, int T, int B, int C, long long st_t, long
   p.ckpt = reinterpret_cast<double*>(base + pl.ws_scale);  // ws_scale is a multiple of 16
   p.K = pl.K; p.nseg = pl.nseg; p.Upad = pl.Upad; p.Cpad = pl.Cpad;
   p.only_if = use_fast ? retry : nullptr;
-  // (set at every launch: the attribute is per device, and a process may drive several; the call is cheap)
-  NASR_CUDA(cudaFuncSetAttribute(ctc_robust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+  NASR_CUDA((ensure_max_dynamic_smem<ctc_robust_kernel>((int)kSmemBudget)));
   ctc_robust_kernel<<<B, pl.threads, pl.smem, stream>>>(p);
   count_launch();
   NASR_CUDA(cudaGetLastError());

@@ -48,6 +48,20 @@ inline cudaError_t device_sm_count(int* out) {
   return cudaSuccess;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: set it once per (kernel, device).  (Setting it at every
+// launch costs ~0.2 ms of host time per call -- measured: it made nasr_edit_distance host-bound.)
+template <auto Kernel>
+inline cudaError_t ensure_max_dynamic_smem(int bytes) {
+  static std::atomic<int> done[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && done[dev].load(std::memory_order_acquire) >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev].store(bytes, std::memory_order_release);
+  return e;
+}
+
 constexpr int kWarp = 32;
 
 __device__ __forceinline__ float warp_max(float v) {
