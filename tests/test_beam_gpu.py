@@ -385,3 +385,23 @@ def test_zero_frames():
     dec, lp = common.beam_decoding(x, np.zeros(3, np.int32), beam_width=8, top_paths=2)
     assert dec[0].hyp_len.cpu().tolist() == [0, 0, 0] and dec[1].hyp_len.cpu().tolist() == [0, 0, 0]
     assert lp[:, 0].cpu().tolist() == [0.0, 0.0, 0.0] and torch.isinf(lp[:, 1]).all()
+
+
+def test_tf_published_beam_search_case_through_the_c_abi():
+    """TensorFlow's own ctc_decoder_ops_test.py beam search case (tests/golden/tf_ctc_decoder_ops_test_beam.json):
+    the kernel, through the C-ABI, returns the published hypotheses [1, 0] and [1] with log probabilities -5.811451
+    and -6.63339 (float32 tolerance 5e-6); the two padding frames beyond seq_len are ignored as TF ignores them."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "tf_ctc_decoder_ops_test_beam.json")) as f:
+        g = json.load(f)
+    p = np.asarray(g["input_prob_matrix"], np.float32) + np.float32(g["offset"])
+    x = np.ascontiguousarray(np.concatenate([p, np.zeros((g["padding_frames"], p.shape[1]), np.float32)])[:, None, :])
+    # a batch of three copies: the case must not depend on the batch position
+    x = np.ascontiguousarray(np.repeat(x, 3, axis=1))
+    got, lp = _run(x, np.full(3, g["seq_len"], np.int32), W=g["beam_width"], P=g["top_paths"],
+                   merge=g["merge_repeated"])
+    for b in range(3):
+        for j, (lab, v) in enumerate(zip(g["decoded"], g["log_prob"])):
+            assert got[j][b] == lab, (b, j, got[j][b])
+            assert abs(lp[b, j] - v) < 5e-6, (b, j, lp[b, j])

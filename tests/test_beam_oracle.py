@@ -1,5 +1,7 @@
 """The beam-search oracle against brute force: with a beam wider than the number of prefixes the search is
 exhaustive, so it must return the exact most probable labelling and its exact log probability."""
+import os
+
 import numpy as np
 import pytest
 
@@ -88,3 +90,26 @@ def test_both_oracles_reproduce_the_golden_fixture():
         for j, (lab, v) in enumerate(want):
             assert got[j][0] == lab and abs(got[j][1] - v) < 1e-9
             assert hyp[0, j, : hl[0, j]].tolist() == lab and abs(lp[0, j] - v) < 1e-9
+
+
+def _tf_published_beam_case():
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "tf_ctc_decoder_ops_test_beam.json")) as f:
+        g = json.load(f)
+    p = np.asarray(g["input_prob_matrix"], np.float32) + np.float32(g["offset"])
+    x = np.concatenate([p, np.zeros((g["padding_frames"], p.shape[1]), np.float32)])[:, None, :]
+    return g, np.ascontiguousarray(x)
+
+
+def test_tf_published_beam_search_case():
+    """TensorFlow's own ctc_decoder_ops_test.py beam search case (tests/golden/tf_ctc_decoder_ops_test_beam.json):
+    both oracles return the published hypotheses and their log probabilities to the printed digits."""
+    from oracle import c_oracle
+    g, x = _tf_published_beam_case()
+    T = g["seq_len"]
+    got = bo.beam_search_one(x[:T, 0, :], g["beam_width"], g["merge_repeated"], blank=g["blank"],
+                             top_paths=g["top_paths"])
+    hyp, hl, lp = c_oracle.beam_search(x, [T], g["beam_width"], g["top_paths"], g["merge_repeated"], blank=g["blank"])
+    for j, (lab, v) in enumerate(zip(g["decoded"], g["log_prob"])):
+        assert got[j][0] == lab and abs(got[j][1] - v) < 5e-6, (j, got[j])
+        assert hyp[0, j, : hl[0, j]].tolist() == lab and abs(lp[0, j] - v) < 5e-6, (j, lp[0, j])

@@ -689,3 +689,15 @@ def test_device_side_label_ingest(common, narrow_kernel):
     loss_h, grad_h, _ = common.ctc_loss_and_grad(x, (i3, v3, s3), g["seq_len"])
     torch.cuda.synchronize()
     assert torch.equal(loss_d, loss_h) and torch.equal(grad_d, grad_h)
+
+
+def test_tf_published_greedy_decoder_case_through_the_c_abi(common):
+    """TensorFlow's own ctc_decoder_ops_test.py greedy case (tests/golden/tf_ctc_decoder_ops_test_greedy.json) through
+    the C-ABI: the published SparseTensor triple and log probabilities, -inf logits included."""
+    from test_oracle import tf_greedy_case
+    g, x = tf_greedy_case()
+    dec, nsl = common.decoding(torch.from_numpy(x).cuda(), g["seq_len"])
+    idx, vals, shape = dec
+    assert vals.tolist() == g["values"] and idx.tolist() == g["indices"] and shape.tolist() == g["dense_shape"]
+    want_lp = np.array([np.sum(-np.log(np.asarray(p, np.float32))) for p in g["max_probs"]], np.float32)
+    assert np.allclose(nsl[:, 0].cpu().numpy(), want_lp, rtol=1e-6)

@@ -215,3 +215,42 @@ def test_tf_published_ctc_loss_basic_case():
         assert cst[0] == 0 and abs(closs[0] - case["loss"]) < 5e-6
         for t, c, g in case["grad_entries"]:
             assert abs(cgrad[t, 0, c] - g) < 2e-6
+
+
+def tf_greedy_case():
+    """-> (fixture, logits float32 [6, 2, 4]) of TensorFlow's published greedy decoder test."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "tf_ctc_decoder_ops_test_greedy.json")) as f:
+        g = json.load(f)
+    with np.errstate(divide="ignore"):
+        x = np.log(np.stack([np.asarray(g["input_prob_matrix_0"], np.float32),
+                             np.asarray(g["input_prob_matrix_1"], np.float32)], axis=1))
+    return g, np.ascontiguousarray(x.astype(np.float32))
+
+
+def test_tf_published_greedy_decoder_case():
+    """TensorFlow's own ctc_decoder_ops_test.py greedy case (tests/golden/tf_ctc_decoder_ops_test_greedy.json): both
+    oracles return the published SparseTensor and log probabilities (-inf logits included)."""
+    g, x = tf_greedy_case()
+    want_lp = np.array([np.sum(-np.log(np.asarray(p, np.float32))) for p in g["max_probs"]], np.float32)
+    for dec in (o.greedy_decode, c_oracle.greedy_decode):
+        vals, offs, nsl = dec(x, np.asarray(g["seq_len"], np.int32))
+        assert vals.tolist() == g["values"]
+        idx, _, shape = o.csr_to_sparse(vals, offs)
+        assert np.asarray(idx).tolist() == g["indices"] and np.asarray(shape).tolist() == g["dense_shape"]
+        assert offs.tolist() == [0, 2, 5]
+        assert np.allclose(nsl, want_lp, rtol=1e-6)
+
+
+def test_tf_documented_edit_distance_example():
+    """The example in tf.edit_distance's own docstring (normalize=True): hypothesis (0,0)=[a], (1,0)=[b]; truth
+    (0,1)=[a], (1,0)=[b,c], (1,1)=[a] -> [[inf, 1.0], [0.5, 1.0]].  The rank-3 tensor flattened to four utterances
+    (a, b, c = 0, 1, 2); numpy and C oracle."""
+    hyp_vals, hyp_offs = np.array([0, 1], np.int64), np.array([0, 1, 1, 2, 2], np.int32)
+    tr_vals, tr_offs = np.array([0, 1, 2, 0], np.int32), np.array([0, 0, 1, 3, 4], np.int32)
+    for ed in (o.edit_distance, c_oracle.edit_distance):
+        d, ler = ed(hyp_vals, hyp_offs, tr_vals, tr_offs)
+        assert np.asarray(d).tolist() == [1, 1, 1, 1]
+        ler = np.asarray(ler, np.float64)
+        assert np.isinf(ler[0]) and ler[1] == 1.0 and ler[2] == 0.5 and ler[3] == 1.0
