@@ -257,6 +257,32 @@ int nasr_host_ctc_step(nasr_host_ctx* ctx, const float* logits, int T, int B, in
                        int64_t* hyp /*[B,T]*/, int32_t* hyp_len, float* neg_sum_logits,
                        int32_t* dist, float* ler);
 
+/* ------------------------------------------------------------------------------------------------
+ * The model tails' affine projection.  Replaces
+ *     outputs = tf.reshape(outputs, [-1, num_hidden]); logits = tf.matmul(outputs, W) + b
+ * of networks/bilstm_ctc_net.py:33-45 and lstm_ctc_net.py:28-40 (num_hidden = 500, W [K, C], b [C]) and, for
+ * training, the three gradients TensorFlow derives from it.  float32 in and out; the products run on the tensor
+ * cores as 3xTF32 (hi*hi + hi*lo + lo*hi, float32 accumulation), i.e. within float32 rounding of a float32 matmul.
+ *   H       float32 [rows, K], row r at H + r*ldh   (rows = B*T in the callers' batch-major order)
+ *   logits  float32 [rows, C], row r at logits + r*ldl; viewed as [B, T, C] it is the tensor the reference then
+ *           transposes -- nasr_ctc_loss_grad_strided_f32 (stride_t = C, stride_b = T*C) reads it in place.
+ * bias may be NULL.  Not fused into the CTC kernel on purpose: H is 13 times the logits in bytes and the loss reads
+ * every frame twice, so a fused producer would move more bytes than writing the logits once.
+ * ---------------------------------------------------------------------------------------------- */
+int nasr_affine_logits_f32(const float* H, long long rows, int K, long long ldh, const float* W,
+                           const float* bias, int C, float* logits, long long ldl, void* stream);
+
+/* Bytes of device workspace nasr_affine_backward_f32 needs for dW / db (per-CTA partial sums, added in a fixed
+ * order: the result does not depend on scheduling). */
+int nasr_affine_workspace_bytes(long long rows, int K, int C, size_t* out_bytes);
+
+/* dH[r, k] = sum_c dlogits[r, c] * W[k, c];  dW[k, c] = sum_r H[r, k] * dlogits[r, c];  db[c] = sum_r dlogits[r, c].
+ * Each of dH, dW, db may be NULL to skip it (H may be NULL when only dH is wanted, the workspace when neither dW
+ * nor db is). */
+int nasr_affine_backward_f32(const float* H, long long rows, int K, long long ldh, const float* W, int C,
+                             const float* dlogits, long long ldd, float* dH, long long lddh, float* dW,
+                             float* db, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Number of kernel launches this library has enqueued since load (for bench.py's gpu_launches). */
 uint64_t nasr_launch_count(void);
 

@@ -40,6 +40,11 @@ SIGNATURES = {
     "nasr_edit_distance_i64": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "nasr_edit_distance_csr_i64": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "nasr_batch_sums_f64": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "nasr_affine_logits_f32": (_i, [_vp, ctypes.c_longlong, _i, ctypes.c_longlong, _vp, _vp, _i, _vp,
+                                    ctypes.c_longlong, _vp]),
+    "nasr_affine_workspace_bytes": (_i, [ctypes.c_longlong, _i, _i, ctypes.POINTER(_sz)]),
+    "nasr_affine_backward_f32": (_i, [_vp, ctypes.c_longlong, _i, ctypes.c_longlong, _vp, _i, _vp, ctypes.c_longlong,
+                                      _vp, ctypes.c_longlong, _vp, _vp, _vp, _sz, _vp]),
     "nasr_host_ctx_create": (_i, [_i, _i, _i, _i, _i, ctypes.POINTER(_vp)]),
     "nasr_host_ctx_destroy": (None, [_vp]),
     "nasr_host_ctx_set_decoder": (_i, [_vp, _i, _i]),

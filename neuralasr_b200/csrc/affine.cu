@@ -1,0 +1,551 @@
+// The model tails' affine projection and its backward: logits = H.W + b on the reshaped recurrent
+// outputs H [rows, K] (reference networks/bilstm_ctc_net.py:33-45, lstm_ctc_net.py:28-40: K = num_hidden = 500,
+// W [K, C] Xavier, b [C] zero; rows = B*T, or 2*B*T for the BiLSTM tail, whose reshape stacks both directions).
+//
+// Why its own kernels instead of a producer fused into the CTC kernel: H is 13 times the logits in bytes and the
+// loss reads every frame in two phases half a recursion apart, so a fused producer would read H twice.
+// Here H is read ONCE, the logits are written once (39 MB at cfg3: they stay in the 126 MB L2 for the loss kernel
+// that follows on the same stream), and the roofline is HBM: 4*(rows*K + rows*C) bytes per call.
+//
+// Arithmetic: float32 in, float32 out, on the tensor cores as 3xTF32 -- every operand is split into a TF32 high
+// part and a TF32 low part, and hi*hi + hi*lo + lo*hi is accumulated in float32 (mma.sync.m16n8k8; the dropped
+// lo*lo term is 2^-22 relative), which keeps the result within float32 rounding of tf.matmul's float32 product.
+// A single-pass TF32 product (10-bit mantissa) would put ~1e-3 absolute error on the logits and break the 1e-4
+// gradient tolerance of the path; tcgen05 has no float32-accurate mode and its operands come from shared memory, so
+// the split would need a conversion pass through registers anyway, for a kernel that is bound by reading H from HBM.
+//
+// Kernels:
+//   affine_rows_kernel   out[r, n] (+)= sum_k A[r, k] * Wt[n, k] (+ bias[n]);  Wt (<= 40 columns x <= 672 k, hi and lo
+//                        parts) lives in shared memory for the whole CTA, each warp walks its own contiguous range of
+//                        rows and reads A straight from global memory into mma fragments (16-byte loads along k: the
+//                        k order inside a tile is permuted identically for A and Wt, so no transposition is needed).
+//                        Forward: A = H, Wt = W^T.  Backward dH = dL.W^T: A = dL, Wt = W itself, 13 column blocks.
+//   affine_dw_kernel     dW[k, c] = sum_r H[r, k] * dL[r, c], db[c] = sum_r dL[r, c]: each CTA streams its range of
+//                        rows through a three-stage cp.async ring (32 rows of H and dL per stage), every warp owns 32
+//                        of the 512 k of a block as accumulators; per-CTA partials go to the workspace and
+//                        affine_reduce_kernel adds them in a fixed order (deterministic, no atomics).
+#include "nasr_common.cuh"
+
+namespace nasr {
+namespace affine {
+
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr int kNT = 5;            // n8 tiles of a column block
+constexpr int kNB = 8 * kNT;      // 40 output columns per CTA
+constexpr int kMaxSeg = 672;      // longest contraction segment whose Wt (hi + lo) fits shared memory
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// hi*hi + hi*lo + lo*hi, small terms first
+__device__ __forceinline__ void mma_3x(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                       uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+  mma_tf32(d, al[0], al[1], al[2], al[3], bh0, bh1);
+  mma_tf32(d, ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+  mma_tf32(d, ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+}
+
+struct RowsParams {
+  const float* A;        // [rows, Kc] at stride lda
+  long long lda;
+  long long rows;
+  int Kc;                // contraction length of this call (<= kMaxSeg)
+  const float* W;        // element (n, k) of Wt at W[n * w_sn + k * w_sk]
+  long long w_sn, w_sk;
+  int N;                 // output columns
+  const float* bias;     // [N] or NULL
+  float* out;            // [rows, N] at stride ldo
+  long long ldo;
+  int accumulate;        // out += instead of out =
+  int kstride;           // floats per staged Wt row: round_up(Kc, 32) + 16 (16-byte loads of 8 rows hit 32 banks once)
+  int vec_a;             // rows of A start 16-byte aligned
+  int vec_o;             // rows of out start 8-byte aligned
+};
+
+__device__ __forceinline__ float4 load_a(const float* row, bool ok, int k, int Kc, int vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ok) {
+    if (vec && k + 3 < Kc) {
+      v = __ldg(reinterpret_cast<const float4*>(row + k));
+    } else {
+      if (k < Kc) v.x = __ldg(row + k);
+      if (k + 1 < Kc) v.y = __ldg(row + k + 1);
+      if (k + 2 < Kc) v.z = __ldg(row + k + 2);
+      if (k + 3 < Kc) v.w = __ldg(row + k + 3);
+    }
+  }
+  return v;
+}
+
+// One warp, MT m16 tiles of rows starting at r0 (rows >= r_end are masked), all kNT column tiles of the CTA's block.
+// Lane (g = lane / 4, t = lane % 4) loads A[row g + 8i][16*ch + 4t .. +3]; the four values are the k slots
+// (t, t+4) of two m16n8k8 products, and Wt is read with the same permutation, so the sum over k is unchanged.
+template <int MT>
+__device__ __forceinline__ void rows_tile(const RowsParams& p, const uint32_t* __restrict__ Wh,
+                                          const uint32_t* __restrict__ Wl, long long r0, long long r_end,
+                                          int n_base, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  float acc[MT][kNT][4];
+#pragma unroll
+  for (int m = 0; m < MT; m++)
+#pragma unroll
+    for (int j = 0; j < kNT; j++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) acc[m][j][e] = 0.f;
+  const float* arow[2 * MT];
+  bool ok[2 * MT];
+#pragma unroll
+  for (int i = 0; i < 2 * MT; i++) {
+    const long long r = r0 + g + 8 * i;
+    ok[i] = r < r_end;
+    arow[i] = p.A + (ok[i] ? r : r0) * p.lda;
+  }
+  const int nch = (p.Kc + 15) >> 4;
+  float4 cur[2 * MT], nxt[2 * MT];
+#pragma unroll
+  for (int i = 0; i < 2 * MT; i++) {
+    cur[i] = load_a(arow[i], ok[i], 4 * t, p.Kc, p.vec_a);
+    nxt[i] = cur[i];
+  }
+  for (int ch = 0; ch < nch; ch++) {
+    if (ch + 1 < nch) {
+#pragma unroll
+      for (int i = 0; i < 2 * MT; i++) nxt[i] = load_a(arow[i], ok[i], (ch + 1) * 16 + 4 * t, p.Kc, p.vec_a);
+    }
+    // the rows' bytes four chunks ahead go to L2 now: the register prefetch above then waits an L2 hit, not DRAM
+    if (t == 0) {
+      const int kpf = (ch + 5) * 16;
+      if (kpf < p.Kc) {
+#pragma unroll
+        for (int i = 0; i < 2 * MT; i++)
+          if (ok[i]) asm volatile("prefetch.global.L2 [%0];" ::"l"(arow[i] + kpf));
+      }
+    }
+    uint32_t ah[MT][2][4], al[MT][2][4];   // [m tile][product 0/1][a0..a3]
+#pragma unroll
+    for (int m = 0; m < MT; m++) {
+      const float4 lo_rows = cur[2 * m], hi_rows = cur[2 * m + 1];   // rows g and g + 8 of the tile
+      split_tf32(lo_rows.x, ah[m][0][0], al[m][0][0]);
+      split_tf32(hi_rows.x, ah[m][0][1], al[m][0][1]);
+      split_tf32(lo_rows.y, ah[m][0][2], al[m][0][2]);
+      split_tf32(hi_rows.y, ah[m][0][3], al[m][0][3]);
+      split_tf32(lo_rows.z, ah[m][1][0], al[m][1][0]);
+      split_tf32(hi_rows.z, ah[m][1][1], al[m][1][1]);
+      split_tf32(lo_rows.w, ah[m][1][2], al[m][1][2]);
+      split_tf32(hi_rows.w, ah[m][1][3], al[m][1][3]);
+    }
+#pragma unroll
+    for (int j = 0; j < kNT; j++) {
+      const int off = (j * 8 + g) * p.kstride + ch * 16 + 4 * t;
+      const uint4 bh = *reinterpret_cast<const uint4*>(Wh + off);
+      const uint4 bl = *reinterpret_cast<const uint4*>(Wl + off);
+#pragma unroll
+      for (int m = 0; m < MT; m++) {
+        mma_3x(acc[m][j], ah[m][0], al[m][0], bh.x, bh.y, bl.x, bl.y);
+        mma_3x(acc[m][j], ah[m][1], al[m][1], bh.z, bh.w, bl.z, bl.w);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2 * MT; i++) cur[i] = nxt[i];
+  }
+  // epilogue: accumulator (c0, c1) = (row g, columns 2t, 2t+1), (c2, c3) = row g + 8
+#pragma unroll
+  for (int m = 0; m < MT; m++) {
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      const long long r = r0 + 16 * m + 8 * half + g;
+      if (r >= r_end) continue;
+      float* orow = p.out + r * p.ldo;
+#pragma unroll
+      for (int j = 0; j < kNT; j++) {
+        const int n = n_base + j * 8 + 2 * t;
+        if (n >= p.N) continue;
+        float v0 = acc[m][j][2 * half], v1 = acc[m][j][2 * half + 1];
+        const bool two = n + 1 < p.N;
+        if (p.bias) {
+          v0 += __ldg(p.bias + n);
+          if (two) v1 += __ldg(p.bias + n + 1);
+        }
+        if (two && p.vec_o) {
+          float2* dst = reinterpret_cast<float2*>(orow + n);
+          if (p.accumulate) {
+            const float2 old = *dst;
+            v0 += old.x;
+            v1 += old.y;
+          }
+          *dst = make_float2(v0, v1);
+        } else {
+          if (p.accumulate) {
+            v0 += orow[n];
+            if (two) v1 += orow[n + 1];
+          }
+          orow[n] = v0;
+          if (two) orow[n + 1] = v1;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) affine_rows_kernel(const RowsParams p) {
+  extern __shared__ __align__(16) uint32_t smem_u[];
+  uint32_t* Wh = smem_u;
+  uint32_t* Wl = smem_u + kNB * p.kstride;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_base = blockIdx.y * kNB;
+  // stage this block's 40 columns of Wt, split once for every warp; the index runs along whichever axis is
+  // contiguous in global memory
+  const int total = kNB * p.kstride;
+  for (int idx = tid; idx < total; idx += kThreads) {
+    int n, k;
+    if (p.w_sn == 1) {
+      k = idx / kNB;
+      n = idx - k * kNB;
+    } else {
+      n = idx / p.kstride;
+      k = idx - n * p.kstride;
+    }
+    float w = 0.f;
+    if (n_base + n < p.N && k < p.Kc) w = __ldg(p.W + (long long)(n_base + n) * p.w_sn + (long long)k * p.w_sk);
+    uint32_t hi, lo;
+    split_tf32(w, hi, lo);
+    Wh[n * p.kstride + k] = hi;
+    Wl[n * p.kstride + k] = lo;
+  }
+  __syncthreads();
+  // every warp of the grid takes one contiguous range of rows (a multiple of 16), walked in tiles of 32 and 16
+  const long long warps = (long long)gridDim.x * kWarps;
+  const long long gw = (long long)blockIdx.x * kWarps + warp;
+  long long per = (p.rows + warps - 1) / warps;
+  per = (per + 15) & ~15LL;
+  long long r = gw * per;
+  const long long r_end = min(p.rows, r + per);
+  while (r < r_end) {
+    if (r_end - r > 16) {
+      rows_tile<2>(p, Wh, Wl, r, r_end, n_base, lane);
+      r += 32;
+    } else {
+      rows_tile<1>(p, Wh, Wl, r, r_end, n_base, lane);
+      r += 16;
+    }
+  }
+}
+
+// ---- dW / db ---------------------------------------------------------------------------------------------------
+constexpr int kSlab = 32;            // rows per stage
+constexpr int kKB = 512;             // k per CTA (32 per warp)
+constexpr int kHS = kKB + 8;         // floats per staged H row (8 mod 32: the fragment loads hit 32 banks once)
+constexpr int kDS = kNB;             // floats per staged dL row (40 = 8 mod 32)
+constexpr int kStages = 3;
+constexpr size_t kDwSmem = (size_t)kStages * kSlab * (kHS + kDS) * sizeof(float);
+
+struct DwParams {
+  const float* H;
+  long long ldh;
+  const float* dL;
+  long long ldd;
+  long long rows;
+  int K, C;
+  float* part;     // [gridDim.x][gridDim.y * kKB + 1][gridDim.z * kNB]; the last row of a slice holds db's partial
+  int vec_h;       // 16-byte cp.async legal for H rows
+  int vec_d;       // 8-byte cp.async legal for dL rows
+};
+
+__device__ __forceinline__ void cp_async(void* dst, const void* src, int bytes, int src_bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  if (bytes == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+  else if (bytes == 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1) affine_dw_kernel(const DwParams p) {
+  extern __shared__ __align__(16) float smem_f[];
+  float* Hs = smem_f;                                        // [stage][kSlab][kHS]
+  float* Ds = smem_f + (size_t)kStages * kSlab * kHS;        // [stage][kSlab][kDS]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int k0 = blockIdx.y * kKB, c0 = blockIdx.z * kNB;
+  const int kv = min(kKB, p.K - k0), cv = min(kNB, p.C - c0);   // valid k / c of this block
+  // columns the copies never write stay zero for the whole kernel
+  for (int i = tid; i < kStages * kSlab * kHS; i += kThreads) Hs[i] = 0.f;
+  for (int i = tid; i < kStages * kSlab * kDS; i += kThreads) Ds[i] = 0.f;
+  __syncthreads();
+
+  long long per = (p.rows + gridDim.x - 1) / gridDim.x;
+  per = (per + kSlab - 1) / kSlab * kSlab;
+  const long long r_begin = (long long)blockIdx.x * per;
+  const long long r_end = min(p.rows, r_begin + per);
+  const int slabs = r_begin < r_end ? (int)((r_end - r_begin + kSlab - 1) / kSlab) : 0;
+
+  auto issue = [&](int s) {   // copies of slab s into stage s % kStages (rows past r_end arrive as zeros)
+    float* hs = Hs + (size_t)(s % kStages) * kSlab * kHS;
+    float* ds = Ds + (size_t)(s % kStages) * kSlab * kDS;
+    const long long rs = r_begin + (long long)s * kSlab;
+    if (p.vec_h) {
+      const int per_row = (kv + 3) >> 2;          // kv is a multiple of 4 whenever vec_h is set
+      for (int i = tid; i < kSlab * per_row; i += kThreads) {
+        const int rr = i / per_row, q = i - rr * per_row;
+        const bool in = rs + rr < r_end;
+        cp_async(hs + rr * kHS + 4 * q, p.H + (in ? rs + rr : r_begin) * p.ldh + k0 + 4 * q, 16, in ? 16 : 0);
+      }
+    } else {
+      for (int i = tid; i < kSlab * kv; i += kThreads) {
+        const int rr = i / kv, q = i - rr * kv;
+        const bool in = rs + rr < r_end;
+        cp_async(hs + rr * kHS + q, p.H + (in ? rs + rr : r_begin) * p.ldh + k0 + q, 4, in ? 4 : 0);
+      }
+    }
+    if (p.vec_d) {
+      const int per_row = (cv + 1) >> 1;          // cv is even whenever vec_d is set
+      for (int i = tid; i < kSlab * per_row; i += kThreads) {
+        const int rr = i / per_row, q = i - rr * per_row;
+        const bool in = rs + rr < r_end;
+        cp_async(ds + rr * kDS + 2 * q, p.dL + (in ? rs + rr : r_begin) * p.ldd + c0 + 2 * q, 8, in ? 8 : 0);
+      }
+    } else {
+      for (int i = tid; i < kSlab * cv; i += kThreads) {
+        const int rr = i / cv, q = i - rr * cv;
+        const bool in = rs + rr < r_end;
+        cp_async(ds + rr * kDS + q, p.dL + (in ? rs + rr : r_begin) * p.ldd + c0 + q, 4, in ? 4 : 0);
+      }
+    }
+  };
+
+  float acc[2][kNT][4];
+#pragma unroll
+  for (int m = 0; m < 2; m++)
+#pragma unroll
+    for (int j = 0; j < kNT; j++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) acc[m][j][e] = 0.f;
+  float db_acc = 0.f;
+
+  if (slabs > 0) issue(0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (slabs > 1) issue(1);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int s = 0; s < slabs; s++) {
+    asm volatile("cp.async.wait_group 1;" ::: "memory");   // slab s has landed (one younger group may be in flight)
+    __syncthreads();                                        // ... for every thread; and stage (s+2)%3 is free again
+    if (s + 2 < slabs) issue(s + 2);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const float* hs = Hs + (size_t)(s % kStages) * kSlab * kHS;
+    const float* ds = Ds + (size_t)(s % kStages) * kSlab * kDS;
+    if (blockIdx.y == 0 && tid < kNB) {
+      float sum = 0.f;
+#pragma unroll 8
+      for (int rr = 0; rr < kSlab; rr++) sum += ds[rr * kDS + tid];
+      db_acc += sum;
+    }
+#pragma unroll
+    for (int ks = 0; ks < kSlab / 8; ks++) {
+      // A = H^T: a0 (m = g, k slot t) = H[row t][k g], a1 = k g+8, a2/a3 = row t+4
+      const float* h0 = hs + (ks * 8 + t) * kHS + warp * 32 + g;
+      const float* h1 = h0 + 4 * kHS;
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int m = 0; m < 2; m++) {
+        split_tf32(h0[16 * m], ah[m][0], al[m][0]);
+        split_tf32(h0[16 * m + 8], ah[m][1], al[m][1]);
+        split_tf32(h1[16 * m], ah[m][2], al[m][2]);
+        split_tf32(h1[16 * m + 8], ah[m][3], al[m][3]);
+      }
+      const float* d0 = ds + (ks * 8 + t) * kDS + g;
+      const float* d1 = d0 + 4 * kDS;
+#pragma unroll
+      for (int j = 0; j < kNT; j++) {
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(d0[8 * j], bh0, bl0);
+        split_tf32(d1[8 * j], bh1, bl1);
+#pragma unroll
+        for (int m = 0; m < 2; m++) mma_3x(acc[m][j], ah[m], al[m], bh0, bh1, bl0, bl1);
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // partials: slice of this CTA, rows = k of the whole grid (+ one row for db), columns = c of the whole grid
+  const long long ncols = (long long)gridDim.z * kNB;
+  const long long nrows = (long long)gridDim.y * kKB + 1;
+  float* slice = p.part + (long long)blockIdx.x * nrows * ncols;
+#pragma unroll
+  for (int m = 0; m < 2; m++)
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      const long long kk = k0 + warp * 32 + 16 * m + 8 * half + g;
+#pragma unroll
+      for (int j = 0; j < kNT; j++) {
+        float2* dst = reinterpret_cast<float2*>(slice + kk * ncols + c0 + j * 8 + 2 * t);
+        *dst = make_float2(acc[m][j][2 * half], acc[m][j][2 * half + 1]);
+      }
+    }
+  if (blockIdx.y == 0 && tid < kNB) slice[(nrows - 1) * ncols + c0 + tid] = db_acc;
+}
+
+__global__ void affine_reduce_kernel(const float* __restrict__ part, int slices, long long nrows, long long ncols,
+                                     int K, int C, float* __restrict__ dW, float* __restrict__ db) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)(K + 1) * C;
+  if (i >= n) return;
+  const int kk = (int)(i / C), c = (int)(i - (long long)kk * C);
+  const long long row = kk < K ? kk : nrows - 1;
+  if (kk < K ? dW == nullptr : db == nullptr) return;
+  float s = 0.f;
+  for (int x = 0; x < slices; x++) s += part[((long long)x * nrows + row) * ncols + c];
+  if (kk < K) dW[(long long)kk * C + c] = s;
+  else db[c] = s;
+}
+
+static int launch_rows(const float* A, long long lda, long long rows, int Kc_total, const float* W, long long w_sn,
+                       long long w_sk, int N, const float* bias, float* out, long long ldo, cudaStream_t stream) {
+  int sms = 0;
+  NASR_CUDA(device_sm_count(&sms));
+  const long long tiles16 = (rows + 15) / 16;
+  const int gx = (int)max(1LL, min((long long)sms, (tiles16 + kWarps - 1) / kWarps));
+  const int gy = (N + kNB - 1) / kNB;
+  NASR_CUDA((ensure_max_dynamic_smem<affine_rows_kernel>(227 * 1024)));
+  for (int kseg = 0; kseg < Kc_total; kseg += kMaxSeg) {
+    RowsParams p;
+    p.Kc = min(kMaxSeg, Kc_total - kseg);
+    p.A = A + kseg;
+    p.lda = lda;
+    p.rows = rows;
+    p.W = W + (long long)kseg * w_sk;
+    p.w_sn = w_sn;
+    p.w_sk = w_sk;
+    p.N = N;
+    p.bias = kseg == 0 ? bias : nullptr;
+    p.out = out;
+    p.ldo = ldo;
+    p.accumulate = kseg > 0;
+    p.kstride = ((p.Kc + 31) & ~31) + 16;
+    p.vec_a = (((uintptr_t)p.A & 15) == 0) && (lda % 4 == 0);
+    p.vec_o = (((uintptr_t)out & 7) == 0) && (ldo % 2 == 0);
+    const size_t smem = (size_t)2 * kNB * p.kstride * sizeof(uint32_t);
+    affine_rows_kernel<<<dim3(gx, gy), kThreads, smem, stream>>>(p);
+    count_launch();
+    NASR_CUDA(cudaGetLastError());
+  }
+  return NASR_OK;
+}
+
+static void dw_grid(long long rows, int K, int C, int sms, int* gx, int* gy, int* gz) {
+  *gy = (K + kKB - 1) / kKB;
+  *gz = (C + kNB - 1) / kNB;
+  const long long slabs = (rows + kSlab - 1) / kSlab;
+  const int want = max(1, sms / ((*gy) * (*gz)));
+  *gx = (int)max(1LL, min((long long)want, slabs));
+}
+
+int workspace_bytes(long long rows, int K, int C, size_t* out) {
+  int sms = 0;
+  NASR_CUDA(device_sm_count(&sms));
+  int gx, gy, gz;
+  dw_grid(rows, K, C, sms, &gx, &gy, &gz);
+  *out = sizeof(float) * (size_t)gx * ((size_t)gy * kKB + 1) * ((size_t)gz * kNB);
+  return NASR_OK;
+}
+
+int forward(const float* H, long long rows, int K, long long ldh, const float* W, const float* bias, int C,
+            float* logits, long long ldl, cudaStream_t stream) {
+  if (rows == 0) return NASR_OK;
+  // Wt[n = c][k] = W[k*C + c]
+  return launch_rows(H, ldh, rows, K, W, 1, C, C, bias, logits, ldl, stream);
+}
+
+int backward(const float* H, long long rows, int K, long long ldh, const float* W, int C, const float* dL,
+             long long ldd, float* dH, long long lddh, float* dW, float* db, void* ws, size_t ws_bytes,
+             cudaStream_t stream) {
+  if (dH && rows > 0) {
+    // dH[r, k] = sum_c dL[r, c] * W[k, c]: Wt[n = k][contraction c] = W[k*C + c]
+    const int rc = launch_rows(dL, ldd, rows, C, W, C, 1, K, nullptr, dH, lddh, stream);
+    if (rc != NASR_OK) return rc;
+  }
+  if (dW || db) {
+    if (rows == 0) {
+      if (dW) NASR_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)K * C, stream));
+      if (db) NASR_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)C, stream));
+      return NASR_OK;
+    }
+    int sms = 0;
+    NASR_CUDA(device_sm_count(&sms));
+    int gx, gy, gz;
+    dw_grid(rows, K, C, sms, &gx, &gy, &gz);
+    const size_t need = sizeof(float) * (size_t)gx * ((size_t)gy * kKB + 1) * ((size_t)gz * kNB);
+    if (!ws || ws_bytes < need) {
+      set_error("nasr_affine_backward_f32: workspace of %zu bytes, %zu needed (nasr_affine_workspace_bytes)",
+                ws_bytes, need);
+      return NASR_ERR_WORKSPACE_TOO_SMALL;
+    }
+    DwParams p;
+    p.H = H;
+    p.ldh = ldh;
+    p.dL = dL;
+    p.ldd = ldd;
+    p.rows = rows;
+    p.K = K;
+    p.C = C;
+    p.part = static_cast<float*>(ws);
+    p.vec_h = (((uintptr_t)H & 15) == 0) && (ldh % 4 == 0) && (K % 4 == 0);
+    p.vec_d = (((uintptr_t)dL & 7) == 0) && (ldd % 2 == 0) && (C % 2 == 0);
+    NASR_CUDA((ensure_max_dynamic_smem<affine_dw_kernel>((int)kDwSmem)));
+    affine_dw_kernel<<<dim3(gx, gy, gz), kThreads, kDwSmem, stream>>>(p);
+    count_launch();
+    NASR_CUDA(cudaGetLastError());
+    const long long n = (long long)(K + 1) * C;
+    affine_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+        p.part, gx, (long long)gy * kKB + 1, (long long)gz * kNB, K, C, dW, db);
+    count_launch();
+    NASR_CUDA(cudaGetLastError());
+  }
+  return NASR_OK;
+}
+
+}  // namespace affine
+}  // namespace nasr
+
+using namespace nasr;
+
+int nasr_affine_workspace_bytes(long long rows, int K, int C, size_t* out_bytes) {
+  NASR_CHECK_ARG(out_bytes, "nasr_affine_workspace_bytes: out_bytes is NULL");
+  NASR_CHECK_ARG(rows >= 0 && K >= 1 && C >= 1, "nasr_affine_workspace_bytes: bad shape rows=%lld K=%d C=%d", rows, K,
+                 C);
+  return affine::workspace_bytes(rows, K, C, out_bytes);
+}
+
+int nasr_affine_logits_f32(const float* H, long long rows, int K, long long ldh, const float* W, const float* bias,
+                           int C, float* logits, long long ldl, void* stream) {
+  NASR_CHECK_ARG(rows >= 0 && K >= 1 && C >= 1, "nasr_affine_logits_f32: bad shape rows=%lld K=%d C=%d", rows, K, C);
+  NASR_CHECK_ARG(ldh >= K && ldl >= C, "nasr_affine_logits_f32: row strides ldh=%lld ldl=%lld shorter than a row",
+                 ldh, ldl);
+  NASR_CHECK_ARG(W && (rows == 0 || (H && logits)), "nasr_affine_logits_f32: NULL argument");
+  return affine::forward(H, rows, K, ldh, W, bias, C, logits, ldl, static_cast<cudaStream_t>(stream));
+}
+
+int nasr_affine_backward_f32(const float* H, long long rows, int K, long long ldh, const float* W, int C,
+                             const float* dlogits, long long ldd, float* dH, long long lddh, float* dW, float* db,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  NASR_CHECK_ARG(rows >= 0 && K >= 1 && C >= 1, "nasr_affine_backward_f32: bad shape rows=%lld K=%d C=%d", rows, K,
+                 C);
+  NASR_CHECK_ARG(ldd >= C && (!dH || lddh >= K) && (!(dW || db) || ldh >= K),
+                 "nasr_affine_backward_f32: a row stride is shorter than its row");
+  NASR_CHECK_ARG(rows == 0 || dlogits, "nasr_affine_backward_f32: dlogits is NULL");
+  NASR_CHECK_ARG(!dH || W, "nasr_affine_backward_f32: dH needs W");
+  NASR_CHECK_ARG(!(dW || db) || rows == 0 || H, "nasr_affine_backward_f32: dW / db need H");
+  return affine::backward(H, rows, K, ldh, W, C, dlogits, ldd, dH, lddh, dW, db, workspace, workspace_bytes,
+                          static_cast<cudaStream_t>(stream));
+}

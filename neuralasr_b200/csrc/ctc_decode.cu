@@ -246,33 +246,24 @@ edit_distance_kernel(const HypT* __restrict__ hyp, long hyp_stride, const int32_
       __syncwarp();
       for (int j = lane; j < m; j += 32) atomicOr(&peq[truth_values[t0 + j] * W + (j >> 5)], 1u << (j & 31));
       __syncwarp();
-      // the hypothesis goes into shared memory behind the table (as int32: the reference casts the decoder's int64
-      // ids first, tfnetwork.py:68) so that the loop below never waits on global memory
-      int* hy = sm + table_words;
-      for (int i = lane; i < n; i += 32) hy[i] = (int)h[i];
-      __syncwarp();
       unsigned Pv = 0xffffffffu, Mv = 0u;
       int score = m;
       const int lastw = W - 1;
       const int topbit = lane == lastw ? ((m - 1) & 31) : 31;
       int hout = 0;
-      const bool mine = lane < W;
-      // software pipeline: the match mask of step s+1 and the symbol of step s+2 are requested in step s, so the
-      // loop-carried chain is the bit-vector arithmetic and one shuffle only
-      auto sym = [&](int i) -> int { return (mine && i >= 0 && i < n) ? hy[i] : -1; };
-      auto mask = [&](int c) -> unsigned { return (c >= 0 && c < nsym) ? peq[c * W + lane] : 0u; };
-      unsigned eq_next = mask(sym(-lane));
-      int c_next = sym(1 - lane);
+      long long cnext = (lane == 0) ? (long long)h[0] : 0;
       const int steps = n + W - 1;
       for (int s = 0; s < steps; s++) {
         const int hin_up = __shfl_up_sync(0xffffffffu, hout, 1);
         const int i = s - lane;
-        const bool active = mine && i >= 0 && i < n;
-        unsigned Eq = eq_next;
-        eq_next = mask(c_next);
-        c_next = sym(s + 2 - lane);
+        const bool active = lane < W && i >= 0 && i < n;
+        const long long c = cnext;
+        // prefetch the symbol of the next step (lane w reads hyp[s+1-w])
+        const int inext = i + 1;
+        if (lane < W && inext >= 0 && inext < n) cnext = (long long)h[inext];
         if (active) {
           const int hin = lane == 0 ? 1 : hin_up;
+          unsigned Eq = (c >= 0 && c < nsym) ? peq[(int)c * W + lane] : 0u;
           const unsigned Xv = Eq | Mv;
           if (hin < 0) Eq |= 1u;
           const unsigned Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
@@ -406,8 +397,7 @@ int launch_edit_distance(const HypT* hyp, long hyp_stride, const int32_t* hyp_le
                          int normalize, int32_t* dist, float* ler, cudaStream_t stream) {
   const size_t dp = sizeof(int) * ((size_t)max_truth_len + max_hyp_len + 3 * ((size_t)max_truth_len + 1));
   const size_t table = 64 * 1024;  // match masks of the bit-vector path: (max symbol + 1) * ceil(|truth|/32) words
-  const size_t fast = table + sizeof(int) * (size_t)max_hyp_len;  // the table + the staged hypothesis
-  const size_t smem = dp > fast ? dp : fast;
+  const size_t smem = dp > table ? dp : table;
   if (smem > 200 * 1024) {
     set_error("nasr_edit_distance: max_truth_len=%d max_hyp_len=%d exceed shared memory", max_truth_len,
               max_hyp_len);

@@ -314,6 +314,102 @@ def loss(logits, labels, seq_len, check=True):
 
 
 # --------------------------------------------------------------------------------------------
+# the model tails' affine projection
+# --------------------------------------------------------------------------------------------
+def _rows2d(t, name, cols=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32 or t.dim() != 2:
+        raise ValueError("%s must be a float32 CUDA [rows, %s] tensor (there is no CPU path)" % (name, cols or "K"))
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    if t.shape[0] > 1 and t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t
+
+
+def affine_logits(H, W, b=None, out=None):
+    """``tf.matmul(outputs, W) + b`` of the reference's tails (``bilstm_ctc_net.py:33-45``): ``H`` float32 CUDA
+    ``[rows, K]`` (rows may be strided), ``W`` ``[K, C]``, ``b`` ``[C]`` -> ``[rows, C]`` (no autograd: see
+    :func:`affine_projection`)."""
+    H = _rows2d(H, "H")
+    if W.dim() != 2 or W.shape[0] != H.shape[1] or W.dtype != torch.float32 or not W.is_cuda:
+        raise ValueError("W must be a float32 CUDA [K=%d, C] tensor, got %s" % (H.shape[1], tuple(W.shape)))
+    W = W.contiguous()
+    rows, K = H.shape
+    C = W.shape[1]
+    if b is not None:
+        if b.shape != (C,) or b.dtype != torch.float32 or not b.is_cuda:
+            raise ValueError("b must be a float32 CUDA [C=%d] tensor" % C)
+        b = b.contiguous()
+    if out is None:
+        out = torch.empty((rows, C), dtype=torch.float32, device=H.device)
+    lib = _lib.load()
+    with torch.cuda.device(H.device):
+        _lib.check(lib.nasr_affine_logits_f32(_ptr(H), rows, K, H.stride(0) if rows > 1 else K, _ptr(W), _ptr(b), C,
+                                              _ptr(out), out.stride(0) if rows > 1 else C,
+                                              _stream_ptr(H.device)), "nasr_affine_logits_f32")
+    return out
+
+
+def affine_backward(H, W, dlogits, want_dH=True, want_dW=True, want_db=True):
+    """The three gradients of :func:`affine_logits`: ``(dH [rows, K], dW [K, C], db [C])`` (``None`` where not
+    wanted)."""
+    H = _rows2d(H, "H")
+    dlogits = _rows2d(dlogits, "dlogits", "C")
+    W = W.contiguous()
+    rows, K = H.shape
+    C = W.shape[1]
+    dev = H.device
+    dH = torch.empty((rows, K), dtype=torch.float32, device=dev) if want_dH else None
+    dW = torch.empty((K, C), dtype=torch.float32, device=dev) if want_dW else None
+    db = torch.empty((C,), dtype=torch.float32, device=dev) if want_db else None
+    lib = _lib.load()
+    ws, nbytes = None, 0
+    if want_dW or want_db:
+        need = ctypes.c_size_t(0)
+        with torch.cuda.device(dev):
+            _lib.check(lib.nasr_affine_workspace_bytes(rows, K, C, ctypes.byref(need)), "nasr_affine_workspace_bytes")
+        nbytes = int(need.value)
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.nasr_affine_backward_f32(_ptr(H), rows, K, H.stride(0) if rows > 1 else K, _ptr(W), C,
+                                                _ptr(dlogits), dlogits.stride(0) if rows > 1 else C, _ptr(dH), K,
+                                                _ptr(dW), _ptr(db), _ptr(ws), nbytes, _stream_ptr(dev)),
+                   "nasr_affine_backward_f32")
+    return dH, dW, db
+
+
+class _AffineFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, H, W, b):
+        ctx.save_for_backward(H, W)
+        ctx.has_bias = b is not None
+        return affine_logits(H.detach(), W.detach(), None if b is None else b.detach())
+
+    @staticmethod
+    def backward(ctx, g):
+        H, W = ctx.saved_tensors
+        dH, dW, db = affine_backward(H, W, g, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                     ctx.has_bias and ctx.needs_input_grad[2])
+        return dH, dW, db
+
+
+def affine_projection(outputs, W, b, batch_size):
+    """The tail every CTC model of the reference ends with (``bilstm_ctc_net.py:31-48``, ``lstm_ctc_net.py:26-43``)::
+
+        outputs = tf.reshape(outputs, [-1, num_hidden]); logits = tf.matmul(outputs, W) + b
+        logits = tf.reshape(logits, [batch_s, -1, num_classes]); logits = tf.transpose(logits, (1, 0, 2))
+
+    ``outputs`` float32 CUDA ``[..., num_hidden]`` (batch-major, any leading shape — the BiLSTM tail reshapes the
+    (forward, backward) pair, which stacks both directions along the rows).  Returns the time-major ``[T', B, C]``
+    VIEW of the batch-major result: no transpose is executed, ``loss`` / ``decoding`` read it through its strides.
+    Differentiable w.r.t. ``outputs``, ``W`` and ``b``."""
+    K = W.shape[0]
+    H = outputs.reshape(-1, K)
+    logits = _AffineFn.apply(H, W, b)
+    return batch_major(logits.reshape(int(batch_size), -1, W.shape[1]))
+
+
+# --------------------------------------------------------------------------------------------
 # greedy decode
 # --------------------------------------------------------------------------------------------
 class DecodedSparse:
