@@ -69,98 +69,40 @@ struct RowsParams {
   float* out;            // [rows, N] at stride ldo
   long long ldo;
   int accumulate;        // out += instead of out =
-  int kstride;           // floats per staged Wt row: round_up(Kc, 32) + 16 (16-byte loads of 8 rows hit 32 banks once)
-  int vec_a;             // rows of A start 16-byte aligned
+  int kstride;           // floats per staged Wt row (see launch_rows)
+  int vec_a;             // rows of A allow the mode's vector loads (16-byte in MODE 16, 8-byte in MODE 8)
   int vec_o;             // rows of out start 8-byte aligned
 };
 
-__device__ __forceinline__ float4 load_a(const float* row, bool ok, int k, int Kc, int vec) {
+// Split of an operand that is about to be fed to an mma: hi is x rounded to TF32's 10 mantissa bits (add half an ulp,
+// clear the low 13 bits: 2 instructions where cvt.rna.tf32.f32 compiles to 4), lo = x - hi exactly; lo goes to the
+// tensor core as it is, which ignores its low 13 bits (error < 2^-21 |x|, either sign).
+__device__ __forceinline__ void split_fast(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+__device__ __forceinline__ float4 load_a4_checked(const float* row, int k, int Kc) {
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (ok) {
-    if (vec && k + 3 < Kc) {
-      v = __ldg(reinterpret_cast<const float4*>(row + k));
-    } else {
-      if (k < Kc) v.x = __ldg(row + k);
-      if (k + 1 < Kc) v.y = __ldg(row + k + 1);
-      if (k + 2 < Kc) v.z = __ldg(row + k + 2);
-      if (k + 3 < Kc) v.w = __ldg(row + k + 3);
-    }
-  }
+  if (k < Kc) v.x = __ldg(row + k);
+  if (k + 1 < Kc) v.y = __ldg(row + k + 1);
+  if (k + 2 < Kc) v.z = __ldg(row + k + 2);
+  if (k + 3 < Kc) v.w = __ldg(row + k + 3);
   return v;
 }
 
-// One warp, MT m16 tiles of rows starting at r0 (rows >= r_end are masked), all kNT column tiles of the CTA's block.
-// Lane (g = lane / 4, t = lane % 4) loads A[row g + 8i][16*ch + 4t .. +3]; the four values are the k slots
-// (t, t+4) of two m16n8k8 products, and Wt is read with the same permutation, so the sum over k is unchanged.
+__device__ __forceinline__ float2 load_a2_checked(const float* row, int k, int Kc) {
+  float2 v = make_float2(0.f, 0.f);
+  if (k < Kc) v.x = __ldg(row + k);
+  if (k + 1 < Kc) v.y = __ldg(row + k + 1);
+  return v;
+}
+
+// accumulator (c0, c1) = (row g, columns 2t, 2t+1), (c2, c3) = row g + 8
 template <int MT>
-__device__ __forceinline__ void rows_tile(const RowsParams& p, const uint32_t* __restrict__ Wh,
-                                          const uint32_t* __restrict__ Wl, long long r0, long long r_end,
-                                          int n_base, int lane) {
+__device__ __forceinline__ void store_tile(const RowsParams& p, const float (&acc)[MT][kNT][4], long long r0,
+                                           long long r_end, int n_base, int lane) {
   const int g = lane >> 2, t = lane & 3;
-  float acc[MT][kNT][4];
-#pragma unroll
-  for (int m = 0; m < MT; m++)
-#pragma unroll
-    for (int j = 0; j < kNT; j++)
-#pragma unroll
-      for (int e = 0; e < 4; e++) acc[m][j][e] = 0.f;
-  const float* arow[2 * MT];
-  bool ok[2 * MT];
-#pragma unroll
-  for (int i = 0; i < 2 * MT; i++) {
-    const long long r = r0 + g + 8 * i;
-    ok[i] = r < r_end;
-    arow[i] = p.A + (ok[i] ? r : r0) * p.lda;
-  }
-  const int nch = (p.Kc + 15) >> 4;
-  float4 cur[2 * MT], nxt[2 * MT];
-#pragma unroll
-  for (int i = 0; i < 2 * MT; i++) {
-    cur[i] = load_a(arow[i], ok[i], 4 * t, p.Kc, p.vec_a);
-    nxt[i] = cur[i];
-  }
-  for (int ch = 0; ch < nch; ch++) {
-    if (ch + 1 < nch) {
-#pragma unroll
-      for (int i = 0; i < 2 * MT; i++) nxt[i] = load_a(arow[i], ok[i], (ch + 1) * 16 + 4 * t, p.Kc, p.vec_a);
-    }
-    // the rows' bytes four chunks ahead go to L2 now: the register prefetch above then waits an L2 hit, not DRAM
-    if (t == 0) {
-      const int kpf = (ch + 5) * 16;
-      if (kpf < p.Kc) {
-#pragma unroll
-        for (int i = 0; i < 2 * MT; i++)
-          if (ok[i]) asm volatile("prefetch.global.L2 [%0];" ::"l"(arow[i] + kpf));
-      }
-    }
-    uint32_t ah[MT][2][4], al[MT][2][4];   // [m tile][product 0/1][a0..a3]
-#pragma unroll
-    for (int m = 0; m < MT; m++) {
-      const float4 lo_rows = cur[2 * m], hi_rows = cur[2 * m + 1];   // rows g and g + 8 of the tile
-      split_tf32(lo_rows.x, ah[m][0][0], al[m][0][0]);
-      split_tf32(hi_rows.x, ah[m][0][1], al[m][0][1]);
-      split_tf32(lo_rows.y, ah[m][0][2], al[m][0][2]);
-      split_tf32(hi_rows.y, ah[m][0][3], al[m][0][3]);
-      split_tf32(lo_rows.z, ah[m][1][0], al[m][1][0]);
-      split_tf32(hi_rows.z, ah[m][1][1], al[m][1][1]);
-      split_tf32(lo_rows.w, ah[m][1][2], al[m][1][2]);
-      split_tf32(hi_rows.w, ah[m][1][3], al[m][1][3]);
-    }
-#pragma unroll
-    for (int j = 0; j < kNT; j++) {
-      const int off = (j * 8 + g) * p.kstride + ch * 16 + 4 * t;
-      const uint4 bh = *reinterpret_cast<const uint4*>(Wh + off);
-      const uint4 bl = *reinterpret_cast<const uint4*>(Wl + off);
-#pragma unroll
-      for (int m = 0; m < MT; m++) {
-        mma_3x(acc[m][j], ah[m][0], al[m][0], bh.x, bh.y, bl.x, bl.y);
-        mma_3x(acc[m][j], ah[m][1], al[m][1], bh.z, bh.w, bl.z, bl.w);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 2 * MT; i++) cur[i] = nxt[i];
-  }
-  // epilogue: accumulator (c0, c1) = (row g, columns 2t, 2t+1), (c2, c3) = row g + 8
 #pragma unroll
   for (int m = 0; m < MT; m++) {
 #pragma unroll
@@ -199,6 +141,124 @@ __device__ __forceinline__ void rows_tile(const RowsParams& p, const uint32_t* _
   }
 }
 
+// One warp, MT m16 tiles of rows starting at r0 (rows >= r_end are computed on a clamped row and not stored), all kNT
+// column tiles of the CTA's block.  The k order inside a tile is permuted identically for A and Wt, so that a lane
+// reads consecutive k of one row with one vector load and the sum over k is unchanged:
+//   MODE 16 (rows of A 16-byte aligned): lane (g = lane / 4, t = lane % 4) loads A[row g + 8i][16*ch + 4t .. +3]; the
+//            four values are the k slots (t, t+4) of two m16n8k8 products;
+//   MODE 8  (anything else; 8-byte loads where the rows allow): A[row][8*st + 2t, +1] are the slots (t, t+4) of one.
+template <int MT, int MODE>
+__device__ __forceinline__ void rows_tile(const RowsParams& p, const uint32_t* __restrict__ Wh,
+                                          const uint32_t* __restrict__ Wl, long long r0, long long r_end,
+                                          int n_base, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  float acc[MT][kNT][4];
+#pragma unroll
+  for (int m = 0; m < MT; m++)
+#pragma unroll
+    for (int j = 0; j < kNT; j++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) acc[m][j][e] = 0.f;
+  const float* arow[2 * MT];
+#pragma unroll
+  for (int i = 0; i < 2 * MT; i++) arow[i] = p.A + min(r0 + g + 8 * i, p.rows - 1) * p.lda;
+  const int kstride = p.kstride;
+  const int Kc = p.Kc;
+
+  if (MODE == 16) {
+    const int nch = (Kc + 15) >> 4, nfull = Kc >> 4;   // chunks, and chunks whose 16 k all exist
+    const uint32_t* wh = Wh + g * kstride + 4 * t;
+    const uint32_t* wl = Wl + g * kstride + 4 * t;
+    float4 cur[2 * MT], nxt[2 * MT];
+#pragma unroll
+    for (int i = 0; i < 2 * MT; i++) {
+      cur[i] = nfull > 0 ? __ldg(reinterpret_cast<const float4*>(arow[i] + 4 * t))
+                         : load_a4_checked(arow[i], 4 * t, Kc);
+      nxt[i] = cur[i];
+    }
+    for (int ch = 0; ch < nch; ch++) {
+      const int kn = (ch + 1) * 16 + 4 * t;
+      if (ch + 1 < nfull) {
+#pragma unroll
+        for (int i = 0; i < 2 * MT; i++) nxt[i] = __ldg(reinterpret_cast<const float4*>(arow[i] + kn));
+      } else if (ch + 1 < nch) {
+#pragma unroll
+        for (int i = 0; i < 2 * MT; i++) nxt[i] = load_a4_checked(arow[i], kn, Kc);
+      }
+      // the rows' bytes five chunks ahead go to L2 now: the register prefetch above then waits an L2 hit, not DRAM
+      if (t == 0 && (ch + 5) * 16 < Kc) {
+#pragma unroll
+        for (int i = 0; i < 2 * MT; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(arow[i] + (ch + 5) * 16));
+      }
+      uint32_t ah[MT][2][4], al[MT][2][4];   // [m tile][product 0/1][a0..a3]
+#pragma unroll
+      for (int m = 0; m < MT; m++) {
+        const float4 ra = cur[2 * m], rb = cur[2 * m + 1];   // rows g and g + 8 of the tile
+        split_fast(ra.x, ah[m][0][0], al[m][0][0]);
+        split_fast(rb.x, ah[m][0][1], al[m][0][1]);
+        split_fast(ra.y, ah[m][0][2], al[m][0][2]);
+        split_fast(rb.y, ah[m][0][3], al[m][0][3]);
+        split_fast(ra.z, ah[m][1][0], al[m][1][0]);
+        split_fast(rb.z, ah[m][1][1], al[m][1][1]);
+        split_fast(ra.w, ah[m][1][2], al[m][1][2]);
+        split_fast(rb.w, ah[m][1][3], al[m][1][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < kNT; j++) {
+        const uint4 bh = *reinterpret_cast<const uint4*>(wh + j * 8 * kstride + ch * 16);
+        const uint4 bl = *reinterpret_cast<const uint4*>(wl + j * 8 * kstride + ch * 16);
+#pragma unroll
+        for (int m = 0; m < MT; m++) {
+          mma_3x(acc[m][j], ah[m][0], al[m][0], bh.x, bh.y, bl.x, bl.y);
+          mma_3x(acc[m][j], ah[m][1], al[m][1], bh.z, bh.w, bl.z, bl.w);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 2 * MT; i++) cur[i] = nxt[i];
+    }
+  } else {
+    const int nst = (Kc + 7) >> 3, nfull = p.vec_a ? (Kc >> 3) : 0;   // vec_a: rows 8-byte aligned in this mode
+    const uint32_t* wh = Wh + g * kstride + 2 * t;
+    const uint32_t* wl = Wl + g * kstride + 2 * t;
+    float2 cur[2 * MT], nxt[2 * MT];
+#pragma unroll
+    for (int i = 0; i < 2 * MT; i++) {
+      cur[i] = nfull > 0 ? __ldg(reinterpret_cast<const float2*>(arow[i] + 2 * t))
+                         : load_a2_checked(arow[i], 2 * t, Kc);
+      nxt[i] = cur[i];
+    }
+    for (int st = 0; st < nst; st++) {
+      const int kn = (st + 1) * 8 + 2 * t;
+      if (st + 1 < nfull) {
+#pragma unroll
+        for (int i = 0; i < 2 * MT; i++) nxt[i] = __ldg(reinterpret_cast<const float2*>(arow[i] + kn));
+      } else if (st + 1 < nst) {
+#pragma unroll
+        for (int i = 0; i < 2 * MT; i++) nxt[i] = load_a2_checked(arow[i], kn, Kc);
+      }
+      uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+      for (int m = 0; m < MT; m++) {
+        split_fast(cur[2 * m].x, ah[m][0], al[m][0]);
+        split_fast(cur[2 * m + 1].x, ah[m][1], al[m][1]);
+        split_fast(cur[2 * m].y, ah[m][2], al[m][2]);
+        split_fast(cur[2 * m + 1].y, ah[m][3], al[m][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < kNT; j++) {
+        const uint2 bh = *reinterpret_cast<const uint2*>(wh + j * 8 * kstride + st * 8);
+        const uint2 bl = *reinterpret_cast<const uint2*>(wl + j * 8 * kstride + st * 8);
+#pragma unroll
+        for (int m = 0; m < MT; m++) mma_3x(acc[m][j], ah[m], al[m], bh.x, bh.y, bl.x, bl.y);
+      }
+#pragma unroll
+      for (int i = 0; i < 2 * MT; i++) cur[i] = nxt[i];
+    }
+  }
+  store_tile<MT>(p, acc, r0, r_end, n_base, lane);
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) affine_rows_kernel(const RowsParams p) {
   extern __shared__ __align__(16) uint32_t smem_u[];
   uint32_t* Wh = smem_u;
@@ -234,10 +294,110 @@ __global__ void __launch_bounds__(kThreads, 1) affine_rows_kernel(const RowsPara
   const long long r_end = min(p.rows, r + per);
   while (r < r_end) {
     if (r_end - r > 16) {
-      rows_tile<2>(p, Wh, Wl, r, r_end, n_base, lane);
+      rows_tile<2, MODE>(p, Wh, Wl, r, r_end, n_base, lane);
       r += 32;
     } else {
-      rows_tile<1>(p, Wh, Wl, r, r_end, n_base, lane);
+      rows_tile<1, MODE>(p, Wh, Wl, r, r_end, n_base, lane);
+      r += 16;
+    }
+  }
+}
+
+// Contractions of at most 40 (dH = dL.W^T at the reference's C = 38 / 41): a warp keeps its rows of A in registers
+// (five 8-byte steps), Wt for up to 17 column blocks lives in shared memory, and the warp walks the column blocks
+// itself -- A is read from global memory once, the prologue runs once per row tile.
+constexpr int kSmallK = 40;
+constexpr int kSmallSteps = kSmallK / 8;
+constexpr int kSmallBlocks = 17;      // 17 * 40 rows of Wt, hi + lo, 40 floats each: 217.6 KB
+
+template <int MT>
+__device__ __forceinline__ void smallk_tile(const RowsParams& p, const uint32_t* __restrict__ Wh,
+                                            const uint32_t* __restrict__ Wl, long long r0, long long r_end,
+                                            int n_first, int nblocks, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const int Kc = p.Kc, nst = (Kc + 7) >> 3, nfull = p.vec_a ? (Kc >> 3) : 0;
+  float2 a[kSmallSteps][2 * MT];
+#pragma unroll
+  for (int i = 0; i < 2 * MT; i++) {
+    const float* row = p.A + min(r0 + g + 8 * i, p.rows - 1) * p.lda;
+#pragma unroll
+    for (int st = 0; st < kSmallSteps; st++) {
+      if (st < nfull) a[st][i] = __ldg(reinterpret_cast<const float2*>(row + st * 8 + 2 * t));
+      else a[st][i] = load_a2_checked(row, st * 8 + 2 * t, Kc);
+    }
+  }
+  const uint32_t* wh = Wh + g * kSmallK + 2 * t;
+  const uint32_t* wl = Wl + g * kSmallK + 2 * t;
+  for (int nb = 0; nb < nblocks; nb++) {
+    float acc[MT][kNT][4];
+#pragma unroll
+    for (int m = 0; m < MT; m++)
+#pragma unroll
+      for (int j = 0; j < kNT; j++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) acc[m][j][e] = 0.f;
+#pragma unroll
+    for (int st = 0; st < kSmallSteps; st++) {
+      if (st < nst) {
+        uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+        for (int m = 0; m < MT; m++) {
+          split_fast(a[st][2 * m].x, ah[m][0], al[m][0]);
+          split_fast(a[st][2 * m + 1].x, ah[m][1], al[m][1]);
+          split_fast(a[st][2 * m].y, ah[m][2], al[m][2]);
+          split_fast(a[st][2 * m + 1].y, ah[m][3], al[m][3]);
+        }
+#pragma unroll
+        for (int j = 0; j < kNT; j++) {
+          const int off = (nb * kNB + j * 8) * kSmallK + st * 8;
+          const uint2 bh = *reinterpret_cast<const uint2*>(wh + off);
+          const uint2 bl = *reinterpret_cast<const uint2*>(wl + off);
+#pragma unroll
+          for (int m = 0; m < MT; m++) mma_3x(acc[m][j], ah[m], al[m], bh.x, bh.y, bl.x, bl.y);
+        }
+      }
+    }
+    store_tile<MT>(p, acc, r0, r_end, n_first + nb * kNB, lane);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) affine_smallk_kernel(const RowsParams p) {
+  extern __shared__ __align__(16) uint32_t smem_u[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_first = blockIdx.y * kSmallBlocks * kNB;
+  const int nblocks = min(kSmallBlocks, (p.N - n_first + kNB - 1) / kNB);
+  uint32_t* Wh = smem_u;
+  uint32_t* Wl = smem_u + nblocks * kNB * kSmallK;
+  const int total = nblocks * kNB * kSmallK;
+  for (int idx = tid; idx < total; idx += kThreads) {
+    int n, k;
+    if (p.w_sn == 1) {
+      k = idx / (nblocks * kNB);
+      n = idx - k * (nblocks * kNB);
+    } else {
+      n = idx / kSmallK;
+      k = idx - n * kSmallK;
+    }
+    float w = 0.f;
+    if (n_first + n < p.N && k < p.Kc) w = __ldg(p.W + (long long)(n_first + n) * p.w_sn + (long long)k * p.w_sk);
+    uint32_t hi, lo;
+    split_tf32(w, hi, lo);
+    Wh[n * kSmallK + k] = hi;
+    Wl[n * kSmallK + k] = lo;
+  }
+  __syncthreads();
+  const long long warps = (long long)gridDim.x * kWarps;
+  const long long gw = (long long)blockIdx.x * kWarps + warp;
+  long long per = (p.rows + warps - 1) / warps;
+  per = (per + 15) & ~15LL;
+  long long r = gw * per;
+  const long long r_end = min(p.rows, r + per);
+  while (r < r_end) {
+    if (r_end - r > 16) {
+      smallk_tile<2>(p, Wh, Wl, r, r_end, n_first, nblocks, lane);
+      r += 32;
+    } else {
+      smallk_tile<1>(p, Wh, Wl, r, r_end, n_first, nblocks, lane);
       r += 16;
     }
   }
@@ -360,18 +520,18 @@ __global__ void __launch_bounds__(kThreads, 1) affine_dw_kernel(const DwParams p
       uint32_t ah[2][4], al[2][4];
 #pragma unroll
       for (int m = 0; m < 2; m++) {
-        split_tf32(h0[16 * m], ah[m][0], al[m][0]);
-        split_tf32(h0[16 * m + 8], ah[m][1], al[m][1]);
-        split_tf32(h1[16 * m], ah[m][2], al[m][2]);
-        split_tf32(h1[16 * m + 8], ah[m][3], al[m][3]);
+        split_fast(h0[16 * m], ah[m][0], al[m][0]);
+        split_fast(h0[16 * m + 8], ah[m][1], al[m][1]);
+        split_fast(h1[16 * m], ah[m][2], al[m][2]);
+        split_fast(h1[16 * m + 8], ah[m][3], al[m][3]);
       }
       const float* d0 = ds + (ks * 8 + t) * kDS + g;
       const float* d1 = d0 + 4 * kDS;
 #pragma unroll
       for (int j = 0; j < kNT; j++) {
         uint32_t bh0, bl0, bh1, bl1;
-        split_tf32(d0[8 * j], bh0, bl0);
-        split_tf32(d1[8 * j], bh1, bl1);
+        split_fast(d0[8 * j], bh0, bl0);
+        split_fast(d1[8 * j], bh1, bl1);
 #pragma unroll
         for (int m = 0; m < 2; m++) mma_3x(acc[m][j], ah[m], al[m], bh0, bh1, bl0, bl1);
       }
@@ -417,7 +577,34 @@ static int launch_rows(const float* A, long long lda, long long rows, int Kc_tot
   const long long tiles16 = (rows + 15) / 16;
   const int gx = (int)max(1LL, min((long long)sms, (tiles16 + kWarps - 1) / kWarps));
   const int gy = (N + kNB - 1) / kNB;
-  NASR_CUDA((ensure_max_dynamic_smem<affine_rows_kernel>(227 * 1024)));
+  if (Kc_total <= kSmallK) {
+    RowsParams p;
+    p.Kc = Kc_total;
+    p.A = A;
+    p.lda = lda;
+    p.rows = rows;
+    p.W = W;
+    p.w_sn = w_sn;
+    p.w_sk = w_sk;
+    p.N = N;
+    p.bias = bias;
+    p.out = out;
+    p.ldo = ldo;
+    p.accumulate = 0;
+    p.kstride = kSmallK;
+    p.vec_a = (((uintptr_t)A & 7) == 0) && (lda % 2 == 0);
+    p.vec_o = (((uintptr_t)out & 7) == 0) && (ldo % 2 == 0);
+    const int nb_total = (N + kNB - 1) / kNB;
+    const int gy_s = (nb_total + kSmallBlocks - 1) / kSmallBlocks;
+    const size_t smem = (size_t)2 * min(nb_total, kSmallBlocks) * kNB * kSmallK * sizeof(uint32_t);
+    NASR_CUDA((ensure_max_dynamic_smem<affine_smallk_kernel>(227 * 1024)));
+    affine_smallk_kernel<<<dim3(gx, gy_s), kThreads, smem, stream>>>(p);
+    count_launch();
+    NASR_CUDA(cudaGetLastError());
+    return NASR_OK;
+  }
+  NASR_CUDA((ensure_max_dynamic_smem<affine_rows_kernel<16>>(227 * 1024)));
+  NASR_CUDA((ensure_max_dynamic_smem<affine_rows_kernel<8>>(227 * 1024)));
   for (int kseg = 0; kseg < Kc_total; kseg += kMaxSeg) {
     RowsParams p;
     p.Kc = min(kMaxSeg, Kc_total - kseg);
@@ -432,11 +619,16 @@ static int launch_rows(const float* A, long long lda, long long rows, int Kc_tot
     p.out = out;
     p.ldo = ldo;
     p.accumulate = kseg > 0;
-    p.kstride = ((p.Kc + 31) & ~31) + 16;
-    p.vec_a = (((uintptr_t)p.A & 15) == 0) && (lda % 4 == 0);
+    // 16-byte loads of A where its rows allow them and are long enough to pay; otherwise 8-byte steps
+    const bool mode16 = (((uintptr_t)p.A & 15) == 0) && (lda % 4 == 0) && p.Kc >= 64;
+    p.vec_a = mode16 ? 1 : ((((uintptr_t)p.A & 7) == 0) && (lda % 2 == 0));
+    // floats per staged Wt row: the fragment loads of 8 rows must hit every bank once (16 mod 32 for 16-byte loads,
+    // 8 mod 32 for 8-byte loads)
+    p.kstride = ((p.Kc + 31) & ~31) + (mode16 ? 16 : 8);
     p.vec_o = (((uintptr_t)out & 7) == 0) && (ldo % 2 == 0);
     const size_t smem = (size_t)2 * kNB * p.kstride * sizeof(uint32_t);
-    affine_rows_kernel<<<dim3(gx, gy), kThreads, smem, stream>>>(p);
+    if (mode16) affine_rows_kernel<16><<<dim3(gx, gy), kThreads, smem, stream>>>(p);
+    else affine_rows_kernel<8><<<dim3(gx, gy), kThreads, smem, stream>>>(p);
     count_launch();
     NASR_CUDA(cudaGetLastError());
   }
