@@ -448,6 +448,15 @@ def run_ours(args, w, rank, world, local_rank):
         except Exception as e:  # a context number, never a reason to fail the bench
             lib_base = {"unavailable": repr(e)[:200]}
 
+    # ---- the model tail's affine projection in front of the loss (bilstm_ctc_net.py:33-45: K = 500):
+    #      forward, dH, dW + db on B*T rows, two rotating H sets (2 x 4*rows*K bytes > L2), against the HBM roofline
+    proj = None
+    if rank == 0:
+        try:
+            proj = projection_record(common, dev, B * T, 500, C)
+        except Exception as e:  # a secondary record: never a reason to fail the headline
+            proj = {"unavailable": repr(e)[:200]}
+
     if rank == 0:
         peak, peak_kind = hbm_peak()
         k_ms = statistics.mean(kern_ms)
@@ -485,9 +494,53 @@ def run_ours(args, w, rank, world, local_rank):
             "beam_search": beam,
             "e2e_train_step": train_step,
             "library_baseline": lib_base,
+            "projection": proj,
         }))
     if world > 1:
         dist.destroy_process_group()
+
+
+def projection_record(common, dev, rows, K, C):
+    """ms per call and fraction of the HBM peak of nasr_affine_logits_f32 / nasr_affine_backward_f32."""
+    import torch
+    peak, _ = hbm_peak()
+    rows = min(rows, 512000)                       # two H sets of at most 1 GB each
+    g = torch.Generator(device=dev).manual_seed(7)
+    Hs = [torch.randn((rows, K), device=dev, generator=g) for _ in range(2)]
+    W = torch.randn((K, C), device=dev, generator=g) / K ** 0.5
+    b = torch.zeros((C,), device=dev)
+    dL = torch.randn((rows, C), device=dev, generator=g)
+    out = torch.empty((rows, C), device=dev)
+
+    def timed(fn, n=10):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n):
+            fn(i)
+        e.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(e) / n
+
+    rec = {"rows": rows, "K": K, "C": C, "arithmetic": "3xTF32 mma.sync, float32 accumulation",
+           "l2": "two rotating H sets (%.0f MB) > 126 MB L2" % (2 * 4 * rows * K / 1e6)}
+    for name, fn, nbytes in (
+            ("forward", lambda i: common.affine_logits(Hs[i & 1], W, b, out=out), 4 * (rows * K + rows * C + K * C)),
+            ("backward_dH", lambda i: common.affine_backward(Hs[i & 1], W, dL, True, False, False), 4 * (rows * K + rows * C)),
+            ("backward_dW_db", lambda i: common.affine_backward(Hs[i & 1], W, dL, False, True, True), 4 * (rows * K + rows * C))):
+        ms = timed(fn)
+        rec[name] = {"ms": ms, "algorithmic_gbs": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak}
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        rec["library_fp32"] = {"forward_ms": timed(lambda i: torch.addmm(b, Hs[i & 1], W, out=out)),
+                               "backward_ms": timed(lambda i: (torch.mm(dL, W.t()), torch.mm(Hs[i & 1].t(), dL), dL.sum(0))),
+                               "what": "torch.addmm / torch.mm float32 (TF32 off) on the same tensors"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return rec
 
 
 def main():
