@@ -200,6 +200,11 @@ greedy_argmax_wide_kernel(const float* __restrict__ logits, int T, int C, long l
 // s-w at step s), so the hand-off is one shuffle per step and the whole utterance takes |hyp| + W - 1 steps
 // instead of the |hyp| + |truth| barrier-separated anti-diagonals of the plain DP.  Match masks Peq[sym][w]
 // live in shared memory, indexed by symbol value.  Exact integers (tests compare with the oracle bit for bit).
+// Truths of up to 512 symbols run TWO-ENDED: half the warp takes the first half of the hypothesis, the other half the
+// reversed second half against the reversed truth, and the two last columns are joined (see below) -- the chain of
+// dependent steps, which is what the kernel's time is (one warp per utterance, ~300 cycles per step), halves.
+// (Measured and dropped: staging the hypothesis in shared memory, 0.128 -> 0.27 ms; a skew of two symbols per lane
+// to take the shuffle off the chain, 0.128 -> 0.140 ms.)
 // Slow path (truth longer than 1024 symbols, or symbol values too large for the table): anti-diagonal
 // wavefront, three diagonals and both strings in shared memory.
 template <typename HypT>
@@ -240,37 +245,56 @@ edit_distance_kernel(const HypT* __restrict__ hyp, long hyp_stride, const int32_
     mn = __reduce_min_sync(0xffffffffu, mn);
     const long long need = (long long)(mx + 1) * W;
     if (W <= 32 && mn >= 0 && need <= table_words) {
-      unsigned* peq = reinterpret_cast<unsigned*>(sm);  // [sym][W]
+      unsigned* peq = reinterpret_cast<unsigned*>(sm);  // [direction][sym][W]
       const int nsym = mx + 1;
-      for (int i = lane; i < nsym * W; i += 32) peq[i] = 0u;
+      // Two-ended run (truths up to 512 symbols): lanes 0-15 take the first half of the hypothesis against the truth,
+      // lanes 16-31 the REVERSED second half against the reversed truth, in the same instruction stream; the distance
+      // is min over j of D_fwd[j] + D_bwd[m-j], the last columns of the two halves, which the vertical deltas of the
+      // bit vectors spell out.  Halves the chain of |hyp| dependent steps (cfg3: 128 -> 70 us).
+      const bool two = W <= 16 && n >= 32 && 2 * need + 2 * ((long long)m + 1) <= table_words;
+      const int ntab = two ? 2 : 1;
+      for (int i = lane; i < ntab * nsym * W; i += 32) peq[i] = 0u;
       __syncwarp();
-      for (int j = lane; j < m; j += 32) atomicOr(&peq[truth_values[t0 + j] * W + (j >> 5)], 1u << (j & 31));
+      for (int j = lane; j < m; j += 32) {
+        const int v = truth_values[t0 + j];
+        atomicOr(&peq[v * W + (j >> 5)], 1u << (j & 31));
+        if (two) {
+          const int jr = m - 1 - j;
+          atomicOr(&peq[(nsym + v) * W + (jr >> 5)], 1u << (jr & 31));
+        }
+      }
       __syncwarp();
+      const int GW = two ? 16 : 32;                 // lanes per direction
+      const int dir = two ? (lane >> 4) : 0, w = lane & (GW - 1);
+      const int n1 = two ? n - n / 2 : n;           // symbols of the forward half (>= the backward half's)
+      const int nd = dir ? n - n1 : n1;
+      const unsigned* tab = peq + dir * nsym * W;
       unsigned Pv = 0xffffffffu, Mv = 0u;
       int score = m;
       const int lastw = W - 1;
-      const int topbit = lane == lastw ? ((m - 1) & 31) : 31;
+      const int topbit = w == lastw ? ((m - 1) & 31) : 31;
       int hout = 0;
-      long long cnext = (lane == 0) ? (long long)h[0] : 0;
-      const int steps = n + W - 1;
+      // symbol i of this lane's direction: forward h[i], backward h[n-1-i]
+      long long cnext = (w == 0 && nd > 0) ? (long long)h[dir ? n - 1 : 0] : 0;
+      const int steps = n1 + W - 1;
       for (int s = 0; s < steps; s++) {
-        const int hin_up = __shfl_up_sync(0xffffffffu, hout, 1);
-        const int i = s - lane;
-        const bool active = lane < W && i >= 0 && i < n;
+        const int hin_up = __shfl_up_sync(0xffffffffu, hout, 1, GW);
+        const int i = s - w;
+        const bool active = w < W && i >= 0 && i < nd;
         const long long c = cnext;
-        // prefetch the symbol of the next step (lane w reads hyp[s+1-w])
+        // prefetch the symbol of the next step (lane w reads symbol s+1-w)
         const int inext = i + 1;
-        if (lane < W && inext >= 0 && inext < n) cnext = (long long)h[inext];
+        if (w < W && inext >= 0 && inext < nd) cnext = (long long)h[dir ? n - 1 - inext : inext];
         if (active) {
-          const int hin = lane == 0 ? 1 : hin_up;
-          unsigned Eq = (c >= 0 && c < nsym) ? peq[(int)c * W + lane] : 0u;
+          const int hin = w == 0 ? 1 : hin_up;
+          unsigned Eq = (c >= 0 && c < nsym) ? tab[(int)c * W + w] : 0u;
           const unsigned Xv = Eq | Mv;
           if (hin < 0) Eq |= 1u;
           const unsigned Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
           unsigned Ph = Mv | ~(Xh | Pv);
           unsigned Mh = Pv & Xh;
           hout = (int)((Ph >> topbit) & 1u) - (int)((Mh >> topbit) & 1u);
-          if (lane == lastw) score += hout;
+          if (w == lastw) score += hout;
           Ph <<= 1;
           Mh <<= 1;
           if (hin < 0) Mh |= 1u;
@@ -279,7 +303,33 @@ edit_distance_kernel(const HypT* __restrict__ hyp, long hyp_stride, const int32_
           Mv = Ph & Xv;
         }
       }
-      d = __shfl_sync(0xffffffffu, score, lastw);
+      if (!two) {
+        d = __shfl_sync(0xffffffffu, score, lastw);
+      } else {
+        // last column of each half: D[0] = symbols consumed, D[j+1] - D[j] = (Pv bit j) - (Mv bit j)
+        int* Df = sm + 2 * nsym * W;    // [m + 1]
+        int* Db = Df + m + 1;           // [m + 1]
+        const int nb = w < W ? min(32, m - 32 * w) : 0;
+        const unsigned valid = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
+        const int delta = __popc(Pv & valid) - __popc(Mv & valid);
+        int incl = delta;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, incl, o, 16);
+          if (w >= o) incl += up;
+        }
+        int* D = dir ? Db : Df;
+        int v = nd + incl - delta;      // D[32 w]
+        for (int bit = 0; bit < nb; bit++) {
+          D[32 * w + bit] = v;
+          v += (int)((Pv >> bit) & 1u) - (int)((Mv >> bit) & 1u);
+        }
+        if (w == lastw) D[m] = v;
+        __syncwarp();
+        int best = 0x7fffffff;
+        for (int j = lane; j <= m; j += 32) best = min(best, Df[j] + Db[m - j]);
+        d = __reduce_min_sync(0xffffffffu, best);
+      }
     } else {
       int* tr = sm;                       // [max_truth_len]
       int* hy = tr + max_truth_len;       // [max_hyp_len]
