@@ -266,8 +266,10 @@ def run_ours(args, w, rank, world, local_rank):
     launches0 = _lib.launch_count()
     t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
+    host_t0 = time.perf_counter()
     for i in range(args.steps):
         sums = step(args.warmup + i, evs[i])
+    host_loop_s = time.perf_counter() - host_t0     # host time to enqueue the K steps (launch-bound if ~ the device time)
     for wk in pending:
         wk.wait()              # the compute stream now waits for every step's reduction
     pending.clear()
@@ -280,7 +282,16 @@ def run_ours(args, w, rank, world, local_rank):
     ms_total = t_start.elapsed_time(t_stop)
     kern_ms = [a.elapsed_time(b) for a, b in evs]
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        # every rank's own numbers, for the record: its timed region, its mean kernel time, its host loop time per step
+        mine = torch.tensor([ms_total / args.steps, statistics.mean(kern_ms), host_loop_s / args.steps * 1e3],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [round(float(a[0]), 4) for a in allr],
+                    "kernel_ms": [round(float(a[1]), 4) for a in allr],
+                    "host_loop_ms_per_step": [round(float(a[2]), 4) for a in allr]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     mean_loss = float(sums[0].item() / sums[3].item())
@@ -479,6 +490,7 @@ def run_ours(args, w, rank, world, local_rank):
             "notes": {"l2": "%d rotating logits/grad sets (%.0f MB) > 126 MB L2" % (nsets, nsets * set_bytes / 1e6),
                       "mean_loss": mean_loss},
             "strong_scaling": strong,
+            "per_rank": per_rank,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                          "kernel": "ctc_fast_kernel + ctc_robust_kernel retry pass (both launches of nasr_ctc_loss_grad_f32)",
