@@ -57,6 +57,20 @@ class CtcHead:
         ler = common.label_error_rate(model, lab)
         return loss, model, log_prob, ler
 
+    def create_network(self, outputs, W, b, labels, seq_len, batch_size):
+        """What ``create_network`` of the reference's CTC models does after the recurrent layers
+        (``bilstm_ctc_net.py:31-52``, ``lstm_ctc_net.py:26-47``): reshape the outputs to ``[-1, num_hidden]``, the affine
+        projection ``outputs . W + b``, reshape to ``[batch_s, -1, num_classes]``, time-major, then the three helpers.
+        Returns the reference's five values ``(logits, loss, model, prob, ler)``; ``logits`` is the time-major view of
+        the batch-major projection result (no transpose is executed) and the loss backpropagates to ``outputs``, ``W``
+        and ``b``."""
+        logits = common.affine_projection(outputs, W, b, batch_size)
+        lab = common.prepare_labels(labels, logits.device)
+        loss = common.loss(logits, lab, seq_len)
+        model, log_prob = self.create_model(logits.detach(), seq_len)
+        ler = common.label_error_rate(model, lab)
+        return logits, loss, model, log_prob, ler
+
     def _scalars(self, loss, ler):
         sums = common.batch_sums(loss_b=loss.per_utterance, ler=ler.per_utterance, dist=ler.distances)
         mean_loss, mean_ler, _, _ = towers.step_scalars(towers.all_reduce_sums(sums))

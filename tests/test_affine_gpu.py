@@ -145,3 +145,35 @@ def test_full_size_linearity_cfg3_rows():
     assert np.all(np.abs(db.cpu().numpy() - dL.double().sum(0).cpu().numpy()) <= 2e-6 * dL.double().abs().sum(0).cpu().numpy())
     dLs = dL[idx].cpu().numpy()
     _close(dH[idx].cpu().numpy(), dLs.astype(np.float64) @ Wn.T.astype(np.float64), np.abs(dLs).astype(np.float64) @ np.abs(Wn).T)
+
+
+def test_create_network_returns_the_reference_five_values():
+    """steps.CtcHead.create_network = bilstm_ctc_net.py:31-52 after the recurrent layers: (logits, loss, model, prob,
+    ler), each against the oracle chain (greedy decoder)."""
+    from neuralasr_b200.steps import CtcHead
+    from neuralasr_b200.utils import sparse_tuple_from
+    from oracle import c_oracle
+    rng = np.random.default_rng(9)
+    B, T, K, C, Lmax = 4, 40, 500, 38, 8
+    outputs = rng.standard_normal((B, T, K)).astype(np.float32)
+    W = (rng.standard_normal((K, C)) * (3.0 / np.sqrt(K))).astype(np.float32)
+    b = (rng.standard_normal(C) * 0.1).astype(np.float32)
+    lens = rng.integers(1, Lmax + 1, size=B)
+    labels = sparse_tuple_from(rng.integers(0, C - 1, size=(B, Lmax)), lens)
+    seq = np.array([T, T, 31, T], np.int32)
+    head = CtcHead(decoder="greedy")
+    logits, loss, model, prob, ler = head.create_network(torch.from_numpy(outputs).cuda(), torch.from_numpy(W).cuda(),
+                                                         torch.from_numpy(b).cuda(), labels, seq, B)
+    torch.cuda.synchronize()
+    want_logits = ao.tail(outputs, W, b, B)
+    assert tuple(logits.shape) == (T, B, C) and np.abs(logits.cpu().numpy() - want_logits).max() < 1e-4
+    x32 = np.ascontiguousarray(logits.cpu().numpy())        # decode on the kernel's own float32 logits: bit-exact ids
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    want_loss, _, _ = c_oracle.ctc_loss_grad(x32, labels[1], offs, seq, precision="f64")
+    assert np.allclose(loss.per_utterance.cpu().numpy(), want_loss, rtol=1e-4)
+    hv, ho, nsl = c_oracle.greedy_decode(x32, seq)
+    assert np.array_equal(model.values.cpu().numpy(), hv)
+    assert np.allclose(prob[:, 0].cpu().numpy(), nsl, rtol=1e-6)
+    want_d, want_ler = c_oracle.edit_distance(hv, ho, labels[1], offs)
+    assert np.array_equal(ler.distances.cpu().numpy(), want_d)
+    assert abs(float(ler) - float(np.asarray(want_ler, np.float64).mean())) < 1e-6
