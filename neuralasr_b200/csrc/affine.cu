@@ -24,6 +24,8 @@
 //                        rows through a three-stage cp.async ring (32 rows of H and dL per stage), every warp owns 32
 //                        of the 512 k of a block as accumulators; per-CTA partials go to the workspace and
 //                        affine_reduce_kernel adds them in a fixed order (deterministic, no atomics).
+#include <cstdlib>
+
 #include "nasr_common.cuh"
 
 namespace nasr {
@@ -710,7 +712,22 @@ int backward(const float* H, long long rows, int K, long long ldh, const float* 
 }  // namespace affine
 }  // namespace nasr
 
+namespace nasr {
+namespace affine_tc {   // csrc/affine_tc.cu: the tcgen05 / TMA / TMEM forward
+bool eligible(const float* H, long long rows, int K, long long ldh, int C);
+int forward(const float* H, long long rows, int K, long long ldh, const float* W, const float* bias, int C,
+            float* logits, long long ldl, cudaStream_t stream);
+}  // namespace affine_tc
+}  // namespace nasr
+
 using namespace nasr;
+
+// The forward runs on the tcgen05 kernel (csrc/affine_tc.cu) wherever its shape rules allow; NASR_AFFINE_TC=0 in the
+// environment (read at every call: tests switch it) keeps everything on the mma.sync kernels.
+static bool use_tcgen05() {
+  const char* e = getenv("NASR_AFFINE_TC");
+  return !(e && e[0] == '0');
+}
 
 int nasr_affine_workspace_bytes(long long rows, int K, int C, size_t* out_bytes) {
   NASR_CHECK_ARG(out_bytes, "nasr_affine_workspace_bytes: out_bytes is NULL");
@@ -725,6 +742,8 @@ int nasr_affine_logits_f32(const float* H, long long rows, int K, long long ldh,
   NASR_CHECK_ARG(ldh >= K && ldl >= C, "nasr_affine_logits_f32: row strides ldh=%lld ldl=%lld shorter than a row",
                  ldh, ldl);
   NASR_CHECK_ARG(W && (rows == 0 || (H && logits)), "nasr_affine_logits_f32: NULL argument");
+  if (use_tcgen05() && affine_tc::eligible(H, rows, K, ldh, C))
+    return affine_tc::forward(H, rows, K, ldh, W, bias, C, logits, ldl, static_cast<cudaStream_t>(stream));
   return affine::forward(H, rows, K, ldh, W, bias, C, logits, ldl, static_cast<cudaStream_t>(stream));
 }
 

@@ -25,10 +25,19 @@ def _case(seed, rows, K, C, scale=1.0):
     return H, W, b
 
 
+@pytest.fixture(params=["tcgen05", "mma.sync"])
+def forward_path(request, monkeypatch):
+    """The forward has two kernels: the tcgen05 / TMA / TMEM one (csrc/affine_tc.cu; C <= 40, 16-byte aligned rows, at
+    least 64 rows and 32 k) and the mma.sync one that takes everything else.  NASR_AFFINE_TC=0 forces the second."""
+    monkeypatch.setenv("NASR_AFFINE_TC", "1" if request.param == "tcgen05" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("rows,K,C", [(1, 1, 1), (16, 8, 8), (37, 500, 38), (1000, 500, 38), (4099, 500, 38),
                                         (130, 13, 5), (257, 100, 41), (300, 700, 38), (64, 1500, 7),
-                                        (500, 500, 1024), (333, 250, 129)])
-def test_forward_matches_oracle(rows, K, C):
+                                        (500, 500, 1024), (333, 250, 129), (64, 32, 40), (129, 257, 1),
+                                        (20000, 500, 38)])
+def test_forward_matches_oracle(rows, K, C, forward_path):
     from neuralasr_b200.networks import common
     H, W, b = _case(rows * 7 + K + C, rows, K, C)
     got = common.affine_logits(torch.from_numpy(H).cuda(), torch.from_numpy(W).cuda(), torch.from_numpy(b).cuda())
@@ -63,13 +72,18 @@ def test_backward_matches_oracle(rows, K, C):
     assert torch.equal(only_dW, dW)          # deterministic: per-CTA partials added in a fixed order
 
 
-def test_strided_and_misaligned_rows():
+def test_strided_and_misaligned_rows(forward_path):
     from neuralasr_b200.networks import common
     H, W, b = _case(11, 200, 500, 38)
     big = torch.zeros((200, 503), dtype=torch.float32, device="cuda")
     view = big[:, 1:501]                                  # rows start 4 bytes off a 16-byte boundary, stride 503
     view.copy_(torch.from_numpy(H))
     got = common.affine_logits(view, torch.from_numpy(W).cuda(), torch.from_numpy(b).cuda())
+    _close(got.cpu().numpy(), ao.affine_logits(H, W, b), np.abs(H).astype(np.float64) @ np.abs(W) + np.abs(b))
+    wide = torch.zeros((200, 504), dtype=torch.float32, device="cuda")
+    aligned = wide[:, 4:504]                              # 16-byte aligned rows at stride 504: a strided tensor map
+    aligned.copy_(torch.from_numpy(H))
+    got = common.affine_logits(aligned, torch.from_numpy(W).cuda(), torch.from_numpy(b).cuda())
     _close(got.cpu().numpy(), ao.affine_logits(H, W, b), np.abs(H).astype(np.float64) @ np.abs(W) + np.abs(b))
     out = torch.zeros((200, 39), dtype=torch.float32, device="cuda")[:, :38]   # odd row stride: scalar stores
     common.affine_logits(view, torch.from_numpy(W).cuda(), torch.from_numpy(b).cuda(), out=out)
@@ -122,7 +136,7 @@ def test_tail_feeds_the_loss_without_a_transpose_and_backpropagates():
     assert np.abs(both.cpu().numpy() - want).max() < 1e-4
 
 
-def test_full_size_linearity_cfg3_rows():
+def test_full_size_linearity_cfg3_rows(forward_path):
     """BASELINE cfg3's row count (B*T = 256000, K = 500, C = 38), size-independent properties: linearity in H,
     the bias reaching every row, 4096 sampled rows against the oracle, and dW against the oracle on the whole batch."""
     from neuralasr_b200.networks import common
