@@ -512,6 +512,19 @@ def run_ours(args, w, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def _forward_mma_sync(common, H, W, b, out):
+    """The forward on the mma.sync kernel (what shapes outside the tcgen05 kernel's rules get), for comparison."""
+    prev = os.environ.get("NASR_AFFINE_TC")
+    os.environ["NASR_AFFINE_TC"] = "0"
+    try:
+        return common.affine_logits(H, W, b, out=out)
+    finally:
+        if prev is None:
+            del os.environ["NASR_AFFINE_TC"]
+        else:
+            os.environ["NASR_AFFINE_TC"] = prev
+
+
 def projection_record(common, dev, rows, K, C):
     """ms per call and fraction of the HBM peak of nasr_affine_logits_f32 / nasr_affine_backward_f32."""
     import torch
@@ -536,10 +549,12 @@ def projection_record(common, dev, rows, K, C):
         torch.cuda.synchronize()
         return a.elapsed_time(e) / n
 
-    rec = {"rows": rows, "K": K, "C": C, "arithmetic": "3xTF32 mma.sync, float32 accumulation",
+    rec = {"rows": rows, "K": K, "C": C,
+           "arithmetic": "3xTF32, float32 accumulation: forward on tcgen05 (TMA + TMEM, csrc/affine_tc.cu), backward on mma.sync",
            "l2": "two rotating H sets (%.0f MB) > 126 MB L2" % (2 * 4 * rows * K / 1e6)}
     for name, fn, nbytes in (
             ("forward", lambda i: common.affine_logits(Hs[i & 1], W, b, out=out), 4 * (rows * K + rows * C + K * C)),
+            ("forward_mma_sync", lambda i: _forward_mma_sync(common, Hs[i & 1], W, b, out), 4 * (rows * K + rows * C + K * C)),
             ("backward_dH", lambda i: common.affine_backward(Hs[i & 1], W, dL, True, False, False), 4 * (rows * K + rows * C)),
             ("backward_dW_db", lambda i: common.affine_backward(Hs[i & 1], W, dL, False, True, True), 4 * (rows * K + rows * C))):
         ms = timed(fn)
