@@ -32,23 +32,27 @@ namespace affine_tc {
 
 constexpr int kThreads = 320;
 #ifndef TC_BM
-#define TC_BM 64
+#define TC_BM 128   // 128: the shipped kernel (low tile of H in TMEM); 64: both tiles in shared memory (measured: 0.166 ms)
 #endif
 constexpr int kBM = TC_BM;              // rows per tile (UMMA M)
 constexpr int kBN = TC_BM == 128 ? 48 : 40;   // classes (UMMA N: a multiple of 8 at M = 64, of 16 at M = 128)
 constexpr int kBK = 32;                 // k per stage: 128 bytes, one swizzle span
 constexpr int kPassBlocks = 8;          // k-blocks per pass (256 k)
-constexpr int kStages = TC_BM == 128 ? 3 : 8;
+constexpr bool kLoInTmem = TC_BM == 128;  // the low tile of H in TMEM (A operand from TMEM) instead of shared memory
+constexpr int kStages = kLoInTmem ? 6 : 8;
+constexpr int kLoSlots = 4;             // TMEM ring of low tiles (32 columns each)
 constexpr int kATile = kBM * kBK * 4;   // 8192
 constexpr int kBTile = kBN * kBK * 4;   // 5120 (five 8-row groups of 1024 bytes)
 constexpr int kAccCols = 128;           // columns of one accumulator slot: [H.W_hi | H_raw.W_lo], 2 * kBN <= 128
-constexpr int kTmemCols = 2 * kAccCols; // two accumulators
+constexpr int kTmemCols = kLoInTmem ? 512 : 2 * kAccCols;   // two accumulators (+ the low tiles at column 256)
+constexpr int kLoCol0 = 2 * kAccCols;
 
 // shared memory map (offsets from a 1024-byte aligned base)
 constexpr int kOffBhi = 0;
 constexpr int kOffA = kOffBhi + kPassBlocks * 2 * kBTile;          // W: [k-block][hi tile | lo tile]; then H: [stage][raw | lo]
-constexpr int kOffBar = kOffA + kStages * 2 * kATile;
-constexpr int kNumBars = 3 * kStages + 4;                           // full_raw, full_lo, empty per stage; tmem full/empty x2
+constexpr int kStageBytes = kLoInTmem ? kATile : 2 * kATile;       // raw tile (+ low tile)
+constexpr int kOffBar = kOffA + kStages * kStageBytes;
+constexpr int kNumBars = 3 * kStages + 4 + kLoSlots;                // full_raw, full_lo, empty per stage; tmem full/empty x2; lo_empty
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr int kOffBias = kOffTmemPtr + 16;                          // [kBN] floats (zeros without a bias)
 constexpr int kOffOut = (kOffBias + 64 * 4 + 15) & ~15;              // [64][C] floats: the tile's logits before they leave
@@ -100,6 +104,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc_v), "r"(accumulate), "r"(0u)
       : "memory");
 }
+// A operand from TMEM
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc_v,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc_v), "r"(accumulate), "r"(0u)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -121,7 +137,7 @@ struct Params {
   float* out;
   long long ldo;
   int vec16;              // out 16-byte aligned and 64 rows of C floats a multiple of 16 bytes
-  int debug;              // tuning: 1 converters idle, 4 no stores (results wrong), 8 role cycle counters of CTA 0
+  int debug;              // tuning: 4 no stores (results wrong), 8 role cycle counters of CTA 0
 };
 
 __global__ void __launch_bounds__(kThreads, 1) affine_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const Params p) {
@@ -135,6 +151,7 @@ __global__ void __launch_bounds__(kThreads, 1) affine_tc_kernel(const __grid_con
   auto empty = [&](int s) { return bar0 + 8u * (2 * kStages + s); };
   auto tmem_full = [&](int a) { return bar0 + 8u * (3 * kStages + a); };
   auto tmem_empty = [&](int a) { return bar0 + 8u * (3 * kStages + 2 + a); };
+  auto lo_empty = [&](int t) { return bar0 + 8u * (3 * kStages + 4 + t); };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kOffTmemPtr);
 
   // ---- one-time setup ------------------------------------------------------------------------------------------
@@ -149,6 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1) affine_tc_kernel(const __grid_con
       mbar_init(tmem_full(a), 1);
       mbar_init(tmem_empty(a), 128);
     }
+    for (int t = 0; t < kLoSlots; t++) mbar_init(lo_empty(t), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -159,8 +177,8 @@ __global__ void __launch_bounds__(kThreads, 1) affine_tc_kernel(const __grid_con
   }
   const long long ntiles = (p.rows + kBM - 1) / kBM;
   // ring / accumulator state of this thread's role: it runs on across the passes
-  int s = 0, acc = 0;
-  uint32_t ph = 0, acc_ph[2] = {0, 0};
+  int s = 0, acc = 0, lt = 0;
+  uint32_t ph = 0, acc_ph[2] = {0, 0}, lph = 0;
   long long pw = 0, mw = 0, mi = 0, me = 0, cw = 0, cc = 0, ew = 0, ec = 0;
   const long long pstart = clock64();
   uint32_t tmem_base = 0;
@@ -218,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) affine_tc_kernel(const __grid_con
           pw += clock64() - t0;
           if (elect_one()) {
             mbar_expect_tx(full_raw(s), kATile);
-            const uint32_t dst = sbase + kOffA + s * 2 * kATile;
+            const uint32_t dst = sbase + kOffA + s * kStageBytes;
             const int c0 = k0 + kb * kBK, c1 = (int)(tile * kBM);
             asm volatile(
                 "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
@@ -249,11 +267,12 @@ __global__ void __launch_bounds__(kThreads, 1) affine_tc_kernel(const __grid_con
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
         for (int kb = 0; kb < nkb; kb++) {
           const long long t0 = clock64();
-          mbar_wait(full_lo(s), ph);
+          mbar_wait(full_lo(kLoInTmem ? lt : s), kLoInTmem ? lph : ph);
           const long long t1 = clock64();
           mw += t1 - t0;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_raw = a_desc0 + (uint32_t)s * (2 * kATile >> 4), a_lo = a_raw + (kATile >> 4);
+          const uint32_t a_raw = a_desc0 + (uint32_t)s * (kStageBytes >> 4), a_lo = a_raw + (kATile >> 4);
+          const uint32_t a_lo_tmem = tmem_base + (uint32_t)(kLoCol0 + 32 * lt);
           const uint32_t b_hi = b_desc0 + (uint32_t)kb * (2 * kBTile >> 4);   // the lo tile follows the hi tile
           if (elect_one()) {
 #pragma unroll
@@ -262,10 +281,16 @@ __global__ void __launch_bounds__(kThreads, 1) affine_tc_kernel(const __grid_con
               // columns [0, N): H_raw.W_hi, columns [N, 2N): H_raw.W_lo -- ONE product over the stacked W tile
               umma_tf32(d_tmem, make_desc(a_raw + ko), make_desc(b_hi + ko), kIdesc2N, (kb | k8) ? 1u : 0u);
               // columns [0, N) += H_lo.W_hi
-              umma_tf32(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), kIdescN, 1u);
+              if (kLoInTmem) umma_tf32_ts(d_tmem, a_lo_tmem + 8 * k8, make_desc(b_hi + ko), kIdescN, 1u);
+              else umma_tf32(d_tmem, make_desc(a_lo + ko), make_desc(b_hi + ko), kIdescN, 1u);
             }
-          umma_commit(empty(s));            // the stage is free once these products have read it
-          if (kb == nkb - 1) umma_commit(tmem_full(acc));
+            umma_commit(empty(s));            // the stage is free once these products have read it
+            if (kLoInTmem) umma_commit(lo_empty(lt));
+            if (kb == nkb - 1) umma_commit(tmem_full(acc));
+          }
+          if (++lt == kLoSlots) {
+            lt = 0;
+            lph ^= 1;
           }
           __syncwarp();
           mi += clock64() - t1;
@@ -292,14 +317,39 @@ __global__ void __launch_bounds__(kThreads, 1) affine_tc_kernel(const __grid_con
         mbar_wait(full_raw(s), ph);
         const long long t1 = clock64();
         cw += t1 - t0;
-        if (p.debug & 1) {
-          mbar_arrive(full_lo(s));
-          if (++s == kStages) {
-            s = 0;
-            ph ^= 1;
+        if (kLoInTmem) {
+          // thread = row of the tile = TMEM lane (a warp reaches the 32 lanes of its own sub-partition): the row's 32 k
+          // from the swizzled raw tile, their low parts into 32 TMEM columns of the ring slot
+          mbar_wait(lo_empty(lt), lph ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const int r = 32 * (warp & 3) + lane;
+          const uint8_t* rowp = smem + kOffA + s * kStageBytes + r * 128;
+          uint32_t lo[32];
+#pragma unroll
+          for (int c = 0; c < 8; c++) {
+            const float4 v = *reinterpret_cast<const float4*>(rowp + (((c ^ (r & 7)) & 7) << 4));
+            lo[4 * c + 0] = (__float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
+            lo[4 * c + 1] = (__float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
+            lo[4 * c + 2] = (__float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
+            lo[4 * c + 3] = (__float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u)) + 0x1000u) & 0xffffe000u;
           }
-          continue;
-        }
+          const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(kLoCol0 + 32 * lt);
+          asm volatile(
+              "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+              "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+              "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]), "r"(lo[8]),
+              "r"(lo[9]), "r"(lo[10]), "r"(lo[11]), "r"(lo[12]), "r"(lo[13]), "r"(lo[14]), "r"(lo[15]), "r"(lo[16]),
+              "r"(lo[17]), "r"(lo[18]), "r"(lo[19]), "r"(lo[20]), "r"(lo[21]), "r"(lo[22]), "r"(lo[23]), "r"(lo[24]),
+              "r"(lo[25]), "r"(lo[26]), "r"(lo[27]), "r"(lo[28]), "r"(lo[29]), "r"(lo[30]), "r"(lo[31])
+              : "memory");
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(full_lo(lt));
+          if (++lt == kLoSlots) {
+            lt = 0;
+            lph ^= 1;
+          }
+        } else {
         const float4* src = reinterpret_cast<const float4*>(smem + kOffA + s * 2 * kATile);
         float4* dst = reinterpret_cast<float4*>(smem + kOffA + s * 2 * kATile + kATile);
 #pragma unroll
@@ -315,6 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1) affine_tc_kernel(const __grid_con
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(full_lo(s));
+        }
         cc += clock64() - t1;
         if (++s == kStages) {
           s = 0;

@@ -28,7 +28,7 @@ def _case(seed, rows, K, C, scale=1.0):
 @pytest.fixture(params=["tcgen05", "mma.sync"])
 def forward_path(request, monkeypatch):
     """The forward has two kernels: the tcgen05 / TMA / TMEM one (csrc/affine_tc.cu; C <= 40, 16-byte aligned rows, at
-    least 64 rows and 32 k) and the mma.sync one that takes everything else.  NASR_AFFINE_TC=0 forces the second."""
+    least 128 rows and 32 k) and the mma.sync one that takes everything else.  NASR_AFFINE_TC=0 forces the second."""
     monkeypatch.setenv("NASR_AFFINE_TC", "1" if request.param == "tcgen05" else "0")
     return request.param
 
@@ -36,7 +36,7 @@ def forward_path(request, monkeypatch):
 @pytest.mark.parametrize("rows,K,C", [(1, 1, 1), (16, 8, 8), (37, 500, 38), (1000, 500, 38), (4099, 500, 38),
                                         (130, 13, 5), (257, 100, 41), (300, 700, 38), (64, 1500, 7),
                                         (500, 500, 1024), (333, 250, 129), (64, 32, 40), (129, 257, 1),
-                                        (20000, 500, 38)])
+                                        (20000, 500, 38), (128, 32, 40), (256, 260, 3), (300, 96, 40)])
 def test_forward_matches_oracle(rows, K, C, forward_path):
     from neuralasr_b200.networks import common
     H, W, b = _case(rows * 7 + K + C, rows, K, C)
