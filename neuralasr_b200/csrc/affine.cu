@@ -718,6 +718,10 @@ bool eligible(const float* H, long long rows, int K, long long ldh, int C);
 int forward(const float* H, long long rows, int K, long long ldh, const float* W, const float* bias, int C,
             float* logits, long long ldl, cudaStream_t stream);
 }  // namespace affine_tc
+namespace affine_tc_dh {   // csrc/affine_tc_dh.cu: dH = dL.W^T on tcgen05 (both parts of dL in TMEM)
+bool eligible(const float* dL, long long rows, int K, long long ldd, int C);
+int dh(const float* dL, long long rows, int K, const float* W, int C, float* dH, long long ldh, cudaStream_t stream);
+}  // namespace affine_tc_dh
 }  // namespace nasr
 
 using namespace nasr;
@@ -757,6 +761,11 @@ int nasr_affine_backward_f32(const float* H, long long rows, int K, long long ld
   NASR_CHECK_ARG(rows == 0 || dlogits, "nasr_affine_backward_f32: dlogits is NULL");
   NASR_CHECK_ARG(!dH || W, "nasr_affine_backward_f32: dH needs W");
   NASR_CHECK_ARG(!(dW || db) || rows == 0 || H, "nasr_affine_backward_f32: dW / db need H");
+  if (dH && use_tcgen05() && affine_tc_dh::eligible(dlogits, rows, K, ldd, C)) {
+    const int rc = affine_tc_dh::dh(dlogits, rows, K, W, C, dH, lddh, static_cast<cudaStream_t>(stream));
+    if (rc != NASR_OK) return rc;
+    dH = nullptr;   // done; what is left (dW, db) goes to the mma.sync kernels
+  }
   return affine::backward(H, rows, K, ldh, W, C, dlogits, ldd, dH, lddh, dW, db, workspace, workspace_bytes,
                           static_cast<cudaStream_t>(stream));
 }

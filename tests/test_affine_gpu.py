@@ -27,8 +27,9 @@ def _case(seed, rows, K, C, scale=1.0):
 
 @pytest.fixture(params=["tcgen05", "mma.sync"])
 def forward_path(request, monkeypatch):
-    """The forward has two kernels: the tcgen05 / TMA / TMEM one (csrc/affine_tc.cu; C <= 40, 16-byte aligned rows, at
-    least 128 rows and 32 k) and the mma.sync one that takes everything else.  NASR_AFFINE_TC=0 forces the second."""
+    """The forward and dH have two kernels each: the tcgen05 / TMEM ones (csrc/affine_tc.cu: C <= 40, 16-byte aligned
+    rows, at least 128 rows and 32 k; csrc/affine_tc_dh.cu: C <= 40, contiguous dlogits, at least 128 rows) and the
+    mma.sync ones that take everything else.  NASR_AFFINE_TC=0 forces the second."""
     monkeypatch.setenv("NASR_AFFINE_TC", "1" if request.param == "tcgen05" else "0")
     return request.param
 
@@ -49,8 +50,8 @@ def test_forward_matches_oracle(rows, K, C, forward_path):
 
 @pytest.mark.parametrize("rows,K,C", [(1, 1, 1), (16, 8, 8), (37, 500, 38), (1000, 500, 38), (4099, 500, 38),
                                         (130, 13, 5), (257, 100, 41), (300, 700, 38), (500, 500, 1024),
-                                        (20000, 500, 38)])
-def test_backward_matches_oracle(rows, K, C):
+                                        (20000, 500, 38), (128, 8, 40), (999, 129, 7), (640, 256, 38)])
+def test_backward_matches_oracle(rows, K, C, forward_path):
     from neuralasr_b200.networks import common
     H, W, _ = _case(rows * 3 + K + C, rows, K, C)
     rng = np.random.default_rng(5)
