@@ -550,12 +550,15 @@ def projection_record(common, dev, rows, K, C):
         return a.elapsed_time(e) / n
 
     rec = {"rows": rows, "K": K, "C": C,
-           "arithmetic": "3xTF32, float32 accumulation: forward on tcgen05 (TMA + TMEM, csrc/affine_tc.cu), backward on mma.sync",
+           "arithmetic": "3xTF32, float32 accumulation: forward and dH on tcgen05 (csrc/affine_tc.cu, affine_tc_dh.cu), dW + db on mma.sync",
+           "dH_pitch": "backward_dH writes rows pitched at a multiple of 32 floats (128-byte lines); _dense_pitch is a contiguous [rows, K]",
            "l2": "two rotating H sets (%.0f MB) > 126 MB L2" % (2 * 4 * rows * K / 1e6)}
     for name, fn, nbytes in (
             ("forward", lambda i: common.affine_logits(Hs[i & 1], W, b, out=out), 4 * (rows * K + rows * C + K * C)),
             ("forward_mma_sync", lambda i: _forward_mma_sync(common, Hs[i & 1], W, b, out), 4 * (rows * K + rows * C + K * C)),
             ("backward_dH", lambda i: common.affine_backward(Hs[i & 1], W, dL, True, False, False), 4 * (rows * K + rows * C)),
+            ("backward_dH_dense_pitch", lambda i: common.affine_backward(Hs[i & 1], W, dL, True, False, False, dense_dH=True),
+             4 * (rows * K + rows * C)),
             ("backward_dW_db", lambda i: common.affine_backward(Hs[i & 1], W, dL, False, True, True), 4 * (rows * K + rows * C))):
         ms = timed(fn)
         rec[name] = {"ms": ms, "algorithmic_gbs": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak}

@@ -22,7 +22,8 @@
 namespace nasr {
 namespace affine_tc_dh {
 
-constexpr int kThreads = 512;
+constexpr int kThreads = 800;            // 8 converter warps (two sets), the issuing warp, 16 epilogue warps
+constexpr int kMmaWarp = 8, kEpiWarp0 = 9;
 constexpr int kBM = 128;                 // rows per tile
 constexpr int kBN = 128;                 // output columns per product
 constexpr int kCP = 40;                  // contraction, padded (5 steps of 8)
@@ -32,11 +33,11 @@ constexpr int kDCol0 = 2 * kACols;       // accumulators behind the two A slots
 constexpr int kTmemCols = 512;
 constexpr int kSBO = (kCP / 4) * 128;    // bytes between 8-row groups of the W layout
 constexpr int kWBytes = (kPassN / 8) * kSBO;          // one part (hi or lo) of a pass: 40960
-constexpr int kStageWords = 33;          // padded row of the epilogue's 32-column block
+constexpr int kStageWords = 36;          // padded row of the epilogue's 32-column block: 16-byte pieces, conflict-free
 constexpr int kOffWhi = 0;
 constexpr int kOffWlo = kOffWhi + kWBytes;
 constexpr int kOffStage = kOffWlo + kWBytes;                       // [group][128][33] floats
-constexpr int kOffBar = kOffStage + 2 * kBM * kStageWords * 4;
+constexpr int kOffBar = kOffStage + 4 * kBM * kStageWords * 4;
 constexpr int kOffTmemPtr = kOffBar + 8 * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16 + 128;
 
@@ -96,6 +97,8 @@ __device__ __forceinline__ uint32_t tf32_round(float x) { return (__float_as_uin
                "r"(v[o + 7])                                                                                          \
                : "memory")
 
+__device__ long long g_prof_dh[8];   // tuning: CTA 0 cycles: converter load / wait, mma wait a / wait d, epilogue wait / work
+
 struct Params {
   const float* dL;   // [rows, C] contiguous
   const float* W;    // [K, C]
@@ -103,6 +106,7 @@ struct Params {
   long long rows, ldh;
   int K, C;
   int vec16;         // rows of dH 16-byte aligned
+  int debug;         // 8: role cycle counters of CTA 0
 };
 
 __global__ void __launch_bounds__(kThreads, 1) affine_dh_tc_kernel(const Params p) {
@@ -121,11 +125,11 @@ __global__ void __launch_bounds__(kThreads, 1) affine_dh_tc_kernel(const Params 
       mbar_init(a_full(s), 128);
       mbar_init(a_empty(s), 1);
       mbar_init(d_full(s), 1);
-      mbar_init(d_empty(s), 128);
+      mbar_init(d_empty(s), 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
                  "r"((uint32_t)kTmemCols)
                  : "memory");
@@ -134,6 +138,8 @@ __global__ void __launch_bounds__(kThreads, 1) affine_dh_tc_kernel(const Params 
 
   const long long ntiles = (p.rows + kBM - 1) / kBM;
   int acnt = 0, dcnt = 0;          // A slots / accumulators used so far (every role counts the same sequence)
+  long long c0 = 0, c1 = 0;
+  const long long kstart = clock64();
   uint32_t tmem_base = 0;
 
   for (int k0 = 0; k0 < p.K; k0 += kPassN) {
@@ -170,11 +176,15 @@ __global__ void __launch_bounds__(kThreads, 1) affine_dh_tc_kernel(const Params 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     tmem_base = *tmem_ptr_smem;
 
-    if (warp < 4) {
-      // ===== converters: one row of dL per thread -> hi | lo in TMEM =====
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int as = acnt & 1;
-        const long long r = tile * kBM + 32 * warp + lane;
+    if (warp < 8) {
+      // ===== converters: one row of dL per thread -> hi | lo in TMEM.  Two sets of four warps take alternate tiles
+      //       (set = A slot): under the epilogue's store traffic a tile's loads take longer than a tile lasts =====
+      const int cs = warp >> 2, sub = warp & 3;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, acnt++) {
+        if ((acnt & 1) != cs) continue;
+        const int as = cs;
+        const long long r = tile * kBM + 32 * sub + lane;
+        const long long t0 = clock64();
         float x[kCP];
 #pragma unroll
         for (int c = 0; c < kCP; c++) x[c] = 0.f;
@@ -195,9 +205,12 @@ __global__ void __launch_bounds__(kThreads, 1) affine_dh_tc_kernel(const Params 
               if (c < p.C) x[c] = __ldg(row + c);
           }
         }
+        const long long t1 = clock64();
         mbar_wait(a_empty(as), ((acnt >> 1) & 1) ^ 1);
+        c0 += t1 - t0;
+        c1 += clock64() - t1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)(as * kACols);
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * sub) << 16) + (uint32_t)(as * kACols);
 #pragma unroll
         for (int o = 0; o < kCP; o += 8) {
           uint32_t hi[8], lo[8];
@@ -212,19 +225,18 @@ __global__ void __launch_bounds__(kThreads, 1) affine_dh_tc_kernel(const Params 
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(a_full(as));
-        acnt++;
       }
-    } else if (warp == 4) {
+    } else if (warp == kMmaWarp) {
       // ===== MMA issuer =====
       const uint32_t whi = sbase + kOffWhi, wlo = sbase + kOffWlo;
       for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int as = acnt & 1;
-        mbar_wait(a_full(as), (acnt >> 1) & 1);
+        { const long long t0 = clock64(); mbar_wait(a_full(as), (acnt >> 1) & 1); c0 += clock64() - t0; }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_hi = tmem_base + (uint32_t)(as * kACols), a_lo = a_hi + kCP;
         for (int j = 0; j < nnt; j++) {
           const int ds = dcnt & 1;
-          mbar_wait(d_empty(ds), ((dcnt >> 1) & 1) ^ 1);
+          { const long long t0 = clock64(); mbar_wait(d_empty(ds), ((dcnt >> 1) & 1) ^ 1); c1 += clock64() - t0; }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t d_tmem = tmem_base + (uint32_t)(kDCol0 + ds * kBN);
           const uint32_t boff = (uint32_t)(j * (kBN / 8) * kSBO);
@@ -244,21 +256,25 @@ __global__ void __launch_bounds__(kThreads, 1) affine_dh_tc_kernel(const Params 
         }
         acnt++;
       }
-    } else if (warp >= 8) {
-      // ===== epilogue: group g owns accumulator g =====
-      const int g = (warp - 8) >> 2, q = warp & 3;
-      const int et = tid - 256 - 128 * g;          // 0..127 inside the group
-      float* stage = reinterpret_cast<float*>(smem + kOffStage) + g * kBM * kStageWords;
+    } else {
+      // ===== epilogue: four groups of four warps; accumulator g is read by the groups (g, half 0) and (g, half 1),
+      //       64 columns each, so that one group's loads and staging run under another's stores =====
+      const int gi = (warp - kEpiWarp0) >> 2, g = gi >> 1, hf = gi & 1, q = warp & 3;
+      const int et = tid - 32 * kEpiWarp0 - 128 * gi;   // 0..127 inside the group
+      float* stage = reinterpret_cast<float*>(smem + kOffStage) + gi * kBM * kStageWords;
       for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int j = 0; j < nnt; j++, dcnt++) {
           if ((dcnt & 1) != g) continue;
+          const long long t0 = clock64();
           mbar_wait(d_full(g), (dcnt >> 1) & 1);
+          const long long t1 = clock64();
+          c0 += t1 - t0;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(kDCol0 + g * kBN);
+          const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(kDCol0 + g * kBN + 64 * hf);
           const long long r0 = tile * kBM;
-          const int kc0 = k0 + j * kBN;                   // first output column of this accumulator
+          const int kc0 = k0 + j * kBN + 64 * hf;         // first output column of this group's half
 #pragma unroll 1
-          for (int ch = 0; ch < kBN / 32; ch++) {
+          for (int ch = 0; ch < 2; ch++) {
             uint32_t v[32];
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -269,47 +285,54 @@ __global__ void __launch_bounds__(kThreads, 1) affine_dh_tc_kernel(const Params 
                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                 : "r"(taddr + (uint32_t)(32 * ch)));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (ch == kBN / 32 - 1) {
+            if (ch == 1) {
               asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-              mbar_arrive(d_empty(g));       // the accumulator is read: the next product may overwrite it
+              mbar_arrive(d_empty(g));       // this half of the accumulator is read
             }
-            // rows of 32 columns into the padded block (conflict-free: row stride 33 words), then 128-byte row pieces out
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-            float* srow = stage + (32 * q + lane) * kStageWords;
+            // rows of 32 columns into the padded block (row stride 36 words: 16-byte pieces of eight rows hit every
+            // bank once), then 128-byte row pieces out
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + gi) : "memory");
+            float4* srow = reinterpret_cast<float4*>(stage + (32 * q + lane) * kStageWords);
 #pragma unroll
-            for (int c = 0; c < 32; c++) srow[c] = __uint_as_float(v[c]);
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+            for (int c = 0; c < 8; c++)
+              srow[c] = make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
+                                    __uint_as_float(v[4 * c + 3]));
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + gi) : "memory");
             const int col = (et & 7) * 4;
             const int kc = kc0 + 32 * ch + col;
 #pragma unroll
             for (int it = 0; it < kBM / 16; it++) {
               const int rr = (et >> 3) + 16 * it;
               const long long r = r0 + rr;
-              if (r < p.rows && kc < p.K) {
-                const float* sp = stage + rr * kStageWords + col;
+              if (r < p.rows && kc < p.K && !(p.debug & 4)) {
+                const float4 o = *reinterpret_cast<const float4*>(stage + rr * kStageWords + col);
                 float* dst = p.dH + r * p.ldh + kc;
                 if (p.vec16 && kc + 3 < p.K) {
-                  *reinterpret_cast<float4*>(dst) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                  *reinterpret_cast<float4*>(dst) = o;
                 } else {
-                  dst[0] = sp[0];
-                  if (kc + 1 < p.K) dst[1] = sp[1];
-                  if (kc + 2 < p.K) dst[2] = sp[2];
-                  if (kc + 3 < p.K) dst[3] = sp[3];
+                  dst[0] = o.x;
+                  if (kc + 1 < p.K) dst[1] = o.y;
+                  if (kc + 2 < p.K) dst[2] = o.z;
+                  if (kc + 3 < p.K) dst[3] = o.w;
                 }
               }
             }
           }
+          c1 += clock64() - t1;
         }
       }
-    } else {
-      // warps 5-7 have no role; they still count the sequence so that the pass barrier finds them
     }
-    // roles that skipped the loops keep their counters in step (only the roles above use them)
   }
 
+  if ((p.debug & 8) && blockIdx.x == 0) {
+    if (tid == 0) { g_prof_dh[0] = c0; g_prof_dh[1] = clock64() - kstart; }
+    if (tid == 32 * kMmaWarp) { g_prof_dh[2] = c0; g_prof_dh[3] = c1; }
+    if (tid == 32 * kEpiWarp0) { g_prof_dh[4] = c0; g_prof_dh[5] = c1; }
+    if (tid == 32 * kEpiWarp0 + 256) { g_prof_dh[6] = c0; g_prof_dh[7] = c1; }
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
   }
@@ -333,10 +356,21 @@ int dh(const float* dL, long long rows, int K, const float* W, int C, float* dH,
   p.K = K;
   p.C = C;
   p.vec16 = (((uintptr_t)dH & 15) == 0) && (ldh % 4 == 0);
+  {
+    const char* e = getenv("NASR_AFFINE_TC_DEBUG");
+    p.debug = e ? atoi(e) : 0;
+  }
   NASR_CUDA((ensure_max_dynamic_smem<affine_dh_tc_kernel>(kSmemBytes)));
   affine_dh_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
   count_launch();
   NASR_CUDA(cudaGetLastError());
+  if (p.debug & 8) {
+    long long h[8];
+    cudaStreamSynchronize(stream);
+    cudaMemcpyFromSymbol(h, g_prof_dh, sizeof(h));
+    fprintf(stderr, "affine_dh_tc (CTA 0, cycles): converter load %lld, CTA lifetime so far %lld | mma wait A %lld wait D %lld | epilogue (0,0) wait %lld work %lld | "
+            "epilogue (1,0) wait %lld work %lld\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+  }
   return NASR_OK;
 }
 

@@ -350,16 +350,22 @@ def affine_logits(H, W, b=None, out=None):
     return out
 
 
-def affine_backward(H, W, dlogits, want_dH=True, want_dW=True, want_db=True):
+def affine_backward(H, W, dlogits, want_dH=True, want_dW=True, want_db=True, dense_dH=False):
     """The three gradients of :func:`affine_logits`: ``(dH [rows, K], dW [K, C], db [C])`` (``None`` where not
-    wanted)."""
+    wanted).  ``dH`` is a ``[:, :K]`` view of rows pitched at a multiple of 32 floats unless ``dense_dH`` asks for a
+    contiguous tensor (what autograd hands on without a copy)."""
     H = _rows2d(H, "H")
     dlogits = _rows2d(dlogits, "dlogits", "C")
     W = W.contiguous()
     rows, K = H.shape
     C = W.shape[1]
     dev = H.device
-    dH = torch.empty((rows, K), dtype=torch.float32, device=dev) if want_dH else None
+    # dH rows start on 128-byte lines: the row pitch is K rounded up to 32 floats and the result is the [:, :K] view.
+    # (Measured at 256000 x 500: 0.137 ms at a pitch of 512, 0.166 at 504, 0.208 for the dense pitch of 500 floats,
+    # whose odd rows start 16 bytes into a sector so that every 128-byte piece the kernel stores ends in two
+    # half-written sectors.)
+    pitch = K if dense_dH else (K + 31) // 32 * 32
+    dH = torch.empty((rows, pitch), dtype=torch.float32, device=dev)[:, :K] if want_dH else None
     dW = torch.empty((K, C), dtype=torch.float32, device=dev) if want_dW else None
     db = torch.empty((C,), dtype=torch.float32, device=dev) if want_db else None
     lib = _lib.load()
@@ -372,7 +378,8 @@ def affine_backward(H, W, dlogits, want_dH=True, want_dW=True, want_db=True):
         ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.nasr_affine_backward_f32(_ptr(H), rows, K, H.stride(0) if rows > 1 else K, _ptr(W), C,
-                                                _ptr(dlogits), dlogits.stride(0) if rows > 1 else C, _ptr(dH), K,
+                                                _ptr(dlogits), dlogits.stride(0) if rows > 1 else C, _ptr(dH),
+                                                dH.stride(0) if (want_dH and rows > 1) else K,
                                                 _ptr(dW), _ptr(db), _ptr(ws), nbytes, _stream_ptr(dev)),
                    "nasr_affine_backward_f32")
     return dH, dW, db
@@ -389,7 +396,7 @@ class _AffineFn(torch.autograd.Function):
     def backward(ctx, g):
         H, W = ctx.saved_tensors
         dH, dW, db = affine_backward(H, W, g, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
-                                     ctx.has_bias and ctx.needs_input_grad[2])
+                                     ctx.has_bias and ctx.needs_input_grad[2], dense_dH=True)
         return dH, dW, db
 
 

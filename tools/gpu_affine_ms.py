@@ -7,7 +7,8 @@ sys.path.insert(0, ".")
 import bench
 from neuralasr_b200.networks import common
 w = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cfg3"]
-rows, K, C = w["B"] * w["T"], 500, w["C"]
+import os
+rows, K, C = w["B"] * w["T"], int(os.environ.get("AFFINE_K", "500")), w["C"]
 peak = bench.hbm_peak()[0] if hasattr(bench, "hbm_peak") else 6543.4
 torch.backends.cuda.matmul.allow_tf32 = False
 g = torch.Generator(device="cuda").manual_seed(0)
