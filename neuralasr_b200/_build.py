@@ -10,7 +10,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libnasr_ctc.so")
-SOURCES = ["nasr_api.cu", "ctc_loss.cu", "ctc_fast.cu", "ctc_narrow.cu", "ctc_decode.cu", "ctc_beam.cu", "affine.cu", "affine_tc.cu", "affine_tc_dh.cu"]
+SOURCES = ["nasr_api.cu", "ctc_loss.cu", "ctc_fast.cu", "ctc_narrow.cu", "ctc_decode.cu", "ctc_beam.cu", "affine.cu", "affine_tc.cu", "affine_tc_dh.cu", "affine_tc_dw.cu"]
 HEADERS = [os.path.join(CSRC, "nasr_common.cuh"), os.path.join(ROOT, "include", "nasr_ctc.h")]
 
 NVCC_FLAGS = [

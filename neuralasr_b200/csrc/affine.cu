@@ -24,6 +24,7 @@
 //                        rows through a three-stage cp.async ring (32 rows of H and dL per stage), every warp owns 32
 //                        of the 512 k of a block as accumulators; per-CTA partials go to the workspace and
 //                        affine_reduce_kernel adds them in a fixed order (deterministic, no atomics).
+#include <algorithm>
 #include <cstdlib>
 
 #include "nasr_common.cuh"
@@ -722,6 +723,12 @@ namespace affine_tc_dh {   // csrc/affine_tc_dh.cu: dH = dL.W^T on tcgen05 (both
 bool eligible(const float* dL, long long rows, int K, long long ldd, int C);
 int dh(const float* dL, long long rows, int K, const float* W, int C, float* dH, long long ldh, cudaStream_t stream);
 }  // namespace affine_tc_dh
+namespace affine_tc_dw {   // csrc/affine_tc_dw.cu: dW = H^T.dL and db on tcgen05 (H turned on its way into TMEM)
+bool eligible(const float* H, long long rows, int K, long long ldh, long long ldd, int C);
+size_t workspace_bytes(long long rows, int sms);
+int dw(const float* H, long long rows, int K, long long ldh, const float* dL, int C, float* dW, float* db, void* ws,
+       size_t ws_bytes, cudaStream_t stream);
+}  // namespace affine_tc_dw
 }  // namespace nasr
 
 using namespace nasr;
@@ -737,7 +744,12 @@ int nasr_affine_workspace_bytes(long long rows, int K, int C, size_t* out_bytes)
   NASR_CHECK_ARG(out_bytes, "nasr_affine_workspace_bytes: out_bytes is NULL");
   NASR_CHECK_ARG(rows >= 0 && K >= 1 && C >= 1, "nasr_affine_workspace_bytes: bad shape rows=%lld K=%d C=%d", rows, K,
                  C);
-  return affine::workspace_bytes(rows, K, C, out_bytes);
+  const int rc = affine::workspace_bytes(rows, K, C, out_bytes);
+  if (rc != NASR_OK) return rc;
+  int sms = 0;
+  NASR_CUDA(device_sm_count(&sms));
+  *out_bytes = std::max(*out_bytes, affine_tc_dw::workspace_bytes(rows, sms));   // whichever kernel takes the call
+  return NASR_OK;
 }
 
 int nasr_affine_logits_f32(const float* H, long long rows, int K, long long ldh, const float* W, const float* bias,
@@ -764,7 +776,14 @@ int nasr_affine_backward_f32(const float* H, long long rows, int K, long long ld
   if (dH && use_tcgen05() && affine_tc_dh::eligible(dlogits, rows, K, ldd, C)) {
     const int rc = affine_tc_dh::dh(dlogits, rows, K, W, C, dH, lddh, static_cast<cudaStream_t>(stream));
     if (rc != NASR_OK) return rc;
-    dH = nullptr;   // done; what is left (dW, db) goes to the mma.sync kernels
+    dH = nullptr;   // done
+  }
+  if ((dW || db) && use_tcgen05() && affine_tc_dw::eligible(H, rows, K, ldh, ldd, C)) {
+    const int rc = affine_tc_dw::dw(H, rows, K, ldh, dlogits, C, dW, db, workspace, workspace_bytes,
+                                    static_cast<cudaStream_t>(stream));
+    if (rc != NASR_OK) return rc;
+    dW = nullptr;
+    db = nullptr;
   }
   return affine::backward(H, rows, K, ldh, W, C, dlogits, ldd, dH, lddh, dW, db, workspace, workspace_bytes,
                           static_cast<cudaStream_t>(stream));
