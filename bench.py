@@ -525,6 +525,18 @@ def _forward_mma_sync(common, H, W, b, out):
             os.environ["NASR_AFFINE_TC"] = prev
 
 
+def _backward_mma_sync(common, H, W, dL):
+    prev = os.environ.get("NASR_AFFINE_TC")
+    os.environ["NASR_AFFINE_TC"] = "0"
+    try:
+        return common.affine_backward(H, W, dL, True, True, True, dense_dH=True)
+    finally:
+        if prev is None:
+            del os.environ["NASR_AFFINE_TC"]
+        else:
+            os.environ["NASR_AFFINE_TC"] = prev
+
+
 def projection_record(common, dev, rows, K, C):
     """ms per call and fraction of the HBM peak of nasr_affine_logits_f32 / nasr_affine_backward_f32."""
     import torch
@@ -550,7 +562,7 @@ def projection_record(common, dev, rows, K, C):
         return a.elapsed_time(e) / n
 
     rec = {"rows": rows, "K": K, "C": C,
-           "arithmetic": "3xTF32, float32 accumulation: forward and dH on tcgen05 (csrc/affine_tc.cu, affine_tc_dh.cu), dW + db on mma.sync",
+           "arithmetic": "3xTF32, float32 accumulation, all on tcgen05 (csrc/affine_tc.cu, affine_tc_dh.cu, affine_tc_dw.cu); *_mma_sync = the mma.sync kernels that take shapes outside their rules",
            "dH_pitch": "backward_dH writes rows pitched at a multiple of 32 floats (128-byte lines); _dense_pitch is a contiguous [rows, K]",
            "l2": "two rotating H sets (%.0f MB) > 126 MB L2" % (2 * 4 * rows * K / 1e6)}
     for name, fn, nbytes in (
@@ -559,7 +571,8 @@ def projection_record(common, dev, rows, K, C):
             ("backward_dH", lambda i: common.affine_backward(Hs[i & 1], W, dL, True, False, False), 4 * (rows * K + rows * C)),
             ("backward_dH_dense_pitch", lambda i: common.affine_backward(Hs[i & 1], W, dL, True, False, False, dense_dH=True),
              4 * (rows * K + rows * C)),
-            ("backward_dW_db", lambda i: common.affine_backward(Hs[i & 1], W, dL, False, True, True), 4 * (rows * K + rows * C))):
+            ("backward_dW_db", lambda i: common.affine_backward(Hs[i & 1], W, dL, False, True, True), 4 * (rows * K + rows * C)),
+            ("backward_mma_sync", lambda i: _backward_mma_sync(common, Hs[i & 1], W, dL), 4 * 2 * (rows * K + rows * C))):
         ms = timed(fn)
         rec[name] = {"ms": ms, "algorithmic_gbs": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak}
     prev = torch.backends.cuda.matmul.allow_tf32
