@@ -5,12 +5,15 @@
 // semantics per SURVEY.md Appendix A.2 / A.3.  Integer results are bit-exact by construction
 // (first-index argmax on the raw logits, exact integer DP); neg_sum_logits is accumulated in frame
 // order in fp32 like TF's scalar loop, so it is bit-exact too.
+#include <type_traits>
+
 #include "nasr_common.cuh"
 
 namespace nasr {
 namespace {
 
 constexpr int kDecodeThreads = 256;
+constexpr int kLerPending = -2147483647 - 1;  // dist[b] of an utterance edit_distance_lanes_kernel left to the warp kernel
 constexpr int kDecodeChunk = 2048;  // frames staged per pass (argmax ids + max logits in shared memory)
 
 // One CTA per utterance.  Phase 1: one warp per frame finds the first-index argmax of the raw logits
@@ -212,10 +215,12 @@ __global__ void __launch_bounds__(32)
 edit_distance_kernel(const HypT* __restrict__ hyp, long hyp_stride, const int32_t* __restrict__ hyp_len,
                      const int32_t* __restrict__ hyp_offsets,
                      const int32_t* __restrict__ truth_values, const int32_t* __restrict__ truth_offsets,
-                     int max_truth_len, int max_hyp_len, int table_words, int normalize,
+                     int max_truth_len, int max_hyp_len, int table_words, int normalize, int only_pending,
                      int32_t* __restrict__ dist, float* __restrict__ ler) {
   extern __shared__ int sm[];
   const int b = blockIdx.x, lane = threadIdx.x;
+  // second launch behind edit_distance_lanes_kernel: only the utterances that kernel declined
+  if (only_pending && dist[b] != kLerPending) return;
   const int t0 = truth_offsets[b];
   const int m = truth_offsets[b + 1] - t0;  // truth length
   int n;                                     // hyp length
@@ -380,6 +385,273 @@ edit_distance_kernel(const HypT* __restrict__ hyp, long hyp_stride, const int32_
   }
 }
 
+// ---- narrow symbol ranges, truths of up to 224 symbols: one LANE per (utterance, direction) -----------------------
+// The warp-per-utterance kernel above spends its time on the chain of |hyp|/2 dependent steps, each a shuffle plus ~15
+// dependent integer operations in a warp of which W lanes work (~300 cycles per step).  Here a lane keeps the WHOLE
+// column of vertical deltas of its direction as one WT-word integer in registers (Myers' algorithm as published, the
+// only thing that crosses words being the carry of one addition -- an add.cc / addc.cc chain -- and two funnel shifts),
+// so a step needs no shuffle, and 32 lanes = 16 utterances x (forward half of the hypothesis | reversed second half
+// against the reversed truth) fill the warp.  Match masks: table[symbol][word][lane] in shared memory, so that lane l
+// reads bank l whatever its symbol.  No running score: D[n][m] = n + popc(Pv) - popc(Mv) of the last column, and the two
+// halves are joined as in the kernel above (min over j of D_fwd[j] + D_bwd[m-j], spelt out by the vertical deltas).
+// Declines (dist = kLerPending, picked up by the kernel above in the same stream) when the CTA's symbol values or
+// hypothesis lengths do not fit shared memory (96 KB: the table, and every hypothesis as 16-bit table rows).  Exact
+// integers.  Eight warps share the set-up (each of its loops waits on loads), warp 0 runs the recursion.
+// Measured at cfg3 (B=256, hypotheses of ~950 symbols, truths of 100-200): 0.063 ms per call including the second
+// launch, against 0.077 ms for the warp-per-utterance kernel alone; 87 instructions per symbol, of which ~72 on the
+// integer pipe (LOP3 / SHF / IADD3, 16 lanes a cycle: two cycles each) -- the loop is bound by that pipe
+// (profiles/r2_ler_lanes.md has the steps that did not pay: per-lane global loads of the symbols, cp.async rings).
+template <int WT>
+__device__ __forceinline__ void add_words(const unsigned (&a)[WT], const unsigned (&b)[WT], unsigned (&s)[WT]) {
+  static_assert(WT == 2 || WT == 4 || WT == 7, "word counts of the lanes kernel");
+  if constexpr (WT == 2) {
+    asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, %5;"
+        : "=r"(s[0]), "=r"(s[1])
+        : "r"(a[0]), "r"(a[1]), "r"(b[0]), "r"(b[1]));
+  } else if constexpr (WT == 4) {
+    asm("add.cc.u32 %0, %4, %8;\n\taddc.cc.u32 %1, %5, %9;\n\taddc.cc.u32 %2, %6, %10;\n\taddc.u32 %3, %7, %11;"
+        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]));
+  } else {
+    asm("add.cc.u32 %0, %7, %14;\n\taddc.cc.u32 %1, %8, %15;\n\taddc.cc.u32 %2, %9, %16;\n\t"
+        "addc.cc.u32 %3, %10, %17;\n\taddc.cc.u32 %4, %11, %18;\n\taddc.cc.u32 %5, %12, %19;\n\t"
+        "addc.u32 %6, %13, %20;"
+        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(b[0]), "r"(b[1]),
+          "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]));
+  }
+}
+
+constexpr int kLanesWarps = 8;  // warps that set a CTA up (tables, symbol rows); warp 0 alone runs the recursion
+template <typename HypT, int WT, int UPW>
+__global__ void __launch_bounds__(32 * kLanesWarps)
+edit_distance_lanes_kernel(const HypT* __restrict__ hyp, long hyp_stride, const int32_t* __restrict__ hyp_len,
+                           const int32_t* __restrict__ hyp_offsets, const int32_t* __restrict__ truth_values,
+                           const int32_t* __restrict__ truth_offsets, int max_truth_len, int max_hyp_len, int B,
+                           int table_words, int normalize, int32_t* __restrict__ dist, float* __restrict__ ler) {
+  extern __shared__ unsigned smu[];
+  __shared__ int s_range[2];
+  // every warp holds the same per-lane view (lane -> utterance, direction); the eight warps share the set-up work --
+  // each of its loops waits on loads, and one warp alone has too few in flight -- then warp 0 runs the recursion
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, dir = lane & 1;
+  const int b = blockIdx.x * UPW + (lane >> 1);
+  const bool have = lane < 2 * UPW && b < B;
+  int t0 = 0, m = 0, n = 0;
+  const HypT* h = hyp;
+  if (have) {
+    t0 = truth_offsets[b];
+    m = truth_offsets[b + 1] - t0;
+    if (hyp_offsets) {
+      h = hyp + hyp_offsets[b];
+      n = hyp_offsets[b + 1] - hyp_offsets[b];
+    } else {
+      h = hyp + (size_t)b * hyp_stride;
+      n = hyp_len[b];
+    }
+  }
+  const bool refuse = have && (m > max_truth_len || n > max_hyp_len);  // as the kernel above: d = -1
+  const bool work = have && !refuse && n > 0 && m > 0;
+  // symbol range of the CTA's truths (each utterance once: its even lane; utterances dealt to the warps)
+  if (threadIdx.x == 0) {
+    s_range[0] = -1;
+    s_range[1] = 0;
+  }
+  __syncthreads();
+  int mx = -1, mn = 0;
+  for (int t = 2 * wid; t < 2 * UPW; t += 2 * kLanesWarps) {
+    const int mt = __shfl_sync(0xffffffffu, work ? m : 0, t), tt0 = __shfl_sync(0xffffffffu, t0, t);
+    for (int j = lane; j < mt; j += 32) {
+      const int v = truth_values[tt0 + j];
+      mx = max(mx, v);
+      mn = min(mn, v);
+    }
+  }
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  if (lane == 0) {
+    atomicMax(&s_range[0], mx);
+    atomicMin(&s_range[1], mn);
+  }
+  __syncthreads();
+  mx = s_range[0];
+  mn = s_range[1];
+  const int nsym = mx + 1;                       // rows 0..nsym-1 of the table, row nsym stays zero (any other symbol)
+  const int tab_words = (nsym + 1) * WT * 32;
+  int pw = (max_hyp_len + 1) / 2 + 1;            // words per utterance row of 16-bit symbol rows; odd: the forward
+  pw |= 1;                                       // lanes of a warp, all at the same position, hit different banks
+  const long long need = (long long)tab_words + 2 * WT * 32 + (long long)UPW * pw + 1;  // table, last columns, rows
+  const bool decline = mn < 0 || nsym >= 65535 || need > table_words;
+  int d = refuse ? -1 : n + m;                   // n == 0 or m == 0: n + m
+  if (decline) {
+    if (work) d = kLerPending;
+  } else if (nsym > 0) {
+    {
+      uint4* z = reinterpret_cast<uint4*>(smu);
+      for (int i = threadIdx.x; i < tab_words / 4; i += 32 * kLanesWarps) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    {
+      // every lane fills its own table (its truth, reversed for the backward direction), an eighth of it in each
+      // warp: bank = lane, and the reductions return nothing, so they queue behind each other without waiting
+      const int mw = work ? m : 0;
+      const int per = (mw + kLanesWarps - 1) / kLanesWarps;
+      const int j1 = min(mw, (wid + 1) * per);
+#pragma unroll 4
+      for (int j = wid * per; j < j1; j++) {
+        const int v = truth_values[t0 + j];
+        const int pos = dir ? mw - 1 - j : j;
+        atomicOr(&smu[(v * WT + (pos >> 5)) * 32 + lane], 1u << (pos & 31));
+      }
+    }
+    // Hypotheses: the warps turn each utterance's symbols into 16-bit table rows in shared memory with coalesced
+    // loads, eight in flight per lane (row nsym = the zero row for a symbol no truth of the CTA holds); a lane of the
+    // recursion then needs one 2-byte read per symbol.  (A lane fetching its own row from global memory touches 32
+    // lines per instruction, and the loop is bound by the integer pipe -- 16 lanes a cycle: every instruction beside
+    // the bit-vector arithmetic counts.)
+    unsigned short* soff = reinterpret_cast<unsigned short*>(smu + tab_words + 2 * WT * 32);
+    const int P16 = 2 * pw;
+    for (int u = wid; u < UPW; u += kLanesWarps) {
+      const int nu = __shfl_sync(0xffffffffu, work ? n : 0, 2 * u);
+      const unsigned long long hp = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)h, 2 * u);
+      const HypT* hu = reinterpret_cast<const HypT*>((uintptr_t)hp);
+      for (int i = lane; i < nu; i += 32 * 8) {
+        long long c[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) c[q] = i + 32 * q < nu ? (long long)__ldg(hu + i + 32 * q) : 0ll;
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+          if (i + 32 * q < nu)
+            soff[u * P16 + i + 32 * q] =
+                (unsigned short)((unsigned long long)c[q] < (unsigned long long)nsym ? (int)c[q] : nsym);
+      }
+    }
+    if (threadIdx.x == 0) soff[UPW * P16] = (unsigned short)nsym;   // what a lane without work reads
+    __syncthreads();
+    if (wid != 0) return;
+    const int n1 = n - n / 2;                    // symbols of the forward half (>= the backward half's)
+    const int nd = work ? (dir ? n - n1 : n1) : 0;
+    const int steps = __reduce_max_sync(0xffffffffu, nd);
+    const int smin = min(steps, __reduce_min_sync(0xffffffffu, work ? nd : 0x7fffffff));  // every lane with work has this many
+    const unsigned* tl = smu + lane;
+    unsigned Pv[WT], Mv[WT];
+#pragma unroll
+    for (int k = 0; k < WT; k++) {
+      Pv[k] = 0xffffffffu;
+      Mv[k] = 0u;
+    }
+    // symbol i of this lane's direction: forward h[i], backward h[n-1-i]; a lane without work reads the zero row
+    const unsigned short* sp = soff + (work ? (lane >> 1) * P16 + (dir ? n - 1 : 0) : UPW * P16);
+    const int sgn = work ? (dir ? -1 : 1) : 0;
+    const int ilast = nd > 0 ? nd - 1 : 0;
+    auto row_of = [&](int i) -> int { return (int)sp[sgn * min(i, ilast)] * (WT * 32); };
+    constexpr int U = 4;
+    int off[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) off[u] = row_of(u);
+    unsigned EqN[WT];
+#pragma unroll
+    for (int k = 0; k < WT; k++) EqN[k] = tl[off[0] + k * 32];
+    // one round = U symbols; TAIL: lanes past their last symbol keep their column (a select per word), before that
+    // (every lane with work has symbols left; lanes without work compute on the zero row and nobody reads them) none
+    auto round = [&](auto tail, int i0) {
+      constexpr bool TAIL = decltype(tail)::value;
+      int offn[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) offn[u] = row_of(i0 + U + u);
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        unsigned Eq[WT], Xv[WT], A[WT], Sm[WT], Ph[WT], Mh[WT];
+        const int onext = u + 1 < U ? off[u + 1 < U ? u + 1 : 0] : offn[0];
+#pragma unroll
+        for (int k = 0; k < WT; k++) {
+          Eq[k] = EqN[k];
+          EqN[k] = tl[onext + k * 32];
+        }
+#pragma unroll
+        for (int k = 0; k < WT; k++) {
+          Xv[k] = Eq[k] | Mv[k];
+          A[k] = Eq[k] & Pv[k];
+        }
+        add_words<WT>(A, Pv, Sm);
+#pragma unroll
+        for (int k = 0; k < WT; k++) {
+          const unsigned Xh = (Sm[k] ^ Pv[k]) | Eq[k];
+          Ph[k] = Mv[k] | ~(Xh | Pv[k]);
+          Mh[k] = Pv[k] & Xh;
+        }
+        const bool active = !TAIL || i0 + u < nd;
+#pragma unroll
+        for (int k = WT - 1; k >= 0; k--) {
+          // one row down: the horizontal delta entering row 0 is +1 (D[i][0] = i)
+          const unsigned ph = __funnelshift_l(k ? Ph[k - 1] : 0x80000000u, Ph[k], 1);
+          const unsigned mh = __funnelshift_l(k ? Mh[k - 1] : 0u, Mh[k], 1);
+          if (active) {
+            Pv[k] = mh | ~(Xv[k] | ph);
+            Mv[k] = ph & Xv[k];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) off[u] = offn[u];
+    };
+    int i0 = 0;
+    for (; i0 + U <= smin; i0 += U) round(std::false_type{}, i0);
+    for (; i0 < steps; i0 += U) round(std::true_type{}, i0);
+    // last columns to shared memory; join: S[j] = D_fwd[j] + D_bwd[m-j], S[0] = n1 + D_bwd[m],
+    // S[j+1] - S[j] = (Pf_j - Mf_j) - (Pb_(m-1-j) - Mb_(m-1-j))
+    unsigned* xv = smu + tab_words;              // [2 * WT][32]
+#pragma unroll
+    for (int k = 0; k < WT; k++) {
+      xv[k * 32 + lane] = Pv[k];
+      xv[(WT + k) * 32 + lane] = Mv[k];
+    }
+    __syncwarp();
+    if (work) {
+      const int lf = lane & ~1, lb = lane | 1;
+      int S = n;
+      for (int k = 0; k * 32 < m; k++) {
+        const int nb = min(32, m - 32 * k);
+        const unsigned valid = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
+        S += __popc(xv[k * 32 + lb] & valid) - __popc(xv[(WT + k) * 32 + lb] & valid);
+      }
+      int best = S;
+      int wq = (m - 1) >> 5, bq = (m - 1) & 31;
+      unsigned Pb = xv[wq * 32 + lb], Mb = xv[(WT + wq) * 32 + lb], Pf = 0u, Mf = 0u;
+      for (int j = 0; j < m; j++) {
+        if ((j & 31) == 0) {
+          Pf = xv[(j >> 5) * 32 + lf];
+          Mf = xv[(WT + (j >> 5)) * 32 + lf];
+        }
+        S += (int)(Pf & 1u) - (int)(Mf & 1u) - (int)((Pb >> bq) & 1u) + (int)((Mb >> bq) & 1u);
+        Pf >>= 1;
+        Mf >>= 1;
+        best = min(best, S);
+        if (--bq < 0 && wq > 0) {
+          bq = 31;
+          --wq;
+          Pb = xv[wq * 32 + lb];
+          Mb = xv[(WT + wq) * 32 + lb];
+        }
+      }
+      d = best;
+    }
+  }
+  if (wid == 0 && have && dir == 0) {
+    dist[b] = d;
+    if (d != kLerPending) {
+      float r;
+      if (!normalize) {
+        r = (float)d;
+      } else if (m == 0) {
+        r = d ? INFINITY : 0.f;
+      } else {
+        r = (float)d / (float)m;
+      }
+      ler[b] = r;
+    }
+  }
+}
+
 __global__ void hyp_to_sparse_kernel(const int64_t* __restrict__ hyp, long hyp_stride,
                                      const int32_t* __restrict__ offs, int B,
                                      int64_t* __restrict__ indices, int64_t* __restrict__ values) {
@@ -453,10 +725,41 @@ int launch_edit_distance(const HypT* hyp, long hyp_stride, const int32_t* hyp_le
               max_hyp_len);
     return NASR_ERR_UNSUPPORTED;
   }
+  // truths of up to 224 symbols: a lane per (utterance, direction) first; what it declines (symbol values that do not
+  // fit its table) is left marked in dist[] for the warp-per-utterance kernel.  NASR_LER_LANES=0 switches it off
+  // (read at every call, so tests and tools can compare the two).
+  int only_pending = 0;
+  const int WT = max_truth_len <= 64 ? 2 : (max_truth_len <= 128 ? 4 : (max_truth_len <= 224 ? 7 : 0));
+  const char* e = getenv("NASR_LER_LANES");
+  if (WT && !(e && e[0] == '0')) {
+    constexpr int kLanesSmem = 96 * 1024;
+    // 16 utterances per CTA (half-filled warps, 8 per CTA, were measured: no faster -- the integer pipe takes two
+    // cycles for a warp instruction whatever the number of active lanes)
+    const int grid = (B + 15) / 16;
+#define NASR_LANES(W_)                                                                                          \
+  do {                                                                                                          \
+    NASR_CUDA((ensure_max_dynamic_smem<edit_distance_lanes_kernel<HypT, W_, 16>>(kLanesSmem)));                 \
+    edit_distance_lanes_kernel<HypT, W_, 16><<<grid, 32 * kLanesWarps, kLanesSmem, stream>>>(                   \
+        hyp, hyp_stride, hyp_len, hyp_offsets, truth_values, truth_offsets, max_truth_len, max_hyp_len, B,      \
+        kLanesSmem / 4, normalize, dist, ler);                                                                  \
+  } while (0)
+    if (WT == 2) {
+      NASR_LANES(2);
+    } else if (WT == 4) {
+      NASR_LANES(4);
+    } else {
+      NASR_LANES(7);
+    }
+#undef NASR_LANES
+    count_launch();
+    NASR_CUDA(cudaGetLastError());
+    only_pending = 1;
+  }
   NASR_CUDA((ensure_max_dynamic_smem<edit_distance_kernel<HypT>>(200 * 1024)));
   edit_distance_kernel<HypT><<<B, 32, smem, stream>>>(hyp, hyp_stride, hyp_len, hyp_offsets,
                                                      truth_values, truth_offsets, max_truth_len,
-                                                     max_hyp_len, (int)(table / 4), normalize, dist, ler);
+                                                     max_hyp_len, (int)(table / 4), normalize, only_pending, dist,
+                                                     ler);
   count_launch();
   NASR_CUDA(cudaGetLastError());
   return NASR_OK;

@@ -375,6 +375,52 @@ def test_edit_distance_paths_match_oracle(common):
     assert d.cpu().numpy().tolist() == want
 
 
+def test_edit_distance_lane_per_direction_kernel_matches_oracle(common, monkeypatch):
+    """Truths of up to 224 symbols run in edit_distance_lanes_kernel (a lane per utterance and direction, 16
+    utterances per warp, 2 / 4 / 7 words per lane); batches whose symbol values do not fit its table are handed to
+    the warp-per-utterance kernel in the same call.  Both against the oracle, and against each other."""
+    from neuralasr_b200.networks.common import edit_distance
+    rng = np.random.default_rng(77)
+    batches = []
+    for mmax, hi in [(64, 5), (33, 37), (128, 37), (100, 3), (224, 37), (200, 60), (224, 2), (161, 500)]:
+        for B in (1, 5, 16, 17, 40):
+            truths, hyps = [], []
+            for b in range(B):
+                m = int(rng.integers(0, mmax + 1)) if b else mmax
+                n = int(rng.choice([0, 1, 2, 3, 31, 32, 33, int(rng.integers(0, 700))]))
+                if b == 2:
+                    m = 0
+                t = rng.integers(0, hi, m)
+                if b % 3 == 0 and m and n:      # a hypothesis close to the truth: small distances
+                    h = np.repeat(t, rng.integers(1, 3, m))[:n]
+                    h = np.where(rng.random(h.size) < 0.1, rng.integers(0, hi + 1, h.size), h)
+                else:
+                    h = rng.integers(0, hi + 2, n)
+                truths.append(t.tolist())
+                hyps.append(h.tolist())
+            batches.append((truths, hyps))
+    # symbol values outside the table (declined as a whole warp), negative and huge hypothesis symbols (no match)
+    t = rng.integers(0, 30, 150).tolist()
+    batches.append(([t, [100000, 1, 2], t], [t[10:140], [1, 2, 100000], t[::-1]]))
+    batches.append(([t, t[:5]], [[-3] + t[:100] + [2 ** 31 - 1] + t[100:], [4, 4, -1]]))
+
+    def csr(rows):
+        return (np.asarray([v for r in rows for v in r], np.int64),
+                np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int32))
+
+    for truths, hyps in batches:
+        want, want_ler = c_oracle.edit_distance(*csr(hyps), *csr(truths))
+        hyp_sp, truth_sp = _sparse_from_rows(hyps, np.int64), _sparse_from_rows(truths, np.int32)
+        d, ler = edit_distance(hyp_sp, truth_sp)
+        assert d.cpu().numpy().tolist() == want.tolist()
+        assert np.array_equal(ler.cpu().numpy(), want_ler)
+        monkeypatch.setenv("NASR_LER_LANES", "0")
+        d0, ler0 = edit_distance(hyp_sp, truth_sp)
+        monkeypatch.delenv("NASR_LER_LANES")
+        assert d0.cpu().numpy().tolist() == want.tolist()
+        assert np.array_equal(ler0.cpu().numpy(), want_ler)
+
+
 def test_batch_major_logits_without_transpose(common):
     """A [B,T,C] model output goes in as a strided [T,B,C] view (plain and DLPack entries): same loss, the
     gradient comes back in the batch-major layout, decode agrees."""
