@@ -169,6 +169,29 @@ def test_decode_and_ler_match_oracle(common, kw):
     assert np.array_equal(mean2.distances.cpu().numpy(), want_d)
 
 
+def test_greedy_decode_layouts_and_ties(common):
+    """Narrow rows against the oracle: even and odd row lengths, a batch-major view, rows offset by one float (no
+    8-byte alignment), more frames than one staging pass, quantised logits (ties: first index wins)."""
+    rng = np.random.default_rng(9)
+    for C, T, B, layout in [(38, 333, 21, 0), (37, 100, 5, 0), (64, 47, 33, 1), (2, 40, 3, 0), (41, 130, 17, 2),
+                            (38, 2100, 2, 1), (1, 20, 4, 0)]:
+        x = np.round(rng.normal(size=(T, B, C)) * 2).astype(np.float32) / 2
+        seq = rng.integers(0, T + 1, B).astype(np.int32)
+        seq[0] = T
+        xt = torch.from_numpy(x).cuda()
+        if layout == 1:
+            xt = xt.transpose(0, 1).contiguous().transpose(0, 1)
+        elif layout == 2:
+            big = torch.zeros((T, B, C + 3), device="cuda")
+            big[:, :, 1:C + 1] = xt
+            xt = big[:, :, 1:C + 1]
+        hv, ho, want_nsl = c_oracle.greedy_decode(x, seq)
+        dec, nsl = common.decoding(xt, seq)
+        assert np.array_equal(dec.values.cpu().numpy(), hv), (C, T, B, layout)
+        assert np.array_equal(dec.hyp_len.cpu().numpy(), np.diff(ho))
+        assert np.array_equal(nsl.cpu().numpy()[:, 0], want_nsl)
+
+
 def test_decode_known_cases(common):
     a, b, blank = 0, 1, 3
     x = np.full((6, 2, 4), -1.0, np.float32)
