@@ -409,7 +409,7 @@ edit_distance_kernel(const HypT* __restrict__ hyp, long hyp_stride, const int32_
 // Declines (dist = kLerPending, picked up by the kernel above in the same stream) when the CTA's symbol values or
 // hypothesis lengths do not fit shared memory (96 KB: the table, and every hypothesis as 16-bit table rows).  Exact
 // integers.  Eight warps share the set-up (each of its loops waits on loads), warp 0 runs the recursion.
-// Measured at cfg3 (B=256, hypotheses of ~950 symbols, truths of 100-200): 0.063 ms per call including the second
+// Measured at cfg3 (B=256, hypotheses of ~950 symbols, truths of 100-200): 0.058 ms per call including the second
 // launch, against 0.077 ms for the warp-per-utterance kernel alone; 87 instructions per symbol, of which ~72 on the
 // integer pipe (LOP3 / SHF / IADD3, 16 lanes a cycle: two cycles each) -- the loop is bound by that pipe
 // (profiles/r2_ler_lanes.md has the steps that did not pay: per-lane global loads of the symbols, cp.async rings).
@@ -618,18 +618,28 @@ edit_distance_lanes_kernel(const HypT* __restrict__ hyp, long hyp_stride, const 
       xv[(WT + k) * 32 + lane] = Mv[k];
     }
     __syncwarp();
+    // S[j] = n + (sum of the forward deltas below j) + (sum of the backward deltas below m - j); the two lanes of an
+    // utterance take the halves of the range of j (split at a multiple of 32), each from its own S[j0]
+    int best = 0x7fffffff;
     if (work) {
       const int lf = lane & ~1, lb = lane | 1;
-      int S = n;
-      for (int k = 0; k * 32 < m; k++) {
-        const int nb = min(32, m - 32 * k);
-        const unsigned valid = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
-        S += __popc(xv[k * 32 + lb] & valid) - __popc(xv[(WT + k) * 32 + lb] & valid);
-      }
-      int best = S;
-      int wq = (m - 1) >> 5, bq = (m - 1) & 31;
+      auto below = [&](int l, int x) -> int {      // sum of lane l's vertical deltas at positions < x
+        int acc = 0;
+#pragma unroll
+        for (int k = 0; k < WT; k++) {
+          const int nb = min(32, max(0, x - 32 * k));
+          const unsigned valid = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
+          acc += __popc(xv[k * 32 + l] & valid) - __popc(xv[(WT + k) * 32 + l] & valid);
+        }
+        return acc;
+      };
+      const int mh = (m / 2) & ~31;
+      const int j0 = dir ? mh : 0, j1 = dir ? m : mh;
+      int S = n + below(lf, j0) + below(lb, m - j0);
+      best = S;
+      int wq = (m - 1 - j0) >> 5, bq = (m - 1 - j0) & 31;
       unsigned Pb = xv[wq * 32 + lb], Mb = xv[(WT + wq) * 32 + lb], Pf = 0u, Mf = 0u;
-      for (int j = 0; j < m; j++) {
+      for (int j = j0; j < j1; j++) {
         if ((j & 31) == 0) {
           Pf = xv[(j >> 5) * 32 + lf];
           Mf = xv[(WT + (j >> 5)) * 32 + lf];
@@ -645,6 +655,9 @@ edit_distance_lanes_kernel(const HypT* __restrict__ hyp, long hyp_stride, const 
           Mb = xv[(WT + wq) * 32 + lb];
         }
       }
+    }
+    best = min(best, __shfl_xor_sync(0xffffffffu, best, 1));
+    if (work) {
       d = best;
     }
   }
